@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- RGBA-VAE encode + sample + decode throughput (MPix/s), BASELINE.json's metric.
+
+Workload (N=1): config c2 -- RGBA-VAE reconstruction, bf16, 1024x1024, batch 8 on one B200 with the
+alpha-over-white PSNR validation, Qwen-Image VAE architecture, random-init weights, synthetic RGBA.
+One "step" = one pass of the hot path over one batch: [0,1] RGBA -> encode -> posterior sample with
+supplied noise -> decode -> clamp -> composite-over-white PSNR + alpha MAE.  Under torchrun (N>1) every
+rank runs the same per-rank batch (weak scaling, no data-path collective).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--arch qwen|flux]
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle (the restatement of the
+reference's diffusers path; diffusers itself is not installable offline) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "rgba_vae_encode_decode_mpix_per_s"
+UNIT = "MPix/s"
+TFLOP_PER_IMAGE_1024 = {"qwen": 7.5657, "flux": 15.3596}  # SURVEY.md 8(d) / BASELINE.md section 2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--arch", default="qwen", choices=["qwen", "flux"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a):
+    return {"workload": f"c2: RGBA-VAE reconstruction bf16 {a.size}x{a.size} batch {a.batch} per GPU + "
+                        "alpha-over-white PSNR validation (encode -> sample -> decode)",
+            "arch": a.arch, "batch_per_gpu": a.batch, "height": a.size, "width": a.size,
+            "weights": "random-init seed 0", "parallelism": f"batch-sharded x{a.gpus}, no collective"}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_forward_factory(arch, size):
+    import torch
+
+    from oracle import vae_oracle as O
+
+    vae = O.build_oracle(arch, seed=0)
+    x = O.synthetic_rgba(1, size, size, seed=1, structured=True)
+    noise = torch.randn(1, 16, size // 8, size // 8, generator=torch.Generator().manual_seed(2))
+
+    def step():
+        with torch.no_grad():
+            recon, post, _ = O.rgba_vae_forward(vae, x, noise)
+            return float(O.validation_metrics(recon, x, backgrounds=(1.0,))[1.0][0])
+
+    return step
+
+
+def cpu_pick_size(arch, want):
+    """Largest sample (<= want) whose estimated step time stays under ~15 s on this host."""
+    import torch
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    probe = cpu_forward_factory(arch, 256)
+    probe()
+    t0 = time.perf_counter()
+    probe()
+    t256 = time.perf_counter() - t0
+    size = 256
+    while size * 2 <= want and t256 * ((size * 2) / 256) ** 2 * 1.3 < 10.0:
+        size *= 2
+    return size, t256
+
+
+def run_cpu_baseline(arch, want_size, steps, warmup):
+    import torch
+
+    size, _ = cpu_pick_size(arch, want_size)
+    step = cpu_forward_factory(arch, size)
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    mpix = size * size * steps / 1e6 / total
+    return {"value": mpix, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"oracle fp32 (torch CPU), 1x4x{size}x{size} per step, {steps} steps after {warmup} warm-up, "
+                      f"{total:.1f} s; {os.cpu_count()} logical cores"}, total / steps * 1e3
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, ms = run_cpu_baseline(a.arch, a.size, a.steps, a.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(a), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, f"/tmp/rv_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            p = [s.strip() for s in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"tflops": float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1590.0))),
+                "tflops_burst": float(p.get("bf16_tflops", 1590.0)), "hbm_gbs": float(p["hbm_gbs"]), "source": "measured"}
+    return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+def gpu_arm(a):
+    import torch
+    import torch.distributed as dist
+
+    import ragb_vae_b200 as R
+    from ragb_vae_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, S = a.batch, a.size
+
+    torch.manual_seed(0)
+    vae = R.RgbaAutoencoder(a.arch)  # torch default init == the oracle's
+    model = R.RgbaVAE(vae.to(dev, torch.bfloat16))
+
+    g = torch.Generator().manual_seed(1 + rank)
+    x_host = torch.rand(B, 4, S, S, generator=g).to(torch.bfloat16).pin_memory()
+    n_host = torch.randn(B, 16, S // 8, S // 8, generator=torch.Generator().manual_seed(2 + rank)).to(torch.bfloat16).pin_memory()
+    out_host = torch.empty(B, 2, dtype=torch.float32).pin_memory()
+    x_dev, n_dev = x_host.to(dev), n_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(x, noise):
+        recon, _ = model(x, noise=noise)
+        return ops.composite_psnr(recon, x, [(1.0, 1.0, 1.0)])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            flush.zero_()
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def resident():
+        step(x_dev, n_dev)
+
+    def end_to_end():
+        xd = x_host.to(dev, non_blocking=True)
+        nd = n_host.to(dev, non_blocking=True)
+        out_host.copy_(step(xd, nd), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.launch_count()
+    ms_total = timed(resident, a.steps)
+    launches = ops.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    end_to_end()
+    ms_e2e = timed(end_to_end, a.steps)
+    psnr_white = float(out_host[:, 0].mean())
+
+    # roofline of the dominant kernel (the tcgen05 implicit-GEMM conv): CUDA events on the launching
+    # stream around every launch of one more step (rv_prof_*), algorithmic FLOPs / summed duration
+    prof = None
+    if rank == 0:
+        torch.cuda.synchronize()
+        ops.prof_begin()
+        resident()
+        prof = ops.prof_end()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    mpix_step = world * B * S * S / 1e6
+    value = mpix_step * a.steps / (ms_total / 1e3)
+    e2e_value = mpix_step * a.steps / (ms_e2e / 1e3)
+    conv = prof["conv_tc"]
+    ach = conv["work"] / 1e12 / (conv["ms"] / 1e3) if conv["ms"] > 0 else 0.0
+    roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv / GEMM, all launches of one step)",
+            "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
+            "peak_source": f"{pk['source']} bf16_tflops_sustained", "launches_per_step": conv["launches"],
+            "ms_per_step": conv["ms"], "algorithmic_tflop_per_step": conv["work"] / 1e12}
+    kernels = {}
+    for name, rec in prof.items():
+        if rec["launches"] == 0:
+            continue
+        entry = {"ms": round(rec["ms"], 4), "launches": rec["launches"]}
+        if name in ("conv_tc", "conv_direct", "attention"):
+            entry["tflops"] = rec["work"] / 1e12 / (rec["ms"] / 1e3) if rec["ms"] > 0 else None
+        else:
+            gbs = rec["work"] / 1e9 / (rec["ms"] / 1e3) if rec["ms"] > 0 else None
+            entry["gbs"] = gbs
+            entry["hbm_frac"] = gbs / pk["hbm_gbs"] if gbs else None
+        kernels[name] = entry
+    whole = world * B * TFLOP_PER_IMAGE_1024[a.arch] * (S * S / 1048576.0) * a.steps / (ms_total / 1e3) if S == 1024 else None
+
+    cpu_b = None
+    if world == 1 and not a.no_cpu_baseline:
+        cpu_b, _ = run_cpu_baseline(a.arch, S, 2, 1)
+
+    cfg = workload_config(a)
+    cfg["l2"] = "256 MiB buffer rewritten between timed iterations (plus multi-GB activation working set per step)"
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": cfg,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
+                    "h2d_bytes_per_step": (x_host.numel() + n_host.numel()) * 2 * world,
+                    "d2h_bytes_per_step": out_host.numel() * 4 * world},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels,
+            "whole_step_tflops": whole, "cpu_baseline": cpu_b, "psnr_white_db": psnr_white}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+        return
+    from ragb_vae_b200 import build as B
+
+    if not os.path.exists(B.LIB):  # normally prebuilt in-tree (it travels with the snapshot)
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+            B.build()
+        else:
+            while not os.path.exists(B.LIB):
+                time.sleep(1.0)
+            time.sleep(2.0)
+    gpu_arm(a)
+
+
+if __name__ == "__main__":
+    main()

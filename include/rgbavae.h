@@ -1,0 +1,151 @@
+/*
+ * rgbavae.h -- C ABI of librgbavae.so, the sm_100a kernel library behind the RGBA-VAE hot path.
+ *
+ * The reference (jaejung-dev/ragb-vae) has no FFI of its own: its boundary is the diffusers
+ * ModelMixin duck-type (vae.encode(x).latent_dist / vae.decode(z).sample).  The
+ * Python package ragb_vae_b200 implements that surface and is the ONLY caller of this library
+ * (through ctypes).  Each entry point below names the reference call site whose arithmetic it
+ * replaces.  All pointers are DEVICE pointers unless stated otherwise; `stream` is a
+ * cudaStream_t passed as void*.  Every function returns 0 on success and a non-zero code on
+ * failure (1 = CUDA error, 2 = bad argument), in which case rv_last_error() returns a
+ * thread-local message.  There is no CPU path.
+ *
+ * dtype codes: RV_F32 = 0, RV_BF16 = 1.
+ * Activations inside the network are NHWC ("pixels x channels"); image tensors at the
+ * boundary are NCHW exactly as the reference passes them.
+ */
+#ifndef RGBAVAE_H_
+#define RGBAVAE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RV_F32 0
+#define RV_BF16 1
+
+#define RV_ABI_VERSION 2
+#define RV_PROF_CATEGORIES 9
+
+int rv_abi_version(void);
+const char* rv_last_error(void);
+/* Binds the driver entry point used for TMA descriptors and raises the dynamic shared memory
+ * limit of the tcgen05 kernel on the current device.  Call once per process and device. */
+int rv_init(void);
+/* Number of kernels this library has launched since load (all threads, all streams). */
+int64_t rv_launch_count(void);
+/* Per-category device timing with CUDA events recorded on the launching stream, for the
+ * roofline figures in bench.py.  Categories: 0 tcgen05 conv/GEMM, 1 direct conv, 2 norm+SiLU,
+ * 3 softmax, 4 layout, 5 reparam, 6 recon loss, 7 composite+PSNR, 8 fused attention.
+ * rv_prof_end synchronises the device and fills ms[c] (summed kernel time), launches[c] and
+ * work[c] (algorithmic FLOPs for 0/1/8, algorithmic bytes for the others). */
+int rv_prof_begin(void);
+int rv_prof_end(double* ms, int64_t* launches, double* work);
+
+/* ---- convolution / GEMM ---------------------------------------------------------------- */
+/* One descriptor drives both convolution paths.  It covers every conv of diffusers'
+ * Encoder/Decoder (vae.encode / vae.decode: src/models/rgba_vae.py:277,279;
+ * src/training/rgba_vae_stage.py:449,452; src/models/flux_kontext_textalpha.py:331,497):
+ * 3x3 pad 1, 3x3 stride 2 with (0,1,0,1) padding, nearest-x2 upsample + 3x3, and 1x1.
+ * The same kernels run plain GEMMs (attention projections, QK^T, PV) as 1x1 convs:
+ * y[pixel][co] = alpha * sum_k x[pixel][k] * w[co][k] + bias. */
+typedef struct rv_conv_desc {
+  int32_t n, h, w;           /* input batch and spatial size (of the tensor actually stored) */
+  int32_t cin, cout;         /* logical channels */
+  int32_t ksize;             /* 1 or 3 */
+  int32_t stride;            /* 1 or 2 */
+  int32_t pad_lo;            /* zero padding on top/left (1 for 3x3 s1, 0 for the s2 downsampler) */
+  int32_t upsample;          /* 1: nearest x2 upsample of the input fused in front of the conv */
+  int32_t oh, ow;            /* output spatial size */
+  int32_t x_dtype, y_dtype;  /* RV_F32 / RV_BF16 */
+  int32_t x_nchw, y_nchw;    /* 1: tensor is NCHW, else NHWC (x_nchw: direct path only) */
+  int32_t x_cstride;         /* NHWC pixel pitch of x in elements (>= cin) */
+  int32_t y_cstride;         /* NHWC pixel pitch of y / residual in elements (>= cout) */
+  int32_t bias_mode;         /* 0 none, 1 per output channel, 2 per output pixel (GEMM row) */
+  float   in_scale, in_shift;   /* x*in_scale+in_shift applied when loading (direct path only) */
+  float   out_scale, out_shift; /* y*out_scale+out_shift applied after bias and residual */
+  int32_t clamp;             /* 1: clamp to [clamp_lo, clamp_hi] after scale/shift */
+  float   clamp_lo, clamp_hi;
+  float   alpha;             /* accumulator scale (1/sqrt(d) for QK^T), applied before bias */
+} rv_conv_desc;
+
+/* CUDA-core implicit GEMM, fp32 accumulate, any shape / layout / dtype.  Weights are fp32
+ * [cout][ksize*ksize][cin] (K-major).  Used for the 4-channel edge layers, for the fp32
+ * parity mode (config c1) and as the in-library cross-check of the tensor-core path.
+ * residual (optional) has the layout and dtype of y. */
+int rv_conv2d_direct(const rv_conv_desc* d, const void* x, const float* w, const float* bias,
+                     const void* residual, void* y, void* stream);
+
+/* tcgen05/TMEM implicit GEMM fed by TMA (bf16 in, fp32 accumulate).  x is NHWC bf16 with
+ * x_cstride % 8 == 0 and cin % 16 == 0.  Weights are bf16 K-major rows of pitch `w_ld`
+ * elements: [cout][taps][cin] for ksize 1/3 (rv_pack_conv_weights), or for upsample=1 the
+ * four folded 2x2 phase kernels [cout][4 phases][4 taps][cin].  residual (optional) is NHWC
+ * bf16 with pitch y_cstride. */
+int rv_conv2d_tc(const rv_conv_desc* d, const void* x, const void* w_packed, int64_t w_ld,
+                 const float* bias, const void* residual, void* y, void* stream);
+
+/* Packs fp32 weights [cout][cin][ksize][ksize] (PyTorch layout; for the Qwen causal-conv3d
+ * the caller passes the live temporal slice w[:, :, kt-1]) into the bf16 K-major matrix
+ * rv_conv2d_tc reads: [cout][taps][cin].  With upsample=1 the 3x3 kernel is folded into four
+ * 2x2 phase kernels, [cout][16][cin].  The row length is returned through *w_ld. */
+int rv_pack_conv_weights(const float* w, int cout, int cin, int ksize, int upsample,
+                         void* out_bf16, int64_t* w_ld, void* stream);
+/* Same source layout -> fp32 [cout][taps][cin] for rv_conv2d_direct. */
+int rv_pack_conv_weights_direct(const float* w, int cout, int cin, int ksize, float* out, void* stream);
+
+/* ---- normalisation + SiLU (residual blocks: diffusers ResnetBlock2D / QwenImageResidualBlock) */
+/* y = act(x / max(||x||_2 over C, 1e-12) * sqrt(C) * gamma), per pixel (QwenImageRMS_norm);
+ * x, y NHWC dense [pixels][c]; act = SiLU when apply_silu. */
+int rv_rmsnorm_silu(const void* x, const float* gamma, void* y, int64_t pixels, int c, int dtype,
+                    int apply_silu, void* stream);
+/* GroupNorm(groups, eps): rv_groupnorm_stats accumulates sum and sum of squares per (sample,
+ * group) into stats [n][groups][2] fp64 (it zeroes the buffer first); rv_groupnorm_silu applies
+ * y = act((x-mean)*rstd*gamma+beta).  x, y NHWC dense [n][hw][c]. */
+int rv_groupnorm_stats(const void* x, double* stats, int n, int64_t hw, int c, int groups, int dtype,
+                       void* stream);
+int rv_groupnorm_silu(const void* x, const double* stats, const float* gamma, const float* beta, void* y,
+                      int n, int64_t hw, int c, int groups, float eps, int dtype, int apply_silu,
+                      void* stream);
+
+/* ---- mid-block attention (single head, d = C) ------------------------------------------- */
+/* Row softmax of fp32 scores [rows][cols] (already scaled) into probabilities of `dtype`. */
+int rv_softmax_rows(const float* s, void* p, int64_t rows, int64_t cols, int64_t ld_s, int64_t ld_p,
+                    int dtype, void* stream);
+
+/* ---- layout plumbing at the NCHW boundary ----------------------------------------------- */
+/* y[n][hw][c_pad] = x[n][c][hw]*scale+shift (extra channels zero). */
+int rv_nchw_to_nhwc(const void* x, void* y, int n, int c, int64_t hw, int c_pad, int x_dtype,
+                    int y_dtype, float scale, float shift, void* stream);
+int rv_nhwc_to_nchw(const void* x, void* y, int n, int c, int64_t hw, int x_cstride, int x_dtype,
+                    int y_dtype, void* stream);
+
+/* ---- posterior (diffusers DiagonalGaussianDistribution; src/models/rgba_vae.py:278) ------ */
+/* moments NCHW [n][2*zc][hw]; noise / z NCHW [n][zc][hw].
+ * z = (mean + exp(0.5*clamp(logvar,-30,20))*noise - z_shift) * z_scale   (z_shift 0 / z_scale 1
+ * for the plain sample(); the Flux latent normalisation of flux_kontext_textalpha.py:330-332
+ * otherwise).  kl_out (optional, [n] fp32) = 0.5*sum(mean^2 + var - 1 - logvar). */
+int rv_reparam(const void* moments, const void* noise, void* z, float* kl_out, int n, int zc,
+               int64_t hw, int dtype, float z_shift, float z_scale, void* stream);
+
+/* ---- losses and validation metrics -------------------------------------------------------*/
+/* AlphaVaeLoss.reconstruction_loss (src/models/losses.py:67-83): pred/target NCHW [n][4][hw] in
+ * [-1,1].  per_sample[n] receives the per-sample SUM of the loss map (naive: over 4 channels).
+ * partial is a scratch buffer of n*rv_reduce_blocks(hw) doubles. */
+int rv_recon_loss(const void* pred, const void* target, const float* eb_host, const float* eb2_host,
+                  int naive_mse, float* per_sample, double* partial, int n, int64_t hw, int dtype,
+                  void* stream);
+/* composite_over_background + compute_psnr + alpha MAE (src/models/rgba_vae.py:75-84,
+ * src/training/rgba_vae_stage.py:712-715,742-753) in one pass over recon/target NCHW [n][4][hw]
+ * in [0,1].  bgs_host: nbg (<= 4) RGB triples (HOST pointer).  out: [n][nbg+1] fp32: PSNR per
+ * background, then alpha MAE.  partial: n*rv_reduce_blocks(hw)*(nbg+1) doubles. */
+int rv_composite_psnr(const void* recon, const void* target, const float* bgs_host, int nbg,
+                      float* out, double* partial, int n, int64_t hw, int dtype, void* stream);
+/* number of partial blocks per sample the two reductions above use for `hw` pixels */
+int rv_reduce_blocks(int64_t hw);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGBAVAE_H_ */

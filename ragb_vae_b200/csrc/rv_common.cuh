@@ -1,0 +1,120 @@
+// Shared helpers for librgbavae: error reporting, dtype load/store, warp reductions, launch
+// accounting.  Internal to the library; the public surface is include/rgbavae.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/rgbavae.h"
+
+namespace rv {
+
+void set_error(const char* fmt, ...);
+
+// Launch accounting (rv_launch_count) and the optional per-category CUDA-event profiler
+// (rv_prof_begin / rv_prof_end).  Every kernel launch site wraps itself in a LaunchScope.
+enum Category {
+  CAT_CONV_TC = 0,
+  CAT_CONV_DIRECT = 1,
+  CAT_NORM = 2,
+  CAT_SOFTMAX = 3,
+  CAT_LAYOUT = 4,
+  CAT_REPARAM = 5,
+  CAT_LOSS = 6,
+  CAT_PSNR = 7,
+  CAT_ATTN = 8,
+  CAT_COUNT = RV_PROF_CATEGORIES
+};
+
+struct LaunchScope {
+  int cat;
+  cudaStream_t stream;
+  cudaEvent_t e0, e1;
+  bool timed;
+  LaunchScope(int cat, cudaStream_t stream, double work = 0.0);
+  ~LaunchScope();
+};
+
+#define RV_CHECK_ARG(cond, ...)          \
+  do {                                   \
+    if (!(cond)) {                       \
+      rv::set_error(__VA_ARGS__);        \
+      return 2;                          \
+    }                                    \
+  } while (0)
+
+#define RV_CUDA(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      rv::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      return 1;                                                                         \
+    }                                                                                   \
+  } while (0)
+
+#define RV_LAUNCH_CHECK()                                                               \
+  do {                                                                                  \
+    cudaError_t e_ = cudaGetLastError();                                                \
+    if (e_ != cudaSuccess) {                                                            \
+      rv::set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_));  \
+      return 1;                                                                         \
+    }                                                                                   \
+  } while (0)
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename T> __device__ __forceinline__ void stf(T* p, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// 16-byte vector of T: 4 floats or 8 bf16.
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  float4 v;
+  __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
+  __device__ __forceinline__ float get(int i) const { return reinterpret_cast<const float*>(&v)[i]; }
+  __device__ __forceinline__ void set(int i, float x) { reinterpret_cast<float*>(&v)[i] = x; }
+  __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  uint4 v;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = v; }
+  __device__ __forceinline__ float get(int i) const {
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(&v)[i]);
+  }
+  __device__ __forceinline__ void set(int i, float x) {
+    reinterpret_cast<__nv_bfloat16*>(&v)[i] = __float2bfloat16_rn(x);
+  }
+  __device__ __forceinline__ void zero() { v = make_uint4(0u, 0u, 0u, 0u); }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// x * sigmoid(x).  expf (not __expf) keeps the fp32 parity mode within 1e-6 of torch's silu.
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+
+int num_sms();
+
+}  // namespace rv

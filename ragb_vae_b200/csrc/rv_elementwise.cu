@@ -1,0 +1,488 @@
+// HBM-bound kernels of the RGBA-VAE path: norm+SiLU (RMS and GroupNorm), softmax rows,
+// NCHW<->NHWC plumbing and the posterior reparameterisation.  All are streaming kernels:
+// 16-byte vector accesses, fp32 arithmetic, warp-shuffle + shared-memory reductions.
+#include "rv_common.cuh"
+
+namespace rv {
+
+static inline int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
+
+// ------------------------------------------------------------------------------------------
+// RMS norm + SiLU (QwenImageRMS_norm + F.silu inside QwenImageResidualBlock / norm_out;
+// oracle/vae_oracle.py QwenRMSNorm).  One 16-byte chunk per thread, flat over [pixels][c];
+// the per-pixel sum of squares is reduced over the chunks of a pixel: xor-shuffle inside each
+// lane quad (chunks-per-pixel is a multiple of 4), then a short shared-memory gather.
+// ------------------------------------------------------------------------------------------
+template <typename T, bool SILU, int U>
+__global__ void __launch_bounds__(512) rmsnorm_silu_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                          T* __restrict__ y, int64_t total_chunks, int cpp,
+                                                          float sqrt_c, int iters) {
+  using V = Vec16<T>;
+  extern __shared__ float part[];  // [2][U][blockDim/4]
+  const int tid = threadIdx.x;
+  const int nq = blockDim.x >> 2;
+  const int col = tid % cpp;
+  const int pix = tid / cpp;
+  const int qpp = cpp >> 2;
+  float g[V::N];
+#pragma unroll
+  for (int j = 0; j < V::N; ++j) g[j] = gamma[col * V::N + j] * sqrt_c;
+
+  for (int it = 0; it < iters; ++it) {
+    const int64_t base = ((int64_t)blockIdx.x * iters + it) * (int64_t)(blockDim.x * U);
+    float* pbuf = part + (it & 1) * U * nq;
+    V v[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int64_t i = base + (int64_t)u * blockDim.x + tid;
+      ok[u] = i < total_chunks;
+      if (ok[u]) v[u].load(x + i * V::N);
+      else v[u].zero();
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < V::N; ++j) {
+        float f = v[u].get(j);
+        ss = fmaf(f, f, ss);
+      }
+      ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+      if ((tid & 3) == 0) pbuf[u * nq + (tid >> 2)] = ss;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float tot = 0.f;
+      const float* pp = pbuf + u * nq + pix * qpp;
+      for (int j = 0; j < qpp; ++j) tot += pp[j];
+      float rinv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
+      if (ok[u]) {
+        V o;
+#pragma unroll
+        for (int j = 0; j < V::N; ++j) {
+          float f = v[u].get(j) * rinv * g[j];
+          o.set(j, SILU ? silu(f) : f);
+        }
+        int64_t i = base + (int64_t)u * blockDim.x + tid;
+        o.store(y + i * V::N);
+      }
+    }
+  }
+}
+
+template <typename T>
+static int launch_rmsnorm(const void* x, const float* gamma, void* y, int64_t pixels, int c, int apply_silu,
+                          cudaStream_t st) {
+  constexpr int VN = Vec16<T>::N;
+  constexpr int U = 2;
+  RV_CHECK_ARG(c % (4 * VN) == 0, "rmsnorm: channels (%d) must be a multiple of %d", c, 4 * VN);
+  int cpp = c / VN;
+  int l = cpp / gcd_i(cpp, 32) * 32;  // lcm(cpp, 32)
+  RV_CHECK_ARG(l <= 512, "rmsnorm: unsupported channel count %d", c);
+  int block = l * (256 / l > 0 ? 256 / l : 1);
+  int64_t total_chunks = pixels * cpp;
+  int64_t per_iter = (int64_t)block * U;
+  int64_t need = (total_chunks + per_iter - 1) / per_iter;
+  int64_t target_blocks = (int64_t)num_sms() * 16;
+  int iters = (int)((need + target_blocks - 1) / target_blocks);
+  if (iters < 1) iters = 1;
+  int64_t blocks = (need + iters - 1) / iters;
+  if (blocks < 1) blocks = 1;
+  size_t smem = 2 * U * (block / 4) * sizeof(float);
+  LaunchScope scope(CAT_NORM, st, 2.0 * (double)pixels * c * sizeof(T));
+  if (apply_silu)
+    rmsnorm_silu_kernel<T, true, U><<<(unsigned)blocks, block, smem, st>>>((const T*)x, gamma, (T*)y, total_chunks, cpp,
+                                                                        sqrtf((float)c), iters);
+  else
+    rmsnorm_silu_kernel<T, false, U><<<(unsigned)blocks, block, smem, st>>>((const T*)x, gamma, (T*)y, total_chunks,
+                                                                         cpp, sqrtf((float)c), iters);
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm(32, eps=1e-6) + SiLU (diffusers ResnetBlock2D.norm1/norm2, Attention.group_norm,
+// conv_norm_out).  Pass 1 accumulates (sum, sumsq) per (sample, group) in fp64 through a
+// shared-memory stage; pass 2 is the streaming apply.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(512) groupnorm_stats_kernel(const T* __restrict__ x, double* __restrict__ stats,
+                                                             int64_t hw, int c, int groups, int cpp,
+                                                             int64_t rows_per_block) {
+  using V = Vec16<T>;
+  extern __shared__ double sacc[];  // [groups][2]
+  const int tid = threadIdx.x;
+  const int n = blockIdx.y;
+  for (int i = tid; i < groups * 2; i += blockDim.x) sacc[i] = 0.0;
+  __syncthreads();
+  const int col = tid % cpp;
+  const int rows_per_iter = blockDim.x / cpp;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(hw, r0 + rows_per_block);
+  const T* xb = x + (int64_t)n * hw * c;
+  float s[V::N], q[V::N];
+#pragma unroll
+  for (int j = 0; j < V::N; ++j) s[j] = q[j] = 0.f;
+#pragma unroll 4
+  for (int64_t r = r0 + tid / cpp; r < r1; r += rows_per_iter) {
+    V v;
+    v.load(xb + r * c + col * V::N);
+#pragma unroll
+    for (int j = 0; j < V::N; ++j) {
+      float f = v.get(j);
+      s[j] += f;
+      q[j] = fmaf(f, f, q[j]);
+    }
+  }
+  const int cg = c / groups;
+#pragma unroll
+  for (int j = 0; j < V::N; ++j) {
+    int g = (col * V::N + j) / cg;
+    atomicAdd(&sacc[2 * g], (double)s[j]);
+    atomicAdd(&sacc[2 * g + 1], (double)q[j]);
+  }
+  __syncthreads();
+  for (int i = tid; i < groups * 2; i += blockDim.x) atomicAdd(&stats[(int64_t)n * groups * 2 + i], sacc[i]);
+}
+
+template <typename T, bool SILU>
+__global__ void __launch_bounds__(512) groupnorm_apply_kernel(const T* __restrict__ x, const double* __restrict__ stats,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, T* __restrict__ y,
+                                                             int64_t hw, int c, int groups, int cpp, float eps,
+                                                             int64_t rows_per_block) {
+  using V = Vec16<T>;
+  extern __shared__ float smr[];  // [groups][2]: mean, rstd
+  const int tid = threadIdx.x;
+  const int n = blockIdx.y;
+  const double cnt = (double)hw * (double)(c / groups);
+  for (int g = tid; g < groups; g += blockDim.x) {
+    double m = stats[((int64_t)n * groups + g) * 2] / cnt;
+    double var = stats[((int64_t)n * groups + g) * 2 + 1] / cnt - m * m;
+    if (var < 0.0) var = 0.0;
+    smr[2 * g] = (float)m;
+    smr[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const int col = tid % cpp;
+  const int rows_per_iter = blockDim.x / cpp;
+  const int cg = c / groups;
+  float a[V::N], b[V::N];  // y = x*a + b
+#pragma unroll
+  for (int j = 0; j < V::N; ++j) {
+    int ch = col * V::N + j;
+    int g = ch / cg;
+    float ga = gamma[ch], be = beta[ch];
+    a[j] = smr[2 * g + 1] * ga;
+    b[j] = be - smr[2 * g] * smr[2 * g + 1] * ga;
+  }
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(hw, r0 + rows_per_block);
+  const T* xb = x + (int64_t)n * hw * c;
+  T* yb = y + (int64_t)n * hw * c;
+#pragma unroll 4
+  for (int64_t r = r0 + tid / cpp; r < r1; r += rows_per_iter) {
+    V v, o;
+    v.load(xb + r * c + col * V::N);
+#pragma unroll
+    for (int j = 0; j < V::N; ++j) {
+      float f = fmaf(v.get(j), a[j], b[j]);
+      o.set(j, SILU ? silu(f) : f);
+    }
+    o.store(yb + r * c + col * V::N);
+  }
+}
+
+struct GnGeom {
+  int cpp, block;
+  int64_t rows_per_block;
+  unsigned blocks_x;
+};
+
+template <typename T>
+static int gn_geometry(int n, int64_t hw, int c, int groups, GnGeom* g) {
+  constexpr int VN = Vec16<T>::N;
+  RV_CHECK_ARG(groups > 0 && c % groups == 0 && c % VN == 0, "groupnorm: bad channel/group count %d/%d", c, groups);
+  g->cpp = c / VN;
+  RV_CHECK_ARG(g->cpp <= 512, "groupnorm: too many channels (%d)", c);
+  int rows = 256 / g->cpp;
+  if (rows < 1) rows = 1;
+  g->block = rows * g->cpp;
+  int64_t target = ((int64_t)num_sms() * 8 + n - 1) / n;  // blocks per sample
+  int64_t rpb = (hw + target - 1) / target;
+  rpb = (rpb + rows - 1) / rows * rows;
+  if (rpb < rows) rpb = rows;
+  g->rows_per_block = rpb;
+  g->blocks_x = (unsigned)((hw + rpb - 1) / rpb);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Row softmax (the SDPA softmax of the single-head mid-block attention; scores come from the
+// QK^T GEMM already scaled by 1/sqrt(C)).  One block per row; pass 1 keeps an online
+// (max, sum) pair, pass 2 re-reads the row (L2-resident) and writes probabilities.
+// ------------------------------------------------------------------------------------------
+// fp32 probabilities (the c1 parity mode) use expf; bf16 probabilities the fast intrinsic.
+template <typename TP> __device__ __forceinline__ float sm_exp(float x);
+template <> __device__ __forceinline__ float sm_exp<float>(float x) { return expf(x); }
+template <> __device__ __forceinline__ float sm_exp<__nv_bfloat16>(float x) { return __expf(x); }
+
+template <typename TP>
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, TP* __restrict__ p,
+                                                          int64_t cols, int64_t ld_s, int64_t ld_p) {
+  __shared__ float sm_m[8], sm_l[8];
+  const float* row = s + (int64_t)blockIdx.x * ld_s;
+  TP* out = p + (int64_t)blockIdx.x * ld_p;
+  const int tid = threadIdx.x;
+  float m = -INFINITY, l = 0.f;
+  for (int64_t i = (int64_t)tid * 4; i < cols; i += 256 * 4) {
+    float4 v = *reinterpret_cast<const float4*>(row + i);
+    float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+    float mn = fmaxf(m, mx);
+    l = l * sm_exp<TP>(m - mn) + sm_exp<TP>(v.x - mn) + sm_exp<TP>(v.y - mn) + sm_exp<TP>(v.z - mn) + sm_exp<TP>(v.w - mn);
+    m = mn;
+  }
+  // combine (m, l) across the block
+  float wm = warp_max(m);
+  l *= (m == -INFINITY) ? 0.f : sm_exp<TP>(m - wm);
+  l = warp_sum(l);
+  if ((tid & 31) == 0) {
+    sm_m[tid >> 5] = wm;
+    sm_l[tid >> 5] = l;
+  }
+  __syncthreads();
+  float bm = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bm = fmaxf(bm, sm_m[i]);
+  float bl = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bl += (sm_m[i] == -INFINITY) ? 0.f : sm_l[i] * sm_exp<TP>(sm_m[i] - bm);
+  const float inv = 1.0f / bl;
+  for (int64_t i = (int64_t)tid * 4; i < cols; i += 256 * 4) {
+    float4 v = *reinterpret_cast<const float4*>(row + i);
+    stf(out + i + 0, sm_exp<TP>(v.x - bm) * inv);
+    stf(out + i + 1, sm_exp<TP>(v.y - bm) * inv);
+    stf(out + i + 2, sm_exp<TP>(v.z - bm) * inv);
+    stf(out + i + 3, sm_exp<TP>(v.w - bm) * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// NCHW <-> NHWC (boundary tensors only: 4-channel images, 16/32-channel latents)
+// ------------------------------------------------------------------------------------------
+template <typename TX, typename TY>
+__global__ void nchw_to_nhwc_kernel(const TX* __restrict__ x, TY* __restrict__ y, int c, int64_t hw, int c_pad,
+                                    float scale, float shift) {
+  const int n = blockIdx.y;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hw; i += (int64_t)gridDim.x * blockDim.x) {
+    TY* o = y + ((int64_t)n * hw + i) * c_pad;
+    for (int ch = 0; ch < c_pad; ++ch) {
+      float v = 0.f;
+      if (ch < c) v = ldf(x + ((int64_t)n * c + ch) * hw + i) * scale + shift;
+      stf(o + ch, v);
+    }
+  }
+}
+
+template <typename TX, typename TY>
+__global__ void nhwc_to_nchw_kernel(const TX* __restrict__ x, TY* __restrict__ y, int c, int64_t hw, int x_cstride) {
+  const int n = blockIdx.y;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hw; i += (int64_t)gridDim.x * blockDim.x) {
+    const TX* src = x + ((int64_t)n * hw + i) * x_cstride;
+    for (int ch = 0; ch < c; ++ch) stf(y + ((int64_t)n * c + ch) * hw + i, ldf(src + ch));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// DiagonalGaussianDistribution.sample with a supplied noise tensor (+ optional KL)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) reparam_kernel(const T* __restrict__ moments, const T* __restrict__ noise,
+                                                     T* __restrict__ z, float* __restrict__ kl, int zc, int64_t hw,
+                                                     float z_shift, float z_scale) {
+  __shared__ float red[8];
+  const int n = blockIdx.y;
+  const int64_t per = (int64_t)zc * hw;
+  const T* mean = moments + (int64_t)n * 2 * per;
+  const T* logv = mean + per;
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
+    float mu = ldf(mean + i);
+    float lv = fminf(fmaxf(ldf(logv + i), -30.f), 20.f);
+    float sd = expf(0.5f * lv);
+    if (z) {
+      float e = ldf(noise + (int64_t)n * per + i);
+      stf(z + (int64_t)n * per + i, (fmaf(sd, e, mu) - z_shift) * z_scale);
+    }
+    acc += mu * mu + expf(lv) - 1.0f - lv;
+  }
+  if (kl) {
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float v = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+      v = warp_sum(v);
+      if (threadIdx.x == 0) atomicAdd(kl + n, 0.5f * v);
+    }
+  }
+}
+
+}  // namespace rv
+
+extern "C" {
+
+int rv_rmsnorm_silu(const void* x, const float* gamma, void* y, int64_t pixels, int c, int dtype, int apply_silu,
+                    void* stream) {
+  RV_CHECK_ARG(x && gamma && y && pixels > 0 && c > 0, "rmsnorm: bad argument");
+  if (dtype == RV_F32) return rv::launch_rmsnorm<float>(x, gamma, y, pixels, c, apply_silu, (cudaStream_t)stream);
+  if (dtype == RV_BF16)
+    return rv::launch_rmsnorm<__nv_bfloat16>(x, gamma, y, pixels, c, apply_silu, (cudaStream_t)stream);
+  RV_CHECK_ARG(false, "rmsnorm: bad dtype %d", dtype);
+}
+
+int rv_groupnorm_stats(const void* x, double* stats, int n, int64_t hw, int c, int groups, int dtype, void* stream) {
+  RV_CHECK_ARG(x && stats && n > 0 && hw > 0, "groupnorm_stats: bad argument");
+  RV_CHECK_ARG(dtype == RV_F32 || dtype == RV_BF16, "groupnorm_stats: bad dtype %d", dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  RV_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)n * groups, st));
+  rv::GnGeom g;
+  size_t es = dtype == RV_F32 ? 4 : 2;
+  rv::LaunchScope scope(rv::CAT_NORM, st, (double)n * hw * c * es);
+  if (dtype == RV_F32) {
+    if (int rc = rv::gn_geometry<float>(n, hw, c, groups, &g)) return rc;
+    rv::groupnorm_stats_kernel<float><<<dim3(g.blocks_x, n), g.block, sizeof(double) * 2 * groups, st>>>(
+        (const float*)x, stats, hw, c, groups, g.cpp, g.rows_per_block);
+  } else {
+    if (int rc = rv::gn_geometry<__nv_bfloat16>(n, hw, c, groups, &g)) return rc;
+    rv::groupnorm_stats_kernel<__nv_bfloat16><<<dim3(g.blocks_x, n), g.block, sizeof(double) * 2 * groups, st>>>(
+        (const __nv_bfloat16*)x, stats, hw, c, groups, g.cpp, g.rows_per_block);
+  }
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+int rv_groupnorm_silu(const void* x, const double* stats, const float* gamma, const float* beta, void* y, int n,
+                      int64_t hw, int c, int groups, float eps, int dtype, int apply_silu, void* stream) {
+  RV_CHECK_ARG(x && stats && gamma && beta && y && n > 0 && hw > 0, "groupnorm_silu: bad argument");
+  RV_CHECK_ARG(dtype == RV_F32 || dtype == RV_BF16, "groupnorm_silu: bad dtype %d", dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  rv::GnGeom g;
+  size_t es = dtype == RV_F32 ? 4 : 2;
+  rv::LaunchScope scope(rv::CAT_NORM, st, 2.0 * (double)n * hw * c * es);
+  size_t smem = sizeof(float) * 2 * groups;
+#define RV_GN_LAUNCH(T, S)                                                                              \
+  rv::groupnorm_apply_kernel<T, S><<<dim3(g.blocks_x, n), g.block, smem, st>>>(                          \
+      (const T*)x, stats, gamma, beta, (T*)y, hw, c, groups, g.cpp, eps, g.rows_per_block)
+  if (dtype == RV_F32) {
+    if (int rc = rv::gn_geometry<float>(n, hw, c, groups, &g)) return rc;
+    if (apply_silu) RV_GN_LAUNCH(float, true);
+    else RV_GN_LAUNCH(float, false);
+  } else {
+    if (int rc = rv::gn_geometry<__nv_bfloat16>(n, hw, c, groups, &g)) return rc;
+    if (apply_silu) RV_GN_LAUNCH(__nv_bfloat16, true);
+    else RV_GN_LAUNCH(__nv_bfloat16, false);
+  }
+#undef RV_GN_LAUNCH
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+int rv_softmax_rows(const float* s, void* p, int64_t rows, int64_t cols, int64_t ld_s, int64_t ld_p, int dtype,
+                    void* stream) {
+  RV_CHECK_ARG(s && p && rows > 0 && cols > 0, "softmax: bad argument");
+  RV_CHECK_ARG(cols % 4 == 0 && ld_s % 4 == 0 && ld_s >= cols && ld_p >= cols, "softmax: cols/ld must be multiples of 4");
+  RV_CHECK_ARG(rows < (1ll << 31), "softmax: too many rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  rv::LaunchScope scope(rv::CAT_SOFTMAX, st, (double)rows * cols * (4.0 + (dtype == RV_F32 ? 4.0 : 2.0)));
+  if (dtype == RV_F32)
+    rv::softmax_rows_kernel<float><<<(unsigned)rows, 256, 0, st>>>(s, (float*)p, cols, ld_s, ld_p);
+  else if (dtype == RV_BF16)
+    rv::softmax_rows_kernel<__nv_bfloat16><<<(unsigned)rows, 256, 0, st>>>(s, (__nv_bfloat16*)p, cols, ld_s, ld_p);
+  else
+    RV_CHECK_ARG(false, "softmax: bad dtype %d", dtype);
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+int rv_nchw_to_nhwc(const void* x, void* y, int n, int c, int64_t hw, int c_pad, int x_dtype, int y_dtype, float scale,
+                    float shift, void* stream) {
+  RV_CHECK_ARG(x && y && n > 0 && c > 0 && hw > 0 && c_pad >= c, "nchw_to_nhwc: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned bx = (unsigned)((hw + 255) / 256);
+  if (bx > 4096) bx = 4096;
+  dim3 grid(bx, n);
+  rv::LaunchScope scope(rv::CAT_LAYOUT, st,
+                        (double)n * hw * (c * (x_dtype == RV_F32 ? 4.0 : 2.0) + c_pad * (y_dtype == RV_F32 ? 4.0 : 2.0)));
+  if (x_dtype == RV_F32 && y_dtype == RV_F32)
+    rv::nchw_to_nhwc_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, c, hw, c_pad, scale, shift);
+  else if (x_dtype == RV_F32 && y_dtype == RV_BF16)
+    rv::nchw_to_nhwc_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)x, (__nv_bfloat16*)y, c, hw, c_pad,
+                                                                       scale, shift);
+  else if (x_dtype == RV_BF16 && y_dtype == RV_F32)
+    rv::nchw_to_nhwc_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (float*)y, c, hw, c_pad,
+                                                                       scale, shift);
+  else if (x_dtype == RV_BF16 && y_dtype == RV_BF16)
+    rv::nchw_to_nhwc_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, c, hw, c_pad, scale, shift);
+  else
+    RV_CHECK_ARG(false, "nchw_to_nhwc: bad dtype");
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+int rv_nhwc_to_nchw(const void* x, void* y, int n, int c, int64_t hw, int x_cstride, int x_dtype, int y_dtype,
+                    void* stream) {
+  RV_CHECK_ARG(x && y && n > 0 && c > 0 && hw > 0 && x_cstride >= c, "nhwc_to_nchw: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned bx = (unsigned)((hw + 255) / 256);
+  if (bx > 4096) bx = 4096;
+  dim3 grid(bx, n);
+  rv::LaunchScope scope(rv::CAT_LAYOUT, st,
+                        (double)n * hw * c * ((x_dtype == RV_F32 ? 4.0 : 2.0) + (y_dtype == RV_F32 ? 4.0 : 2.0)));
+  if (x_dtype == RV_F32 && y_dtype == RV_F32)
+    rv::nhwc_to_nchw_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, c, hw, x_cstride);
+  else if (x_dtype == RV_F32 && y_dtype == RV_BF16)
+    rv::nhwc_to_nchw_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)x, (__nv_bfloat16*)y, c, hw,
+                                                                       x_cstride);
+  else if (x_dtype == RV_BF16 && y_dtype == RV_F32)
+    rv::nhwc_to_nchw_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (float*)y, c, hw,
+                                                                       x_cstride);
+  else if (x_dtype == RV_BF16 && y_dtype == RV_BF16)
+    rv::nhwc_to_nchw_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x,
+                                                                               (__nv_bfloat16*)y, c, hw, x_cstride);
+  else
+    RV_CHECK_ARG(false, "nhwc_to_nchw: bad dtype");
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+int rv_reparam(const void* moments, const void* noise, void* z, float* kl_out, int n, int zc, int64_t hw, int dtype,
+               float z_shift, float z_scale, void* stream) {
+  RV_CHECK_ARG(moments && n > 0 && zc > 0 && hw > 0, "reparam: bad argument");
+  RV_CHECK_ARG((z == nullptr) == (noise == nullptr), "reparam: z and noise must be given together");
+  RV_CHECK_ARG(z || kl_out, "reparam: nothing to compute");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (kl_out) RV_CUDA(cudaMemsetAsync(kl_out, 0, sizeof(float) * n, st));
+  int64_t per = (int64_t)zc * hw;
+  unsigned bx = (unsigned)((per + 255) / 256);
+  if (bx > 1024) bx = 1024;
+  dim3 grid(bx, n);
+  size_t es = dtype == RV_F32 ? 4 : 2;
+  rv::LaunchScope scope(rv::CAT_REPARAM, st, (double)n * per * es * (z ? 4.0 : 2.0));
+  if (dtype == RV_F32)
+    rv::reparam_kernel<float><<<grid, 256, 0, st>>>((const float*)moments, (const float*)noise, (float*)z, kl_out, zc, hw,
+                                                   z_shift, z_scale);
+  else if (dtype == RV_BF16)
+    rv::reparam_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)moments, (const __nv_bfloat16*)noise,
+                                                           (__nv_bfloat16*)z, kl_out, zc, hw, z_shift, z_scale);
+  else
+    RV_CHECK_ARG(false, "reparam: bad dtype %d", dtype);
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

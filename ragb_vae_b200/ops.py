@@ -1,0 +1,248 @@
+"""Tensor-level wrappers over the C ABI.  torch supplies device memory and streams only; every
+function below launches librgbavae kernels on ``torch.cuda.current_stream()`` and raises if the
+tensors are not CUDA tensors -- there is no eager path."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, RV_BF16, RV_F32, check
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return RV_F32
+    if t.dtype == torch.bfloat16:
+        return RV_BF16
+    raise TypeError(f"librgbavae supports float32 and bfloat16 tensors, got {t.dtype}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.RvError("ragb_vae_b200 runs on CUDA (sm_100a) tensors only; there is no CPU path")
+
+
+def launch_count() -> int:
+    return int(_lib.load().rv_launch_count())
+
+
+def prof_begin() -> None:
+    check(_lib.load().rv_prof_begin(), "rv_prof_begin")
+
+
+def prof_end() -> dict:
+    n = _lib.PROF_CATEGORIES
+    ms = (C.c_double * n)()
+    cnt = (C.c_int64 * n)()
+    work = (C.c_double * n)()
+    check(_lib.load().rv_prof_end(ms, cnt, work), "rv_prof_end")
+    return {name: {"ms": ms[i], "launches": int(cnt[i]), "work": work[i]} for i, name in enumerate(_lib.PROF_NAMES)}
+
+
+# ------------------------------------------------------------------------------------------
+# convolution / GEMM
+# ------------------------------------------------------------------------------------------
+def conv_out_size(h: int, w: int, ksize: int, stride: int, upsample: bool):
+    if upsample:
+        return 2 * h, 2 * w
+    if ksize == 3 and stride == 2:
+        return h // 2, w // 2
+    return h, w
+
+
+def make_desc(n, h, w, cin, cout, ksize=3, stride=1, upsample=False, *, x_dtype, y_dtype, x_nchw=False, y_nchw=False,
+              x_cstride=None, y_cstride=None, bias_mode=1, in_scale=1.0, in_shift=0.0, out_scale=1.0, out_shift=0.0,
+              clamp=None, alpha=1.0) -> ConvDesc:
+    oh, ow = conv_out_size(h, w, ksize, stride, upsample)
+    d = ConvDesc()
+    d.n, d.h, d.w, d.cin, d.cout = n, h, w, cin, cout
+    d.ksize, d.stride, d.upsample = ksize, stride, int(bool(upsample))
+    d.pad_lo = 1 if (ksize == 3 and stride == 1) else 0
+    d.oh, d.ow = oh, ow
+    d.x_dtype, d.y_dtype = x_dtype, y_dtype
+    d.x_nchw, d.y_nchw = int(x_nchw), int(y_nchw)
+    d.x_cstride = cin if x_cstride is None else x_cstride
+    d.y_cstride = cout if y_cstride is None else y_cstride
+    d.bias_mode = bias_mode
+    d.in_scale, d.in_shift, d.out_scale, d.out_shift = in_scale, in_shift, out_scale, out_shift
+    d.clamp = 0 if clamp is None else 1
+    d.clamp_lo, d.clamp_hi = (0.0, 0.0) if clamp is None else clamp
+    d.alpha = alpha
+    return d
+
+
+def conv2d_direct(desc: ConvDesc, x, w, bias, residual, y) -> None:
+    _need_cuda(x, w, bias, residual, y)
+    check(_lib.load().rv_conv2d_direct(C.byref(desc), _ptr(x), _ptr(w), _ptr(bias), _ptr(residual), _ptr(y), _stream(x)),
+          "rv_conv2d_direct")
+
+
+def conv2d_tc(desc: ConvDesc, x, w_packed, w_ld: int, bias, residual, y) -> None:
+    _need_cuda(x, w_packed, bias, residual, y)
+    check(_lib.load().rv_conv2d_tc(C.byref(desc), _ptr(x), _ptr(w_packed), int(w_ld), _ptr(bias), _ptr(residual), _ptr(y),
+                                   _stream(x)), "rv_conv2d_tc")
+
+
+def pack_conv_weights_tc(w: torch.Tensor, upsample: bool = False) -> torch.Tensor:
+    """fp32 [cout][cin][k][k] -> bf16 [cout][taps*cin] (upsample: [cout][16*cin], phase-folded)."""
+    _need_cuda(w)
+    w = w.detach().to(torch.float32).contiguous()
+    cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+    slots = 16 if upsample else k * k
+    out = torch.empty((cout, slots * cin), dtype=torch.bfloat16, device=w.device)
+    ld = C.c_int64(0)
+    check(_lib.load().rv_pack_conv_weights(_ptr(w), cout, cin, k, int(upsample), _ptr(out), C.byref(ld), _stream(w)),
+          "rv_pack_conv_weights")
+    assert ld.value == slots * cin
+    return out
+
+
+def pack_conv_weights_direct(w: torch.Tensor) -> torch.Tensor:
+    """fp32 [cout][cin][k][k] -> fp32 [cout][taps*cin]."""
+    _need_cuda(w)
+    w = w.detach().to(torch.float32).contiguous()
+    cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+    out = torch.empty((cout, k * k * cin), dtype=torch.float32, device=w.device)
+    check(_lib.load().rv_pack_conv_weights_direct(_ptr(w), cout, cin, k, _ptr(out), _stream(w)),
+          "rv_pack_conv_weights_direct")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# normalisation
+# ------------------------------------------------------------------------------------------
+def rmsnorm_silu(x: torch.Tensor, gamma: torch.Tensor, silu: bool = True, out: Optional[torch.Tensor] = None):
+    """x: NHWC-dense [..., C]."""
+    _need_cuda(x, gamma)
+    c = x.shape[-1]
+    y = torch.empty_like(x) if out is None else out
+    check(_lib.load().rv_rmsnorm_silu(_ptr(x), _ptr(gamma), _ptr(y), x.numel() // c, c, _dt(x), int(silu), _stream(x)),
+          "rv_rmsnorm_silu")
+    return y
+
+
+def groupnorm_silu(x: torch.Tensor, gamma, beta, groups: int = 32, eps: float = 1e-6, silu: bool = True,
+                   out: Optional[torch.Tensor] = None):
+    """x: [N, H, W, C] (or [N, HW, C]) NHWC-dense."""
+    _need_cuda(x, gamma, beta)
+    n, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (n * c)
+    stats = torch.empty((n, groups, 2), dtype=torch.float64, device=x.device)
+    lib = _lib.load()
+    check(lib.rv_groupnorm_stats(_ptr(x), _ptr(stats), n, hw, c, groups, _dt(x), _stream(x)), "rv_groupnorm_stats")
+    y = torch.empty_like(x) if out is None else out
+    check(lib.rv_groupnorm_silu(_ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(y), n, hw, c, groups, eps, _dt(x),
+                                int(silu), _stream(x)), "rv_groupnorm_silu")
+    return y
+
+
+def softmax_rows(s: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    _need_cuda(s)
+    rows, cols = s.shape
+    p = torch.empty((rows, cols), dtype=out_dtype, device=s.device)
+    check(_lib.load().rv_softmax_rows(_ptr(s), _ptr(p), rows, cols, s.stride(0), p.stride(0), _dt(p), _stream(s)),
+          "rv_softmax_rows")
+    return p
+
+
+# ------------------------------------------------------------------------------------------
+# layout
+# ------------------------------------------------------------------------------------------
+def nchw_to_nhwc(x: torch.Tensor, c_pad: int, out_dtype: torch.dtype, scale: float = 1.0, shift: float = 0.0):
+    _need_cuda(x)
+    n, c, h, w = x.shape
+    x = x.contiguous()
+    y = torch.empty((n, h, w, c_pad), dtype=out_dtype, device=x.device)
+    check(_lib.load().rv_nchw_to_nhwc(_ptr(x), _ptr(y), n, c, h * w, c_pad, _dt(x), _dt(y), scale, shift, _stream(x)),
+          "rv_nchw_to_nhwc")
+    return y
+
+
+def nhwc_to_nchw(x: torch.Tensor, c: int, out_dtype: torch.dtype):
+    _need_cuda(x)
+    n, h, w, cs = x.shape
+    y = torch.empty((n, c, h, w), dtype=out_dtype, device=x.device)
+    check(_lib.load().rv_nhwc_to_nchw(_ptr(x), _ptr(y), n, c, h * w, cs, _dt(x), _dt(y), _stream(x)), "rv_nhwc_to_nchw")
+    return y
+
+
+# ------------------------------------------------------------------------------------------
+# posterior, loss, validation metrics
+# ------------------------------------------------------------------------------------------
+def reparam(moments: torch.Tensor, noise: Optional[torch.Tensor], want_kl: bool = False, z_shift: float = 0.0,
+            z_scale: float = 1.0):
+    """moments [N, 2Z, H, W]; returns (z or None, kl or None)."""
+    _need_cuda(moments, noise)
+    moments = moments.contiguous()
+    n, c2, h, w = moments.shape
+    zc = c2 // 2
+    z = None
+    if noise is not None:
+        if tuple(noise.shape) != (n, zc, h, w):
+            raise ValueError(f"noise shape {tuple(noise.shape)} does not match latent shape {(n, zc, h, w)}")
+        noise = noise.to(moments.dtype).contiguous()
+        z = torch.empty((n, zc, h, w), dtype=moments.dtype, device=moments.device)
+    kl = torch.empty((n,), dtype=torch.float32, device=moments.device) if want_kl else None
+    check(_lib.load().rv_reparam(_ptr(moments), _ptr(noise), _ptr(z), _ptr(kl), n, zc, h * w, _dt(moments), z_shift,
+                                 z_scale, _stream(moments)), "rv_reparam")
+    return z, kl
+
+
+def _pair(a: torch.Tensor, b: torch.Tensor):
+    _need_cuda(a, b)
+    if a.shape != b.shape or a.dim() != 4 or a.shape[1] != 4:
+        raise ValueError(f"expected two (B,4,H,W) tensors, got {tuple(a.shape)} and {tuple(b.shape)}")
+    if b.dtype != a.dtype:
+        b = b.to(a.dtype)
+    return a.contiguous(), b.contiguous()
+
+
+def recon_loss_per_sample(pred: torch.Tensor, target: torch.Tensor, eb: Sequence[float], eb2: Sequence[float],
+                          naive_mse: bool = False) -> torch.Tensor:
+    """Per-sample SUM of the AlphaVAE reconstruction loss map, fp32 [B]."""
+    pred, target = _pair(pred, target)
+    n, _, h, w = pred.shape
+    lib = _lib.load()
+    blocks = lib.rv_reduce_blocks(h * w)
+    partial = torch.empty((n * blocks,), dtype=torch.float64, device=pred.device)
+    out = torch.empty((n,), dtype=torch.float32, device=pred.device)
+    ebv = (C.c_float * 3)(*[float(v) for v in eb])
+    eb2v = (C.c_float * 3)(*[float(v) for v in eb2])
+    check(lib.rv_recon_loss(_ptr(pred), _ptr(target), ebv, eb2v, int(naive_mse), _ptr(out), _ptr(partial), n, h * w,
+                            _dt(pred), _stream(pred)), "rv_recon_loss")
+    return out
+
+
+def composite_psnr(recon: torch.Tensor, target: torch.Tensor, backgrounds: Sequence[Sequence[float]]) -> torch.Tensor:
+    """[B, len(backgrounds)+1] fp32: PSNR (dB) of the composites over each RGB background, then alpha MAE."""
+    recon, target = _pair(recon, target)
+    n, _, h, w = recon.shape
+    nbg = len(backgrounds)
+    if nbg > 4:
+        raise ValueError("at most 4 backgrounds per call")
+    lib = _lib.load()
+    blocks = lib.rv_reduce_blocks(h * w)
+    partial = torch.empty((n * blocks * 5,), dtype=torch.float64, device=recon.device)
+    out = torch.empty((n, nbg + 1), dtype=torch.float32, device=recon.device)
+    flat = [float(v) for bg in backgrounds for v in bg]
+    bgs = (C.c_float * max(1, len(flat)))(*flat)
+    check(lib.rv_composite_psnr(_ptr(recon), _ptr(target), bgs, nbg, _ptr(out), _ptr(partial), n, h * w, _dt(recon),
+                                _stream(recon)), "rv_composite_psnr")
+    return out
+
+
+def attn_scale(c: int) -> float:
+    return 1.0 / math.sqrt(c)

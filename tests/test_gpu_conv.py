@@ -1,0 +1,131 @@
+"""GPU parity of the two convolution kernels (C ABI) against torch.nn.functional.conv2d on the CPU:
+rv_conv2d_direct (fp32 CUDA cores) and rv_conv2d_tc (tcgen05 + TMA, bf16)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from ragb_vae_b200._lib import RV_BF16, RV_F32  # noqa: E402
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def ops(lib_built):
+    from ragb_vae_b200 import ops as o
+
+    assert torch.cuda.is_available()
+    return o
+
+
+def ref_conv(x, w, b, k, stride, upsample):
+    """x NCHW fp32; the three conv flavours of the VAE."""
+    if upsample:
+        x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+    if k == 3 and stride == 2:
+        return F.conv2d(F.pad(x, (0, 1, 0, 1)), w, b, stride=2)
+    return F.conv2d(x, w, b, padding=k // 2)
+
+
+CASES = [  # n, h, w, cin, cout, k, stride, upsample
+    (2, 16, 16, 64, 64, 3, 1, False),
+    (1, 24, 40, 96, 96, 3, 1, False),      # BK=32 path, non-pow2 width
+    (1, 8, 8, 16, 384, 3, 1, False),       # BK=16 path (decoder conv_in), two N tiles
+    (2, 16, 24, 128, 128, 3, 2, False),    # stride-2 parity view
+    (1, 12, 20, 192, 96, 3, 1, True),      # fused nearest-x2 upsample, phase-folded weights
+    (1, 16, 16, 96, 192, 1, 1, False),     # 1x1 shortcut
+    (1, 32, 32, 96, 4, 3, 1, False),       # conv_out: Cout=4 padded to one 16-wide tile
+    (1, 128, 130, 64, 32, 3, 1, False),    # 128-wide tiles with a ragged edge
+    (3, 8, 8, 512, 512, 3, 1, False),      # two 256-wide N tiles, deep K
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_direct_conv_fp32(ops, case):
+    n, h, w, cin, cout, k, stride, up = case
+    g = torch.Generator().manual_seed(sum(case[:5]))
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = ref_conv(x, wt, b, k, stride, up)
+    wp = ops.pack_conv_weights_direct(wt.cuda())
+    oh, ow = ref.shape[2:]
+    # NHWC in / NHWC out
+    xh = x.permute(0, 2, 3, 1).contiguous().cuda()
+    y = torch.empty(n, oh, ow, cout, device="cuda")
+    d = ops.make_desc(n, h, w, cin, cout, k, stride, up, x_dtype=RV_F32, y_dtype=RV_F32)
+    ops.conv2d_direct(d, xh, wp, b.cuda(), None, y)
+    assert rel(y.permute(0, 3, 1, 2), ref) < 2e-6
+    # NCHW in / NCHW out with residual, input affine, output affine + clamp
+    res = torch.randn(n, cout, oh, ow, generator=g)
+    y2 = torch.empty(n, cout, oh, ow, device="cuda")
+    d2 = ops.make_desc(n, h, w, cin, cout, k, stride, up, x_dtype=RV_F32, y_dtype=RV_F32, x_nchw=True, y_nchw=True,
+                       in_scale=2.0, in_shift=-1.0, out_scale=0.5, out_shift=0.5, clamp=(0.0, 1.0))
+    ops.conv2d_direct(d2, x.cuda(), wp, b.cuda(), res.cuda(), y2)
+    ref2 = torch.clamp((ref_conv(x * 2 - 1, wt, b, k, stride, up) + res) * 0.5 + 0.5, 0, 1)
+    assert rel(y2, ref2) < 2e-6
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_tc_conv_bf16(ops, case):
+    n, h, w, cin, cout, k, stride, up = case
+    g = torch.Generator().manual_seed(sum(case[:5]) + 1)
+    x = torch.randn(n, cin, h, w, generator=g).bfloat16()
+    wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).bfloat16().float()
+    b = torch.randn(cout, generator=g)
+    ref = ref_conv(x.float(), wt, b, k, stride, up)
+    oh, ow = ref.shape[2:]
+    wp = ops.pack_conv_weights_tc(wt.cuda(), up)
+    xh = x.permute(0, 2, 3, 1).contiguous().cuda()
+    res = torch.randn(n, oh, ow, cout, generator=g).bfloat16()
+    # bf16 NHWC out with residual
+    y = torch.empty(n, oh, ow, cout, dtype=torch.bfloat16, device="cuda")
+    d = ops.make_desc(n, h, w, cin, cout, k, stride, up, x_dtype=RV_BF16, y_dtype=RV_BF16)
+    ops.conv2d_tc(d, xh, wp, wp.shape[1], b.cuda(), res.cuda(), y)
+    tol = 8e-3 if up else 4e-3  # folded phase weights are re-rounded to bf16
+    assert rel(y.float().permute(0, 3, 1, 2), ref + res.float().permute(0, 3, 1, 2)) < tol
+    # fp32 NCHW out, affine + clamp epilogue
+    y2 = torch.empty(n, cout, oh, ow, dtype=torch.float32, device="cuda")
+    d2 = ops.make_desc(n, h, w, cin, cout, k, stride, up, x_dtype=RV_BF16, y_dtype=RV_F32, y_nchw=True, out_scale=0.5,
+                       out_shift=0.5, clamp=(0.0, 1.0))
+    ops.conv2d_tc(d2, xh, wp, wp.shape[1], b.cuda(), None, y2)
+    assert rel(y2, torch.clamp(ref * 0.5 + 0.5, 0, 1)) < tol
+
+
+def test_tc_gemm_modes(ops):
+    """The attention GEMMs: strided operands, alpha scaling, fp32 output, per-row bias."""
+    g = torch.Generator().manual_seed(11)
+    t, c = 256, 384
+    qk = torch.randn(t, 2 * c, generator=g).bfloat16()
+    s = torch.empty(t, t, dtype=torch.float32, device="cuda")
+    qkc = qk.cuda()
+    d = ops.make_desc(1, 1, t, c, t, 1, 1, False, x_dtype=RV_BF16, y_dtype=RV_F32, x_cstride=2 * c, y_cstride=t,
+                      bias_mode=0, alpha=0.05)
+    ops.conv2d_tc(d, qkc, qkc[:, c:], 2 * c, None, None, s)
+    ref = 0.05 * qk[:, :c].float() @ qk[:, c:].float().t()
+    assert rel(s, ref) < 1e-5
+    wv = torch.randn(c, c, generator=g).bfloat16()
+    bv = torch.randn(c, generator=g)
+    xn = torch.randn(t, c, generator=g).bfloat16()
+    vt = torch.empty(c, t, dtype=torch.bfloat16, device="cuda")
+    d2 = ops.make_desc(1, 1, c, c, t, 1, 1, False, x_dtype=RV_BF16, y_dtype=RV_BF16, x_cstride=c, y_cstride=t, bias_mode=2)
+    ops.conv2d_tc(d2, wv.cuda(), xn.cuda(), c, bv.cuda(), None, vt)
+    assert rel(vt.float(), wv.float() @ xn.float().t() + bv[:, None]) < 4e-3
+
+
+def test_tc_rejects_bad_arguments(ops):
+    from ragb_vae_b200._lib import RvError
+
+    x = torch.zeros(1, 8, 8, 24, dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros(16, 9 * 24, dtype=torch.bfloat16, device="cuda")
+    y = torch.zeros(1, 8, 8, 16, dtype=torch.bfloat16, device="cuda")
+    d = ops.make_desc(1, 8, 8, 24, 16, 3, 1, False, x_dtype=RV_BF16, y_dtype=RV_BF16, bias_mode=0)
+    with pytest.raises(RvError):
+        ops.conv2d_tc(d, x, w, 9 * 24, None, None, y)  # cin not a multiple of 16
+    d.oh = 7
+    with pytest.raises(RvError):
+        ops.conv2d_direct(d, x, w.float(), None, None, y)  # inconsistent output size

@@ -1,0 +1,139 @@
+"""End-to-end GPU parity of the drop-in surface against the committed golden vectors (oracle,
+config c1: 1x4x256x256, seed-0 weights, supplied noise) and size-independent properties at larger
+sizes.  Tolerances are BASELINE.json's: 1e-4 relative (fp32), 2e-2 (bf16), PSNR within 0.05 dB."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import vae_oracle as O  # noqa: E402
+
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def R(lib_built):
+    import ragb_vae_b200 as r
+
+    assert torch.cuda.is_available()
+    return r
+
+
+_MODELS = {}
+
+
+def gpu_model(R, oracle_model, arch, dtype):
+    key = (arch, dtype)
+    if key not in _MODELS:
+        m = R.RgbaAutoencoder(arch)
+        m.load_state_dict(oracle_model(arch).state_dict())
+        _MODELS[key] = m.to("cuda", dtype)
+    return _MODELS[key]
+
+
+def c1_inputs():
+    x = O.synthetic_rgba(1, 256, 256, seed=1)
+    noise = torch.randn(1, 16, 32, 32, generator=torch.Generator().manual_seed(2))
+    return x, noise
+
+
+@pytest.mark.parametrize("arch", ["qwen", "flux"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_c1_encode_sample_decode_matches_golden(R, golden, oracle_model, arch, dtype):
+    g = golden(arch)
+    vae = gpu_model(R, oracle_model, arch, dtype)
+    x, noise = c1_inputs()
+    tol = TOL[dtype]
+    post = vae.encode((x * 2 - 1).cuda().to(dtype)).latent_dist
+    assert post.parameters.shape == (1, 32, 32, 32) and post.parameters.dtype == dtype
+    assert rel(post.parameters, g["moments"]) < tol
+    z = post.sample(noise=noise.cuda())
+    assert rel(z, g["z"]) < tol
+    # decode the GOLDEN latent so that decoder error is measured on its own
+    dec = vae.decode(g["z"].cuda().to(dtype)).sample
+    assert dec.shape == (1, 4, 256, 256)
+    assert rel(dec, g["decoded"]) < tol
+    assert abs(float(post.kl()[0]) - float(g["kl"][0])) / float(g["kl"][0]) < (1e-4 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize("arch", ["qwen", "flux"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_c1_rgba_vae_forward_loss_and_psnr(R, golden, oracle_model, arch, dtype):
+    g = golden(arch)
+    model = R.RgbaVAE(gpu_model(R, oracle_model, arch, dtype))
+    x, noise = c1_inputs()
+    recon, post = model(x.cuda().to(dtype), noise=noise.cuda())
+    tol = TOL[dtype]
+    assert recon.shape == (1, 4, 256, 256) and float(recon.min()) >= 0.0 and float(recon.max()) <= 1.0
+    assert rel(recon, g["recon"]) < tol
+    m = R.validation_metrics(recon, x.cuda().to(dtype))
+    assert abs(float(m["psnr_white"][0]) - float(g["psnr_white"][0])) < 0.05
+    assert abs(float(m["psnr_black"][0]) - float(g["psnr_black"][0])) < 0.05
+    assert abs(float(m["alpha_mae"][0]) - float(g["alpha_mae"][0])) < (1e-4 if dtype == torch.float32 else 5e-3)
+    # reconstruction loss on the raw decoder output (train step, rgba_vae_stage.py:452-454)
+    dec = model.vae.decode(g["z"].cuda().to(dtype)).sample
+    tgt = (x * 2 - 1).cuda().to(dtype)
+    for rm, key in ((False, "recon_loss_sum"), (True, "recon_loss_mean")):
+        got = R.AlphaVaeLoss(reduce_mean=rm).reconstruction_loss(dec, tgt)
+        assert abs(float(got) - float(g[key][0])) / float(g[key][0]) < (2e-4 if dtype == torch.float32 else 2e-2), key
+    naive = R.AlphaVaeLoss(reduce_mean=True, use_naive_mse=True).reconstruction_loss(dec, tgt)
+    assert abs(float(naive) - float(g["naive_mse_mean"][0])) / float(g["naive_mse_mean"][0]) < (2e-4 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize("arch", ["qwen", "flux"])
+def test_bf16_tensor_core_path_agrees_with_fp32_cuda_core_path_on_ragged_bucket(R, oracle_model, arch):
+    """Bucket shapes are multiples of 32, not powers of two: 2 x 4 x 160 x 96 exercises ragged tiles."""
+    x = O.synthetic_rgba(2, 160, 96, seed=5, structured=True)
+    noise = torch.randn(2, 16, 20, 12, generator=torch.Generator().manual_seed(6))
+    ref_recon, ref_post, _ = O.rgba_vae_forward(oracle_model(arch), x, noise)
+    for dtype in (torch.float32, torch.bfloat16):
+        model = R.RgbaVAE(gpu_model(R, oracle_model, arch, dtype))
+        recon, post = model(x.cuda().to(dtype), noise=noise.cuda())
+        assert rel(post.parameters, ref_post.parameters) < TOL[dtype]
+        assert rel(recon, ref_recon) < TOL[dtype]
+
+
+@pytest.mark.parametrize("arch", ["qwen", "flux"])
+def test_batch_independence_and_slicing_at_512(R, oracle_model, arch):
+    """Size-independent properties: samples are independent (slicing == batched) and deterministic."""
+    vae = gpu_model(R, oracle_model, arch, torch.bfloat16)
+    x = (O.synthetic_rgba(3, 512, 384, seed=7) * 2 - 1).cuda().bfloat16()
+    m_all = vae.encode(x).latent_dist.parameters
+    m_one = vae.encode(x[1:2]).latent_dist.parameters
+    assert torch.equal(m_all[1:2], m_one)
+    vae.enable_slicing()
+    try:
+        assert torch.equal(vae.encode(x).latent_dist.parameters, m_all)
+    finally:
+        vae.disable_slicing()
+    z = m_all[:, :16].contiguous()
+    d1, d2 = vae.decode(z).sample, vae.decode(z).sample
+    assert torch.equal(d1, d2) and d1.shape == (3, 4, 512, 384)
+    assert torch.isfinite(d1.float()).all()
+    if arch == "qwen":
+        assert float(d1.float().abs().max()) <= 1.0  # AutoencoderKLQwenImage clamps its output
+
+
+def test_three_channel_input_and_flux_latent_plumbing(R, oracle_model):
+    vae = gpu_model(R, oracle_model, "flux", torch.bfloat16)
+    model = R.RgbaVAE(vae)
+    x = O.synthetic_rgba(1, 64, 64, seed=8)
+    noise = torch.randn(1, 16, 8, 8, generator=torch.Generator().manual_seed(9)).cuda()
+    x3 = x.clone()
+    x3[:, 3] = 1.0
+    r4, _ = model(x3.cuda().bfloat16(), noise=noise)
+    r3, _ = model(x3[:, :3].cuda().bfloat16(), noise=noise)   # _ensure_alpha
+    assert torch.equal(r3, r4)
+    # (z - shift) * scale fused into the sample, and its inverse fused into the decoder's loader
+    post = vae.encode((x * 2 - 1).cuda().bfloat16()).latent_dist
+    z = post.sample(noise=noise)
+    zn = post.sample(noise=noise, shift=0.1159, scale=0.3611)
+    assert rel(zn, (z.float() - 0.1159) * 0.3611) < 1e-2
+    a = vae._decode_image(zn, z_scale=1.0 / 0.3611, z_shift=0.1159)
+    b = vae.decode(z).sample
+    assert rel(a, b) < 2e-2
