@@ -211,10 +211,10 @@ static int gn_geometry(int n, int64_t hw, int c, int groups, GnGeom* g) {
   int rows = 256 / g->cpp;
   if (rows < 1) rows = 1;
   g->block = rows * g->cpp;
-  int64_t target = ((int64_t)num_sms() * 8 + n - 1) / n;  // blocks per sample
-  int64_t rpb = (hw + target - 1) / target;
-  rpb = (rpb + rows - 1) / rows * rows;
-  if (rpb < rows) rpb = rows;
+  // 64 rows per thread; the partition depends on hw only, so a sample's statistics (and therefore
+  // its output bits) do not depend on the batch it is in
+  (void)n;
+  int64_t rpb = (int64_t)rows * 64;
   g->rows_per_block = rpb;
   g->blocks_x = (unsigned)((hw + rpb - 1) / rpb);
   return 0;

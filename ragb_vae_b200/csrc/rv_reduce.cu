@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(256) recon_loss_kernel(const T* __restrict__ p
         float da = at - ap;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          float d = tv[c][j] * at - pv[c][j] * ap;
+          // separately rounded products (no fma contraction): identical inputs give exactly 0
+          float d = __fsub_rn(__fmul_rn(tv[c][j], at), __fmul_rn(pv[c][j], ap));
           acc[0] += d * d - 2.0f * lp.eb[c] * d * da + lp.eb2[c] * da * da;
         }
       }
