@@ -112,8 +112,15 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// x * sigmoid(x).  expf (not __expf) keeps the fp32 parity mode within 1e-6 of torch's silu.
+// x * sigmoid(x).  The fp32 parity mode uses expf and an IEEE divide (within 1e-6 of torch's silu);
+// bf16 outputs use the MUFU exp2 / reciprocal approximations (~2^-21 relative, far below bf16's 2^-9):
+// the accurate form costs ~40 instructions per element, which makes a streaming kernel ALU-bound
+// (measured 2.8 TB/s instead of HBM speed).
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+template <typename T> __device__ __forceinline__ float silu_t(float x);
+template <> __device__ __forceinline__ float silu_t<float>(float x) { return silu(x); }
+template <> __device__ __forceinline__ float silu_t<__nv_bfloat16>(float x) { return silu_fast(x); }
 
 int num_sms();
 

@@ -510,8 +510,12 @@ static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_
   p.n_img = d->n;
   p.cin = d->cin;
   p.cin_pitch = d->x_cstride;
-  p.bk = (d->cin % 64 == 0) ? 64 : (d->cin % 32 == 0 ? 32 : 16);
-  p.kc_per_tap = d->cin / p.bk;
+  // 128-byte operand rows move ~2x faster through TMA than 64-byte ones (measured: the row rate, not the
+  // byte rate, bounds small-N layers), so channel counts above 64 always use BK=64: the last block of a tap
+  // is partly out of bounds in x (zero-filled), which cancels whatever weight columns it is paired with.
+  // (not for the stride-2 parity view, whose folded channel axis has real data past cin)
+  p.bk = (d->cin % 64 == 0 || (d->cin > 64 && d->stride == 1)) ? 64 : (d->cin % 32 == 0 ? 32 : 16);
+  p.kc_per_tap = (d->cin + p.bk - 1) / p.bk;
   const CUtensorMapSwizzle sw =
       p.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   p.layout_type = p.bk == 64 ? 2u : (p.bk == 32 ? 4u : 6u);

@@ -64,10 +64,75 @@ __global__ void __launch_bounds__(512) rmsnorm_silu_kernel(const T* __restrict__
 #pragma unroll
         for (int j = 0; j < V::N; ++j) {
           float f = v[u].get(j) * rinv * g[j];
-          o.set(j, SILU ? silu(f) : f);
+          o.set(j, SILU ? silu_t<T>(f) : f);
         }
         int64_t i = base + (int64_t)u * blockDim.x + tid;
         o.store(y + i * V::N);
+      }
+    }
+  }
+}
+
+
+// Fast path: a pixel's channels are split over L lanes (L = 4/8/16/32, a power of two) with three
+// 16-byte chunks per lane, so the sum of squares is a pure xor-shuffle reduction: no shared memory,
+// no block barrier, 3*PIX independent 16-byte loads in flight per thread.
+template <typename T, bool SILU, int PIX>
+__global__ void __launch_bounds__(256) rmsnorm_silu_warp_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                               T* __restrict__ y, int64_t pixels, int lanes_per_pixel,
+                                                               float sqrt_c) {
+  using V = Vec16<T>;
+  constexpr int CPL = 3;
+  const int L = lanes_per_pixel;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (L - 1);          // lane within the pixel group
+  const int grp = lane / L;                // pixel group within the warp
+  const int ppw = 32 / L;                  // pixels per warp per step
+  const int64_t c = (int64_t)L * CPL * V::N;
+  float g[CPL][V::N];
+#pragma unroll
+  for (int k = 0; k < CPL; ++k)
+#pragma unroll
+    for (int j = 0; j < V::N; ++j) g[k][j] = gamma[(k * L + sub) * V::N + j] * sqrt_c;
+  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t p0 = warp_global * ppw * PIX; p0 < pixels; p0 += warps_total * ppw * PIX) {
+    V v[PIX][CPL];
+    bool ok[PIX];
+#pragma unroll
+    for (int u = 0; u < PIX; ++u) {
+      const int64_t pix = p0 + (int64_t)u * ppw + grp;
+      ok[u] = pix < pixels;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        if (ok[u]) v[u][k].load(x + pix * c + (int64_t)(k * L + sub) * V::N);
+        else v[u][k].zero();
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PIX; ++u) {
+      float ss = 0.f;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k)
+#pragma unroll
+        for (int j = 0; j < V::N; ++j) {
+          float f = v[u][k].get(j);
+          ss = fmaf(f, f, ss);
+        }
+      for (int o = 1; o < L; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rinv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+      if (ok[u]) {
+        const int64_t pix = p0 + (int64_t)u * ppw + grp;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          V o;
+#pragma unroll
+          for (int j = 0; j < V::N; ++j) {
+            float f = v[u][k].get(j) * rinv * g[k][j];
+            o.set(j, SILU ? silu_t<T>(f) : f);
+          }
+          o.store(y + pix * c + (int64_t)(k * L + sub) * V::N);
+        }
       }
     }
   }
@@ -80,6 +145,27 @@ static int launch_rmsnorm(const void* x, const float* gamma, void* y, int64_t pi
   constexpr int U = 2;
   RV_CHECK_ARG(c % (4 * VN) == 0, "rmsnorm: channels (%d) must be a multiple of %d", c, 4 * VN);
   int cpp = c / VN;
+  if (cpp % 3 == 0) {
+    const int lanes = cpp / 3;
+    if (lanes >= 1 && lanes <= 32 && (lanes & (lanes - 1)) == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0)) {
+      constexpr int PIX = 2;
+      const int ppw = 32 / lanes;
+      const int64_t warps_needed = (pixels + (int64_t)ppw * PIX - 1) / ((int64_t)ppw * PIX);
+      int64_t blocks = (warps_needed + 7) / 8;
+      const int64_t cap = (int64_t)num_sms() * 32;
+      if (blocks > cap) blocks = cap;
+      if (blocks < 1) blocks = 1;
+      LaunchScope scope(CAT_NORM, st, 2.0 * (double)pixels * c * sizeof(T));
+      if (apply_silu)
+        rmsnorm_silu_warp_kernel<T, true, PIX><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, gamma, (T*)y, pixels, lanes,
+                                                                               sqrtf((float)c));
+      else
+        rmsnorm_silu_warp_kernel<T, false, PIX><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, gamma, (T*)y, pixels, lanes,
+                                                                                sqrtf((float)c));
+      RV_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   int l = cpp / gcd_i(cpp, 32) * 32;  // lcm(cpp, 32)
   RV_CHECK_ARG(l <= 512, "rmsnorm: unsupported channel count %d", c);
   int block = l * (256 / l > 0 ? 256 / l : 1);
@@ -190,7 +276,7 @@ __global__ void __launch_bounds__(512) groupnorm_apply_kernel(const T* __restric
 #pragma unroll
     for (int j = 0; j < V::N; ++j) {
       float f = fmaf(v.get(j), a[j], b[j]);
-      o.set(j, SILU ? silu(f) : f);
+      o.set(j, SILU ? silu_t<T>(f) : f);
     }
     o.store(yb + r * c + col * V::N);
   }

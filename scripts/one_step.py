@@ -1,0 +1,22 @@
+#!/usr/bin/env python
+"""One RgbaVAE step (encode -> sample -> decode -> white-bg PSNR) for profiler captures.
+    python scripts/one_step.py [arch] [batch] [size] [iters]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import ragb_vae_b200 as R
+from ragb_vae_b200 import ops
+
+arch = sys.argv[1] if len(sys.argv) > 1 else "qwen"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+S = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+iters = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+torch.manual_seed(0)
+model = R.RgbaVAE(R.RgbaAutoencoder(arch).to("cuda", torch.bfloat16))
+x = torch.rand(B, 4, S, S, device="cuda").bfloat16()
+noise = torch.randn(B, 16, S // 8, S // 8, device="cuda").bfloat16()
+for _ in range(iters):
+    recon, _ = model(x, noise=noise)
+    m = ops.composite_psnr(recon, x, [(1.0, 1.0, 1.0)])
+torch.cuda.synchronize()
+print("psnr_white", m[:, 0].tolist(), "launches", ops.launch_count())
