@@ -311,8 +311,9 @@ def main():
     if a.impl == "reference":
         reference_arm(a)
         return
-    from ragb_vae_b200 import build as B
+    import __graft_entry__ as G
 
+    B = G._load_builder()
     if not os.path.exists(B.LIB):  # normally prebuilt in-tree (it travels with the snapshot)
         if int(os.environ.get("LOCAL_RANK", "0")) == 0:
             B.build()

@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 2
+#define RV_ABI_VERSION 3
 #define RV_PROF_CATEGORIES 9
 
 int rv_abi_version(void);
@@ -85,6 +85,15 @@ int rv_conv2d_direct(const rv_conv_desc* d, const void* x, const float* w, const
  * bf16 with pitch y_cstride. */
 int rv_conv2d_tc(const rv_conv_desc* d, const void* x, const void* w_packed, int64_t w_ld,
                  const float* bias, const void* residual, void* y, void* stream);
+
+/* rv_conv2d_tc plus the consumer's QwenImageRMS_norm (+SiLU) fused into the epilogue: besides (or, with
+ * y == NULL, instead of) the raw output it writes y_act = act(v / max(||v||_2 over cout, 1e-12) * gamma_scaled)
+ * as a second NHWC bf16 tensor of the same pitch, gamma_scaled = gamma * sqrt(cout) (fp32 [cout]).  Needs
+ * cout <= 256 (one accumulator tile holds the pixel's whole channel vector) and an NHWC bf16 output.
+ * Saves the standalone norm kernel's read+write of the tensor (norm1/norm2 of QwenImageResidualBlock). */
+int rv_conv2d_tc_norm(const rv_conv_desc* d, const void* x, const void* w_packed, int64_t w_ld,
+                      const float* bias, const void* residual, void* y, void* y_act,
+                      const float* gamma_scaled, int apply_silu, void* stream);
 
 /* Packs fp32 weights [cout][cin][ksize][ksize] (PyTorch layout; for the Qwen causal-conv3d
  * the caller passes the live temporal slice w[:, :, kt-1]) into the bf16 K-major matrix

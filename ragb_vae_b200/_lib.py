@@ -9,7 +9,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "librgbavae.so")
 
 RV_F32, RV_BF16 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 PROF_CATEGORIES = 9
 PROF_NAMES = ("conv_tc", "conv_direct", "norm_silu", "softmax", "layout", "reparam", "recon_loss", "composite_psnr",
               "attention")
@@ -51,6 +51,7 @@ SIGNATURES = {
     "rv_prof_end": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "rv_conv2d_direct": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
     "rv_conv2d_tc": (_I, [C.POINTER(ConvDesc), _P, _P, _L, _P, _P, _P, _P]),
+    "rv_conv2d_tc_norm": (_I, [C.POINTER(ConvDesc), _P, _P, _L, _P, _P, _P, _P, _P, _I, _P]),
     "rv_pack_conv_weights": (_I, [_P, _I, _I, _I, _I, _P, C.POINTER(C.c_int64), _P]),
     "rv_pack_conv_weights_direct": (_I, [_P, _I, _I, _I, _P, _P]),
     "rv_rmsnorm_silu": (_I, [_P, _P, _P, _L, _I, _I, _I, _P]),
@@ -75,7 +76,7 @@ def load() -> C.CDLL:
         return _lib
     if not os.path.exists(LIB_PATH):
         raise RvError(
-            f"{LIB_PATH} is missing: build it with `python -m ragb_vae_b200.build` (needs nvcc). "
+            f"{LIB_PATH} is missing: build it with `python ragb_vae_b200/build.py` (needs nvcc). "
             "ragb_vae_b200 has no CPU or eager fallback.")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
@@ -84,7 +85,7 @@ def load() -> C.CDLL:
         fn.argtypes = args
     got = lib.rv_abi_version()
     if got != ABI_VERSION:
-        raise RvError(f"librgbavae ABI {got} != expected {ABI_VERSION}; rebuild with `python -m ragb_vae_b200.build --force`")
+        raise RvError(f"librgbavae ABI {got} != expected {ABI_VERSION}; rebuild with `python ragb_vae_b200/build.py --force`")
     _lib = lib
     return lib
 

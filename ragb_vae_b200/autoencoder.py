@@ -231,6 +231,15 @@ def _build_qwen(in_ch, out_ch, base, z_dim, dim_mult, num_res_blocks, t_down):
 # ------------------------------------------------------------------------------------------
 # outputs / config
 # ------------------------------------------------------------------------------------------
+class _Stream:
+    """The residual stream between blocks: the raw tensor and, when the producing conv could fuse it, the
+    already normalised + activated copy for the consumer identified by ``act_key = (id(norm), silu)``."""
+    __slots__ = ("raw", "act", "act_key")
+
+    def __init__(self, raw, act=None, act_key=None):
+        self.raw, self.act, self.act_key = raw, act, act_key
+
+
 class AutoencoderKLOutput(SimpleNamespace):
     """``.latent_dist`` like diffusers' output dataclass."""
 
@@ -296,6 +305,7 @@ class RgbaAutoencoder(nn.Module):
         self.use_tiling = False
         self.use_slicing = False
         self.gradient_checkpointing = False
+        self.fuse_norm = True  # RMS norm + SiLU in the producing conv's epilogue where one tile holds all channels
         self._pack_cache: Dict[tuple, tuple] = {}
         self.requires_grad_(False)
         self.eval()
@@ -427,23 +437,53 @@ class RgbaAutoencoder(nn.Module):
               y_nchw: bool = False, y_dtype: Optional[torch.dtype] = None, out_scale: float = 1.0, out_shift: float = 0.0,
               clamp=None) -> torch.Tensor:
         """x: NHWC [N,H,W,Cin(+pad)] activations in the model dtype."""
+        return self._conv_fused(x, conv, upsample=upsample, residual=residual, y_nchw=y_nchw, y_dtype=y_dtype,
+                                out_scale=out_scale, out_shift=out_shift, clamp=clamp).raw
+
+    def _can_fuse_norm(self, conv: Conv, norm) -> bool:
+        """The conv epilogue can apply the consumer's norm when it is a per-pixel RMS norm and one accumulator
+        tile holds the pixel's whole channel vector (tensor-core path, Cout <= 256)."""
+        return self.fuse_norm and self.dtype == torch.bfloat16 and isinstance(norm, RMSNorm) and conv.out_channels <= 256
+
+    def _conv_fused(self, x: torch.Tensor, conv: Conv, *, upsample: bool = False, residual: Optional[torch.Tensor] = None,
+                    y_nchw: bool = False, y_dtype: Optional[torch.dtype] = None, out_scale: float = 1.0,
+                    out_shift: float = 0.0, clamp=None, next_norm=None, want_raw: bool = True) -> "_Stream":
+        """Convolution whose result feeds ``next_norm = (norm_module, silu)``: where possible that norm is fused
+        into the epilogue (second output ``act``); ``want_raw=False`` drops the raw tensor when only the
+        normalised one is consumed (conv1 -> norm2 -> conv2 inside a residual block)."""
         tc, act_dt, code = self._mode()
         n, h, w, cx = x.shape
         cin, cout, k, stride = conv.in_channels, conv.out_channels, conv.k, conv.stride
         oh, ow = ops.conv_out_size(h, w, k, stride, upsample)
         y_dt = act_dt if y_dtype is None else y_dtype
-        y = torch.empty((n, cout, oh, ow) if y_nchw else (n, oh, ow, cout), dtype=y_dt, device=x.device)
         bias = self._f32(conv.bias, "bias")
         desc = ops.make_desc(n, h, w, cx if tc else cin, cout, k, stride, upsample, x_dtype=code,
                              y_dtype=RV_F32 if y_dt == torch.float32 else RV_BF16, y_nchw=y_nchw, x_cstride=cx,
                              out_scale=out_scale, out_shift=out_shift, clamp=clamp)
+        fuse = next_norm is not None and not y_nchw and y_dt == torch.bfloat16 and self._can_fuse_norm(conv, next_norm[0])
+        y = None
+        if want_raw or not fuse:
+            y = torch.empty((n, cout, oh, ow) if y_nchw else (n, oh, ow, cout), dtype=y_dt, device=x.device)
         if tc:
             wp = self._conv_weights(conv, True, upsample, cin_pad=cx)
+            if fuse:
+                norm, silu = next_norm
+                act = torch.empty((n, oh, ow, cout), dtype=y_dt, device=x.device)
+                gamma = self._cached((id(norm.gamma), "gamma_scaled"), [norm.gamma],
+                                     lambda: (norm.gamma.detach().to(torch.float32).reshape(-1) * math.sqrt(cout)).contiguous())
+                ops.conv2d_tc_norm(desc, x, wp, wp.shape[1], bias, residual, y, act, gamma, silu)
+                return _Stream(y, act, (id(norm), silu))
             ops.conv2d_tc(desc, x, wp, wp.shape[1], bias, residual, y)
         else:
             wp = self._conv_weights(conv, False)
             ops.conv2d_direct(desc, x, wp, bias, residual, y)
-        return y
+        return _Stream(y, None, None)
+
+    def _normed(self, st: "_Stream", norm, silu: bool = True) -> torch.Tensor:
+        """act(norm(stream)): the fused copy if the producer already wrote it for this norm, else the norm kernel."""
+        if st.act is not None and st.act_key == (id(norm), silu):
+            return st.act
+        return self._norm(st.raw, norm, silu)
 
     def _norm(self, x: torch.Tensor, norm, silu: bool = True) -> torch.Tensor:
         if isinstance(norm, RMSNorm):
@@ -451,11 +491,14 @@ class RgbaAutoencoder(nn.Module):
         return ops.groupnorm_silu(x, self._f32(norm.weight, "gn_w"), self._f32(norm.bias, "gn_b"), norm.num_groups, norm.eps,
                                   silu)
 
-    def _resblock(self, x: torch.Tensor, blk) -> torch.Tensor:
+    def _resblock(self, st: "_Stream", blk, next_norm=None) -> "_Stream":
+        """h = shortcut(x); x = conv2(act(norm2(conv1(act(norm1(x)))))) + h   (diffusers ResnetBlock2D /
+        QwenImageResidualBlock).  conv1 writes only act(norm2(.)), conv2 adds h and also writes the next consumer's norm."""
         short = getattr(blk, "conv_shortcut", None)
-        h = x if short is None else self._conv(x, short)
-        t = self._conv(self._norm(x, blk.norm1), blk.conv1)
-        return self._conv(self._norm(t, blk.norm2), blk.conv2, residual=h)
+        a = self._normed(st, blk.norm1)
+        h = st.raw if short is None else self._conv(st.raw, short)
+        t = self._conv_fused(a, blk.conv1, next_norm=(blk.norm2, True), want_raw=False)
+        return self._conv_fused(self._normed(t, blk.norm2), blk.conv2, residual=h, next_norm=next_norm)
 
     def _gemm(self, x, w, *, rows, k, cols, x_ld, w_ld, y, y_ld, bias=None, bias_mode=0, alpha=1.0, residual=None):
         """y[rows][cols] = alpha * x[rows][k] . w[cols][k]^T (+bias) on the conv kernels (1x1, one 'image row')."""
@@ -469,21 +512,22 @@ class RgbaAutoencoder(nn.Module):
             assert w_ld == k, "direct path needs dense weight rows"
             ops.conv2d_direct(desc, x, w, bias, residual, y)
 
-    def _attention(self, x: torch.Tensor, attn) -> torch.Tensor:
+    def _attention(self, st: "_Stream", attn) -> "_Stream":
         """Single-head self-attention over the H*W tokens of each image, d = C, residual added."""
         tc, act_dt, _ = self._mode()
+        x = st.raw
         n, h, w, c = x.shape
         t = h * w
         dev = x.device
         if self.arch == "qwen":
-            xn = self._norm(x, attn.norm, silu=False)
+            xn = self._normed(st, attn.norm, silu=False)
             wqkv = attn.to_qkv.weight.detach().reshape(3 * c, c)
             bqkv = attn.to_qkv.bias.detach()
             srcs = [attn.to_qkv.weight, attn.to_qkv.bias]
             get = lambda i: (wqkv[i * c:(i + 1) * c], bqkv[i * c:(i + 1) * c])
             wo_p, bo_p = attn.proj.weight, attn.proj.bias
         else:
-            xn = self._norm(x, attn.group_norm, silu=False)
+            xn = self._normed(st, attn.group_norm, silu=False)
             lins = (attn.to_q, attn.to_k, attn.to_v)
             srcs = [p for l in lins for p in (l.weight, l.bias)]
             get = lambda i: (lins[i].weight.detach(), lins[i].bias.detach())
@@ -530,12 +574,13 @@ class RgbaAutoencoder(nn.Module):
         out = torch.empty_like(x)
         self._gemm(o, pk["wo"], rows=n * t, k=c, cols=c, x_ld=c, w_ld=c, y=out.view(n * t, c), y_ld=c, bias=pk["bo"],
                    bias_mode=1, residual=x.view(n * t, c))
-        return out
+        return _Stream(out, None, None)
 
-    def _mid(self, x, mid):
-        x = self._resblock(x, mid.resnets[0])
-        x = self._attention(x, mid.attentions[0])
-        return self._resblock(x, mid.resnets[1])
+    def _mid(self, st, mid, next_norm=None):
+        a = mid.attentions[0]
+        st = self._resblock(st, mid.resnets[0], next_norm=(getattr(a, "norm", None) or a.group_norm, False))
+        st = self._attention(st, a)
+        return self._resblock(st, mid.resnets[1], next_norm=next_norm)
 
     # ---- encode / decode -----------------------------------------------------------------
     def _check_image(self, x: torch.Tensor, channels: int, what: str, mult: int):
@@ -550,66 +595,102 @@ class RgbaAutoencoder(nn.Module):
         if x.dtype not in (torch.float32, torch.bfloat16):
             raise TypeError(f"{what} must be float32 or bfloat16, got {x.dtype}")
 
-    def _stem(self, x: torch.Tensor, conv: Conv, in_scale: float, in_shift: float) -> torch.Tensor:
+    def _stem(self, x: torch.Tensor, conv: Conv, in_scale: float, in_shift: float, next_norm=None) -> "_Stream":
         """NCHW boundary tensor -> first NHWC activation."""
         tc, act_dt, code = self._mode()
         n, c, h, w = x.shape
         x = x.contiguous()
         if tc:
             xp = ops.nchw_to_nhwc(x, 16 * ((c + 15) // 16), act_dt, in_scale, in_shift)
-            return self._conv(xp, conv)
+            return self._conv_fused(xp, conv, next_norm=next_norm)
         y = torch.empty((n, h, w, conv.out_channels), dtype=act_dt, device=x.device)
         desc = ops.make_desc(n, h, w, c, conv.out_channels, conv.k, 1, False,
                              x_dtype=RV_F32 if x.dtype == torch.float32 else RV_BF16, y_dtype=code, x_nchw=True,
                              in_scale=in_scale, in_shift=in_shift)
         ops.conv2d_direct(desc, x, self._conv_weights(conv, False), self._f32(conv.bias, "bias"), None, y)
-        return y
+        return _Stream(y, None, None)
+
+    @staticmethod
+    def _first_norm(item):
+        """(norm, silu) the op ``item = (kind, module)`` applies to the stream first, or None."""
+        kind, m = item
+        if kind == "res":
+            return (m.norm1, True)
+        if kind == "mid":
+            return (m.resnets[0].norm1, True)
+        if kind == "head":
+            return (m[0], True)
+        return None
 
     def _encode_moments(self, x: torch.Tensor, in_scale: float = 1.0, in_shift: float = 0.0) -> torch.Tensor:
         """(B,Cin,H,W) in [-1,1] (after in_scale/in_shift) -> moments (B,2Z,H/8,W/8), model dtype."""
         self._check_image(x, self.encoder.conv_in.in_channels, "encode() input", 8)
         enc = self.encoder
-        h = self._stem(x, enc.conv_in, in_scale, in_shift)
+        items = []
         if self.arch == "flux":
             for blk in enc.down_blocks:
-                for r in blk.resnets:
-                    h = self._resblock(h, r)
+                items += [("res", r) for r in blk.resnets]
                 if getattr(blk, "downsamplers", None) is not None:
-                    h = self._conv(h, blk.downsamplers[0].conv)
-            h = self._mid(h, enc.mid_block)
-            return self._conv(self._norm(h, enc.conv_norm_out), enc.conv_out, y_nchw=True)
-        for blk in enc.down_blocks:
-            h = self._resblock(h, blk) if blk._kind == "res" else self._conv(h, blk.resample[1])
-        h = self._mid(h, enc.mid_block)
-        h = self._conv(self._norm(h, enc.norm_out), enc.conv_out)
-        return self._conv(h, self.quant_conv, y_nchw=True)
+                    items.append(("down", blk.downsamplers[0].conv))
+            items.append(("mid", enc.mid_block))
+            head = (enc.conv_norm_out, enc.conv_out)
+        else:
+            for blk in enc.down_blocks:
+                items.append(("res", blk) if blk._kind == "res" else ("down", blk.resample[1]))
+            items.append(("mid", enc.mid_block))
+            head = (enc.norm_out, enc.conv_out)
+        items.append(("head", head))
+        st = self._stem(x, enc.conv_in, in_scale, in_shift, next_norm=self._first_norm(items[0]))
+        st = self._run_ops_until_head(st, items)
+        h = self._normed(st, head[0])
+        if self.arch == "flux":
+            return self._conv(h, head[1], y_nchw=True)
+        return self._conv(self._conv(h, head[1]), self.quant_conv, y_nchw=True)
+
+    def _run_ops_until_head(self, st, items):
+        """items[-1] is the ("head", (norm, conv)) marker: run everything before it with lookahead into it."""
+        for i, (kind, m) in enumerate(items[:-1]):
+            nxt = self._first_norm(items[i + 1])
+            st = self._run_ops_one(st, kind, m, nxt)
+        return st
+
+    def _run_ops_one(self, st, kind, m, nxt):
+        if kind == "res":
+            return self._resblock(st, m, next_norm=nxt)
+        if kind == "mid":
+            return self._mid(st, m, next_norm=nxt)
+        if kind == "down" or kind == "conv":
+            return self._conv_fused(st.raw, m, next_norm=nxt)
+        if kind == "up":
+            return self._conv_fused(st.raw, m, upsample=True, next_norm=nxt)
+        raise AssertionError(kind)
 
     def _decode_image(self, z: torch.Tensor, out_scale: float = 1.0, out_shift: float = 0.0, clamp=None,
                       z_scale: float = 1.0, z_shift: float = 0.0) -> torch.Tensor:
         """latents (B,Z,h,w) -> image (B,Cout,8h,8w) in the model dtype (optionally y*out_scale+out_shift, clamped)."""
         dec = self.decoder
         self._check_image(z, dec.conv_in.in_channels, "decode() input", 1)
-        if self.arch == "flux":
-            h = self._stem(z, dec.conv_in, z_scale, z_shift)
-            h = self._mid(h, dec.mid_block)
-            for blk in dec.up_blocks:
-                for r in blk.resnets:
-                    h = self._resblock(h, r)
-                if getattr(blk, "upsamplers", None) is not None:
-                    h = self._conv(h, blk.upsamplers[0].conv, upsample=True)
-            return self._conv(self._norm(h, dec.conv_norm_out), dec.conv_out, y_nchw=True, out_scale=out_scale,
-                              out_shift=out_shift, clamp=clamp)
-        h = self._stem(z, self.post_quant_conv, z_scale, z_shift)
-        h = self._conv(h, dec.conv_in)
-        h = self._mid(h, dec.mid_block)
+        items = [("mid", dec.mid_block)]
         for blk in dec.up_blocks:
-            for r in blk.resnets:
-                h = self._resblock(h, r)
+            items += [("res", r) for r in blk.resnets]
             if getattr(blk, "upsamplers", None) is not None:
-                h = self._conv(h, blk.upsamplers[0].resample[1], upsample=True)
+                up = blk.upsamplers[0]
+                items.append(("up", up.conv if self.arch == "flux" else up.resample[1]))
+        if self.arch == "flux":
+            head = (dec.conv_norm_out, dec.conv_out)
+            items.append(("head", head))
+            st = self._stem(z, dec.conv_in, z_scale, z_shift, next_norm=self._first_norm(items[0]))
+            st = self._run_ops_until_head(st, items)
+            return self._conv(self._normed(st, head[0]), head[1], y_nchw=True, out_scale=out_scale, out_shift=out_shift,
+                              clamp=clamp)
+        head = (dec.norm_out, dec.conv_out)
+        items.append(("head", head))
+        st = self._stem(z, self.post_quant_conv, z_scale, z_shift)
+        st = self._conv_fused(st.raw, dec.conv_in, next_norm=self._first_norm(items[0]))
+        st = self._run_ops_until_head(st, items)
         # AutoencoderKLQwenImage._decode clamps to [-1, 1]; composed with the caller's affine + clamp
         lo, hi = -1.0 * out_scale + out_shift, 1.0 * out_scale + out_shift
         if clamp is not None:
             lo, hi = max(lo, clamp[0]), min(hi, clamp[1])
-        return self._conv(self._norm(h, dec.norm_out), dec.conv_out, y_nchw=True, out_scale=out_scale, out_shift=out_shift,
+        return self._conv(self._normed(st, head[0]), head[1], y_nchw=True, out_scale=out_scale, out_shift=out_shift,
                           clamp=(lo, hi))

@@ -1,6 +1,6 @@
 """Builds librgbavae.so (the sm_100a kernel library) in-tree with nvcc.
 
-    python -m ragb_vae_b200.build [--force]
+    python ragb_vae_b200/build.py [--force] [-v]
 
 The library is compiled for sm_100a only (``-gencode arch=compute_100a,code=sm_100a``); nvcc
 cross-compiles without a GPU.  Objects go to ``ragb_vae_b200/csrc/build/``, the shared library to
@@ -18,7 +18,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(PKG, "librgbavae.so")
-SOURCES = ["rv_common.cu", "rv_elementwise.cu", "rv_reduce.cu", "rv_conv_direct.cu", "rv_conv_tc.cu", "rv_attention.cu"]
+SOURCES = ["rv_common.cu", "rv_elementwise.cu", "rv_reduce.cu", "rv_conv_direct.cu", "rv_conv_tc.cu", "rv_conv_halo.cu", "rv_attention.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr",
@@ -35,6 +35,7 @@ def _nvcc() -> str:
 def _deps(src: str):
     yield os.path.join(CSRC, src)
     yield os.path.join(CSRC, "rv_common.cuh")
+    yield os.path.join(CSRC, "rv_tc_common.cuh")
     yield os.path.join(os.path.dirname(PKG), "include", "rgbavae.h")
     yield os.path.abspath(__file__)
 

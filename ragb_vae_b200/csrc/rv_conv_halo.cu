@@ -1,0 +1,360 @@
+// Halo-reuse 3x3 convolution for the narrow, full-resolution layers (sm_100a, tcgen05 + TMA).
+//
+// Why a second conv kernel.  rv_conv_tc.cu re-loads the activation tile once per tap (9x) and the weight tile
+// once per 128 output pixels.  Measured on B200 that kernel is bound by the L2->SM operand stream (~45-55 B/cycle
+// per SM): for Cout = 96 every tap needs 24 KB of A + 24 KB of B for 384 cycles of MMA, i.e. 125 B/cycle, so the
+// 96-channel 1024^2 layers of the Qwen VAE (28 % of its FLOPs) ran at 0.52 PFLOP/s while the 512-channel layers hit
+// 1.4.  Here each input row is loaded ONCE per strip and each weight tap once per TWO output rows:
+//
+//   * a CTA walks a strip: 128 output columns x R output rows of one image, two rows (M = 2 x 128) per step;
+//   * input rows live in a 6-slot shared-memory ring, each slot = the row's 130 pixels (1-pixel halo both sides)
+//     as K-major SWIZZLE_128B [130][64ch] (+ SWIZZLE_64B [130][32ch] when Cin % 64 == 32), written by TMA; image
+//     borders are TMA out-of-bounds zero fill;
+//   * the A operand of tap (dy,dx) for output row y is the slot of input row y+dy-1 addressed from its row dx on:
+//     the UMMA swizzle is a function of the absolute shared-memory address, so a descriptor may start at any row
+//     (verified in scripts/experiments/umma_shift_test.cu) -- no im2col, no per-tap copies;
+//   * weights stream per tap through a 3-slot ring and are consumed by both output rows (24 MMAs per tap);
+//   * accumulators: 2 rows x N columns, double buffered in TMEM (4N <= 512 columns);
+//   * epilogue (8 warps): the lean path of rv_tc_common.cuh incl. the fused RMS-norm + SiLU second output.
+//
+// L2->SM traffic per two output rows (Cin = Cout = 96): 2 x 25 KB of activations + 9 x 18 KB of weights = 212 KB for
+// 5184 MMA cycles = 41 B/cycle (was 125).
+#include <cstring>
+#include <mutex>
+
+#include "rv_tc_common.cuh"
+
+namespace rv {
+
+constexpr int HL_RING = 6;
+constexpr int HL_BRING = 3;
+constexpr int HL_EPI_WARPS = 8;
+constexpr int HL_THREADS = 128 + 32 * HL_EPI_WARPS;  // row-TMA, MMA, weight-TMA, (idle), 8 epilogue warps
+constexpr int HL_PIX = 130;                          // 128 output columns + halo
+constexpr uint32_t HL_R128_BYTES = 17408;            // 130 x 128 B rounded up to 1024
+constexpr uint32_t HL_R64_BYTES = 9216;              // 130 x 64 B rounded up to 1024
+
+struct HaloParams {
+  int n_img, h, w;
+  int cin, bn;                 // bn = cout (multiple of 16, <= 128)
+  int nk128, has64;            // K blocks per tap: nk128 x 64 channels (SW128) + optionally 32 channels (SW64)
+  int col_blocks, strips_per_col, strip_rows, total_strips;
+  uint32_t row_slot_bytes, r64_off, row_tx_bytes;
+  uint32_t b_slot_bytes, b64_off, b_tx_bytes;
+  uint32_t bring_off;          // offset of the weight ring behind the row ring
+  EpiParams e;
+};
+
+struct StripCoord {
+  int img, x0, ys, rows;  // rows: even number of output rows walked (may run past h by one masked row)
+};
+__device__ __forceinline__ StripCoord decode_strip(const HaloParams& p, int s) {
+  StripCoord c;
+  const int sy = s % p.strips_per_col;
+  const int t = s / p.strips_per_col;
+  c.x0 = (t % p.col_blocks) * 128;
+  c.img = t / p.col_blocks;
+  c.ys = sy * p.strip_rows;
+  int rows = p.h - c.ys;
+  if (rows > p.strip_rows) rows = p.strip_rows;
+  c.rows = (rows + 1) & ~1;
+  return c;
+}
+
+__global__ void __launch_bounds__(HL_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a128, const __grid_constant__ CUtensorMap map_a64,
+                 const __grid_constant__ CUtensorMap map_b128, const __grid_constant__ CUtensorMap map_b64,
+                 const __grid_constant__ HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_rowfull[HL_RING];
+  __shared__ __align__(8) uint64_t bar_rowempty[HL_RING];
+  __shared__ __align__(8) uint64_t bar_bfull[HL_BRING];
+  __shared__ __align__(8) uint64_t bar_bempty[HL_BRING];
+  __shared__ __align__(8) uint64_t bar_accfull[2];
+  __shared__ __align__(8) uint64_t bar_accempty[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_bias[128];
+  __shared__ __align__(16) float s_gamma[128];
+  __shared__ float s_ss[2][2][2][128];  // [accumulator buffer][tile row][column half][pixel]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bring = ring + p.bring_off;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < HL_RING; ++s) {
+      mbar_init(smem_u32(&bar_rowfull[s]), 1);
+      mbar_init(smem_u32(&bar_rowempty[s]), 1);
+    }
+    for (int s = 0; s < HL_BRING; ++s) {
+      mbar_init(smem_u32(&bar_bfull[s]), 1);
+      mbar_init(smem_u32(&bar_bempty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&bar_accfull[a]), 1);
+      mbar_init(smem_u32(&bar_accempty[a]), HL_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a128) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b128) : "memory");
+  }
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (p.e.bias_mode == 1)
+    for (int i = threadIdx.x; i < p.bn; i += HL_THREADS) s_bias[i] = p.e.bias[i];
+  if (p.e.norm_gamma)
+    for (int i = threadIdx.x; i < p.bn; i += HL_THREADS) s_gamma[i] = p.e.norm_gamma[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const uint32_t rowfull0 = smem_u32(&bar_rowfull[0]), rowempty0 = smem_u32(&bar_rowempty[0]);
+  const uint32_t bfull0 = smem_u32(&bar_bfull[0]), bempty0 = smem_u32(&bar_bempty[0]);
+  const uint32_t accfull0 = smem_u32(&bar_accfull[0]), accempty0 = smem_u32(&bar_accempty[0]);
+
+  if (warp == 0) {
+    // ------------------------------ input-row producer ------------------------------
+    uint32_t g = 0;  // rows loaded so far (ring position)
+    for (int s = blockIdx.x; s < p.total_strips; s += gridDim.x) {
+      const StripCoord c = decode_strip(p, s);
+      for (int y = c.ys - 1; y <= c.ys + c.rows; ++y) {
+        const uint32_t slot = g % HL_RING, par = (g / HL_RING) & 1u;
+        mbar_wait(rowempty0 + 8u * slot, par ^ 1u);
+        if (elect_one()) {
+          const uint32_t full = rowfull0 + 8u * slot;
+          const uint32_t dst = ring + slot * p.row_slot_bytes;
+          mbar_arrive_expect_tx(full, p.row_tx_bytes);
+          for (int kb = 0; kb < p.nk128; ++kb) tma_load_4d(dst + kb * HL_R128_BYTES, &map_a128, full, kb * 64, c.x0 - 1, y, c.img);
+          if (p.has64) tma_load_4d(dst + p.r64_off, &map_a64, full, p.nk128 * 64, c.x0 - 1, y, c.img);
+        }
+        __syncwarp();
+        ++g;
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------ weight-tap producer ------------------------------
+    uint32_t t = 0;
+    for (int s = blockIdx.x; s < p.total_strips; s += gridDim.x) {
+      const StripCoord c = decode_strip(p, s);
+      const int ntiles = c.rows >> 1;
+      for (int j = 0; j < ntiles; ++j) {
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t slot = t % HL_BRING, par = (t / HL_BRING) & 1u;
+          mbar_wait(bempty0 + 8u * slot, par ^ 1u);
+          if (elect_one()) {
+            const uint32_t full = bfull0 + 8u * slot;
+            const uint32_t dst = bring + slot * p.b_slot_bytes;
+            mbar_arrive_expect_tx(full, p.b_tx_bytes);
+            for (int kb = 0; kb < p.nk128; ++kb)
+              tma_load_2d(dst + kb * (uint32_t)p.bn * 128u, &map_b128, full, tap * p.cin + kb * 64, 0);
+            if (p.has64) tma_load_2d(dst + p.b64_off, &map_b64, full, tap * p.cin + p.nk128 * 64, 0);
+          }
+          __syncwarp();
+          ++t;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t hi128 = make_smem_desc(0u, 1024u, 2u);
+    const uint64_t hi64 = make_smem_desc(0u, 512u, 4u);
+    uint32_t g0 = 0, t = 0, tc = 0;
+    for (int s = blockIdx.x; s < p.total_strips; s += gridDim.x) {
+      const StripCoord c = decode_strip(p, s);
+      const int ntiles = c.rows >> 1;
+      for (int j = 0; j < ntiles; ++j) {
+        const uint32_t buf = tc & 1u;
+        mbar_wait(accempty0 + 8u * buf, ((tc >> 1) & 1u) ^ 1u);
+        for (int i = (j == 0 ? 0 : 2); i < 4; ++i) {
+          const uint32_t g = g0 + 2u * j + i;
+          mbar_wait(rowfull0 + 8u * (g % HL_RING), (g / HL_RING) & 1u);
+        }
+        tc_fence_after();
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dy = tap / 3, dx = tap - 3 * dy;
+          const uint32_t bslot = t % HL_BRING;
+          mbar_wait(bfull0 + 8u * bslot, (t / HL_BRING) & 1u);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t b_addr = bring + bslot * p.b_slot_bytes;
+            for (int r = 0; r < 2; ++r) {
+              const uint32_t g = g0 + 2u * j + r + dy;
+              const uint32_t a_addr = ring + (g % HL_RING) * p.row_slot_bytes;
+              const uint32_t d_tmem = tmem_base + buf * 2u * (uint32_t)p.bn + (uint32_t)r * (uint32_t)p.bn;
+              uint32_t first = (tap == 0) ? 0u : 1u;
+              for (int kb = 0; kb < p.nk128; ++kb) {
+                const uint64_t ad = hi128 | (uint64_t)(((a_addr + kb * HL_R128_BYTES + dx * 128u) & 0x3FFFFu) >> 4);
+                const uint64_t bd = hi128 | (uint64_t)(((b_addr + kb * (uint32_t)p.bn * 128u) & 0x3FFFFu) >> 4);
+                umma_bf16(d_tmem, ad, bd, idesc, first);
+                umma_bf16(d_tmem, ad + 2u, bd + 2u, idesc, 1u);
+                umma_bf16(d_tmem, ad + 4u, bd + 4u, idesc, 1u);
+                umma_bf16(d_tmem, ad + 6u, bd + 6u, idesc, 1u);
+                first = 1u;
+              }
+              if (p.has64) {
+                const uint64_t ad = hi64 | (uint64_t)(((a_addr + p.r64_off + dx * 64u) & 0x3FFFFu) >> 4);
+                const uint64_t bd = hi64 | (uint64_t)(((b_addr + p.b64_off) & 0x3FFFFu) >> 4);
+                umma_bf16(d_tmem, ad, bd, idesc, first);
+                umma_bf16(d_tmem, ad + 2u, bd + 2u, idesc, 1u);
+              }
+            }
+            umma_commit(bempty0 + 8u * bslot);
+            if (tap == 8) {
+              umma_commit(accfull0 + 8u * buf);
+              // rows y-1 and y of this tile are dead now; the strip's last tile frees its remaining two as well
+              const int nfree = (j == ntiles - 1) ? 4 : 2;
+              for (int i = 0; i < nfree; ++i) umma_commit(rowempty0 + 8u * ((g0 + 2u * j + i) % HL_RING));
+            }
+          }
+          __syncwarp();
+          ++t;
+        }
+        ++tc;
+      }
+      g0 += (uint32_t)c.rows + 2u;
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue ------------------------------
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    const int nsplit = (p.bn % 32 == 0) ? 2 : 1;
+    const int cb = nsplit == 2 ? half * (p.bn >> 1) : 0;
+    const int ce = nsplit == 2 ? cb + (p.bn >> 1) : (half == 0 ? p.bn : 0);
+    const float* sbias = p.e.bias_mode == 1 ? s_bias : nullptr;
+    uint32_t tc = 0;
+    for (int s = blockIdx.x; s < p.total_strips; s += gridDim.x) {
+      const StripCoord c = decode_strip(p, s);
+      const int ntiles = c.rows >> 1;
+      const int x = c.x0 + row;
+      for (int j = 0; j < ntiles; ++j) {
+        const uint32_t buf = tc & 1u;
+        mbar_wait(accfull0 + 8u * buf, (tc >> 1) & 1u);
+        tc_fence_after();
+        for (int r = 0; r < 2; ++r) {
+          const int y = c.ys + 2 * j + r;
+          const bool valid = x < p.w && y < p.h;
+          const int64_t pix = ((int64_t)c.img * p.h + y) * p.w + x;
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2u * (uint32_t)p.bn + (uint32_t)r * (uint32_t)p.bn;
+          if (p.e.residual)
+            epilogue_pixel_fast<true>(p.e, sbias, s_gamma, taddr, cb, ce, 0, valid, pix, &s_ss[buf][r][0][0], row, half, nsplit,
+                                      1 + q);
+          else
+            epilogue_pixel_fast<false>(p.e, sbias, s_gamma, taddr, cb, ce, 0, valid, pix, &s_ss[buf][r][0][0], row, half, nsplit,
+                                       1 + q);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(accempty0 + 8u * buf);
+        ++tc;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+int tc_encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                  const cuuint32_t* box, CUtensorMapSwizzle sw);  // rv_conv_tc.cu
+void fill_epi(EpiParams* e, const rv_conv_desc* d, const float* bias, const void* residual, void* y, const NormFuse* nf);
+
+static std::mutex g_halo_mu;
+static bool g_halo_attr[64] = {false};
+constexpr uint32_t HL_SMEM_MAX = 227 * 1024 - 6144;  // dynamic budget next to ~5.3 KB of static shared memory
+
+// Can this convolution run on the halo kernel?  (3x3 stride-1, Cout <= 128, operands fit the rings.)
+bool halo_eligible(const rv_conv_desc* d, const EpiParams& e) {
+  if (d->ksize != 3 || d->stride != 1 || d->upsample || d->pad_lo != 1) return false;
+  if (d->cin % 32 != 0 || d->cin < 64 || d->cout % 16 != 0 || d->cout > 128 || d->cout < 32) return false;
+  if (!e.fast || d->w < 64 || d->h < 2) return false;
+  const int nk128 = d->cin / 64, has64 = (d->cin % 64) ? 1 : 0;
+  const uint32_t row_slot = nk128 * HL_R128_BYTES + has64 * HL_R64_BYTES;
+  const uint32_t b_slot = ((uint32_t)d->cout * (uint32_t)d->cin * 2u + 1023u) & ~1023u;
+  return HL_RING * row_slot + HL_BRING * b_slot + 1024u <= HL_SMEM_MAX;
+}
+
+int launch_halo(const rv_conv_desc* d, const void* x, const void* w, int64_t w_ld, const float* bias, const void* residual,
+                void* y, cudaStream_t st, const NormFuse* nf) {
+  HaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_img = d->n;
+  p.h = d->h;
+  p.w = d->w;
+  p.cin = d->cin;
+  p.bn = d->cout;
+  p.nk128 = d->cin / 64;
+  p.has64 = (d->cin % 64) ? 1 : 0;
+  p.row_slot_bytes = p.nk128 * HL_R128_BYTES + p.has64 * HL_R64_BYTES;
+  p.r64_off = p.nk128 * HL_R128_BYTES;
+  p.row_tx_bytes = (uint32_t)HL_PIX * (uint32_t)(p.nk128 * 128 + p.has64 * 64);
+  p.b64_off = (uint32_t)p.nk128 * (uint32_t)p.bn * 128u;
+  p.b_tx_bytes = (uint32_t)p.bn * (uint32_t)d->cin * 2u;
+  p.b_slot_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
+  p.bring_off = HL_RING * p.row_slot_bytes;
+  p.col_blocks = (d->w + 127) / 128;
+  // strips: ~12 per SM, an even number of rows each, at least 8
+  int64_t cols = (int64_t)d->n * p.col_blocks;
+  int rows = (int)(((int64_t)d->h * cols + (int64_t)num_sms() * 12 - 1) / ((int64_t)num_sms() * 12));
+  rows = (rows + 1) & ~1;
+  if (rows < 8) rows = 8;
+  if (rows > d->h) rows = (d->h + 1) & ~1;
+  p.strip_rows = rows;
+  p.strips_per_col = (d->h + rows - 1) / rows;
+  p.total_strips = (int)(cols * p.strips_per_col);
+  fill_epi(&p.e, d, bias, residual, y, nf);
+  p.e.fast = 1;
+
+  CUtensorMap ma128, ma64, mb128, mb64;
+  const uint64_t pitch_b = (uint64_t)d->x_cstride * 2u;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
+    cuuint64_t str[3] = {pitch_b, pitch_b * d->w, pitch_b * d->w * d->h};
+    cuuint32_t box[4] = {64, (cuuint32_t)HL_PIX, 1, 1};
+    if (int rc = tc_encode_map(&ma128, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    cuuint32_t box64[4] = {32, (cuuint32_t)HL_PIX, 1, 1};
+    if (int rc = tc_encode_map(&ma64, x, 4, dims, str, box64, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)(9 * d->cin), (cuuint64_t)d->cout};
+    cuuint64_t str[1] = {(cuuint64_t)w_ld * 2u};
+    cuuint32_t box[2] = {64, (cuuint32_t)p.bn};
+    if (int rc = tc_encode_map(&mb128, w, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    cuuint32_t box64[2] = {32, (cuuint32_t)p.bn};
+    if (int rc = tc_encode_map(&mb64, w, 2, dims, str, box64, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+  }
+  const size_t smem = (size_t)HL_RING * p.row_slot_bytes + (size_t)HL_BRING * p.b_slot_bytes + 1024;
+  {
+    std::lock_guard<std::mutex> lk(g_halo_mu);
+    int dev = 0;
+    RV_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !g_halo_attr[dev]) {
+      RV_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HL_SMEM_MAX));
+      g_halo_attr[dev] = true;
+    }
+  }
+  int grid = p.total_strips < num_sms() ? p.total_strips : num_sms();
+  const double flops = 2.0 * (double)d->n * d->oh * d->ow * d->cout * d->cin * 9.0;
+  LaunchScope scope(CAT_CONV_TC, st, flops);
+  conv_halo_kernel<<<grid, HL_THREADS, smem, st>>>(ma128, ma64, mb128, mb64, p);
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace rv

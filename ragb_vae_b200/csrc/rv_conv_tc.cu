@@ -19,18 +19,20 @@
 // Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0     TMA producer      (one lane)   smem ring of `stages` {A,B} slots, mbarrier full/empty
 //   warp 1     tcgen05.mma issue (one lane)   fp32 accumulators in TMEM, double-buffered (2 x 256 cols)
-//   warps 2-5  epilogue          tcgen05.ld -> alpha, bias, residual, scale/shift, clamp -> global
-#include <cuda.h>
-
+//   warps 2-9  epilogue          tcgen05.ld -> alpha, bias, residual, scale/shift, clamp -> global
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 
-#include "rv_common.cuh"
+#include "rv_tc_common.cuh"
 
 namespace rv {
 
 int check_conv_desc(const rv_conv_desc* d);  // rv_conv_direct.cu
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;                      // two per TMEM lane quarter, each owning half of the tile's columns
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // + TMA warp + MMA warp
+constexpr int TC_SMEM_BIAS = 2048;                   // per-channel bias staged in shared memory up to this many channels
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_MAX_TAPS = 9;
 constexpr uint32_t TC_SMEM_BUDGET = 200 * 1024;
@@ -49,124 +51,12 @@ struct TcParams {
   int w_k_base;             // column offset into the weight matrix (upsample phase)
   signed char tap_dx[TC_MAX_TAPS], tap_dy[TC_MAX_TAPS], tap_wp[TC_MAX_TAPS], tap_hp[TC_MAX_TAPS];
   // output mapping: out pixel = tile pixel * os + oo
-  int out_h, out_w, osy, osx, ooy, oox;
-  int cout, y_cstride, y_nchw, y_f32;
-  int bias_mode, clamp;
-  int vec_ok;                // NHWC y / residual rows are 16-byte aligned: vector epilogue
-  float alpha, out_scale, out_shift, clamp_lo, clamp_hi;
-  const float* bias;
-  const __nv_bfloat16* residual;
-  void* y;
+  int osy, osx, ooy, oox;
+  EpiParams e;
   int stages;
   uint32_t a_bytes, stage_bytes, tx_bytes;
   uint32_t sbo_bytes, layout_type;
 };
-
-// ---------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// Spin on the phase parity.  A wait that lasts ~2 s of SM clocks is a protocol bug: trap so the
-// launch fails with an error instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  long long t0 = 0;
-  for (uint32_t it = 0;; ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-    if ((it & 1023u) == 1023u) {
-      long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ll) {
-        printf("rgbavae: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
-               (int)threadIdx.x, bar, parity);
-        __trap();
-      }
-    }
-  }
-}
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by one thread for the CTA.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// mbarrier arrive once all previously issued tcgen05.mma of this thread have completed.
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// Shared-memory matrix descriptor, K-major operand written by TMA with a 32/64/128-byte
-// swizzle (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
-// version=1 [46,48), layout [61,64)).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(sbo_bytes >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
 
 struct TileCoord {
   int img, y0, x0, n0;
@@ -184,6 +74,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
   return t;
 }
 
+template <int KSTEPS>  // BK / 16: 4 (128-byte rows), 2 (64-byte) or 1 (32-byte)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ TcParams p) {
@@ -193,6 +84,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __shared__ __align__(8) uint64_t bar_acc_full[2];
   __shared__ __align__(8) uint64_t bar_acc_empty[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_bias[TC_SMEM_BIAS];
+  __shared__ __align__(16) float s_gamma[256];
+  __shared__ float s_ss[2][2][128];  // [accumulator buffer][column half][tile row]: fused-norm partial sums
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -207,7 +101,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&bar_acc_full[a]), 1);
-      mbar_init(smem_u32(&bar_acc_empty[a]), 4);
+      mbar_init(smem_u32(&bar_acc_empty[a]), TC_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
@@ -220,82 +114,101 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  const bool bias_smem = p.e.fast && p.e.bias_mode == 1;
+  if (bias_smem)
+    for (int i = threadIdx.x; i < p.e.cout; i += TC_THREADS) s_bias[i] = p.e.bias[i];
+  if (p.e.norm_gamma)
+    for (int i = threadIdx.x; i < p.e.cout; i += TC_THREADS) s_gamma[i] = p.e.norm_gamma[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
+  // Both single-issuer roles keep their whole warp converged in the loop and elect one lane only around the
+  // asynchronous instructions.  (Running the loop under `if (lane == 0)` made ptxas wrap every UTCHMMA / UTMALDG in
+  // an ELECT + BRA.U.ANY uniformity loop fed through R2UR moves: ~130 dependent scalar instructions per k-block,
+  // i.e. ~215 cycles per MMA regardless of N -- the issue loop, not the tensor pipe, bounded every layer.)
+  const uint32_t bar_full0 = smem_u32(&bar_full[0]);
+  const uint32_t bar_empty0 = smem_u32(&bar_empty[0]);
+  const uint32_t bar_accf0 = smem_u32(&bar_acc_full[0]);
+  const uint32_t bar_acce0 = smem_u32(&bar_acc_empty[0]);
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          const int dx = p.tap_dx[tap], dy = p.tap_dy[tap];
-          const int kcol = p.w_k_base + tap * p.cin;
-          for (int kc = 0; kc < p.kc_per_tap; ++kc) {
-            const uint32_t full = smem_u32(&bar_full[stage]);
-            mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-            mbar_arrive_expect_tx(full, p.tx_bytes);
+    uint32_t stage = 0, phase = 0;
+    const uint32_t nstages = (uint32_t)p.stages;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        const int ax = t.x0 + p.tap_dx[tap], ay = t.y0 + p.tap_dy[tap];
+        const int kcol = p.w_k_base + tap * p.cin;
+        const int c5 = p.tap_wp[tap] * p.cin_pitch, hp = p.tap_hp[tap];
+        for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+          mbar_wait(bar_empty0 + 8u * stage, phase ^ 1u);
+          if (elect_one()) {
+            const uint32_t full = bar_full0 + 8u * stage;
             const uint32_t a_dst = smem_base + stage * p.stage_bytes;
-            const uint32_t b_dst = a_dst + p.a_bytes;
-            if (p.mode == 0)
-              tma_load_4d(a_dst, &map_a, full, kc * p.bk, t.x0 + dx, t.y0 + dy, t.img);
-            else
-              tma_load_5d(a_dst, &map_a, full, p.tap_wp[tap] * p.cin_pitch + kc * p.bk, t.x0 + dx, p.tap_hp[tap],
-                          t.y0 + dy, t.img);
-            tma_load_2d(b_dst, &map_b, full, kcol + kc * p.bk, t.n0);
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1u;
-            }
+            mbar_arrive_expect_tx(full, p.tx_bytes);
+            if (p.mode == 0) tma_load_4d(a_dst, &map_a, full, kc * p.bk, ax, ay, t.img);
+            else tma_load_5d(a_dst, &map_a, full, c5 + kc * p.bk, ax, hp, ay, t.img);
+            tma_load_2d(a_dst + p.a_bytes, &map_b, full, kcol + kc * p.bk, t.n0);
+          }
+          __syncwarp();
+          if (++stage == nstages) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
-      // cute::UMMA::InstrDescriptor: D fp32 (bit 4), A bf16 (bit 7), B bf16 (bit 10), both K-major,
-      // N>>3 at bit 17, M>>4 at bit 24.
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((128u >> 4) << 24);
-      const int ksteps = p.bk >> 4;
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
+    // cute::UMMA::InstrDescriptor: D fp32 (bit 4), A bf16 (bit 7), B bf16 (bit 10), both K-major,
+    // N>>3 at bit 17, M>>4 at bit 24.
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t desc_hi = make_smem_desc(0u, p.sbo_bytes, p.layout_type);
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    const uint32_t nstages = (uint32_t)p.stages;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(bar_acce0 + 8u * acc, acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 256u;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(bar_full0 + 8u * stage, phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(smem_u32(&bar_full[stage]), phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t a_addr = smem_base + stage * p.stage_bytes;
-          const uint64_t a_desc = make_smem_desc(a_addr, p.sbo_bytes, p.layout_type);
-          const uint64_t b_desc = make_smem_desc(a_addr + p.a_bytes, p.sbo_bytes, p.layout_type);
-          for (int k = 0; k < ksteps; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr>>4) field
-            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          const uint64_t a_desc = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
+          const uint64_t b_desc = desc_hi | (uint64_t)(((a_addr + p.a_bytes) & 0x3FFFFu) >> 4);
+          // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr>>4) field
+          umma_bf16(d_tmem, a_desc, b_desc, idesc, (uint32_t)(kb != 0));
+          if (KSTEPS > 1) umma_bf16(d_tmem, a_desc + 2u, b_desc + 2u, idesc, 1u);
+          if (KSTEPS > 2) {
+            umma_bf16(d_tmem, a_desc + 4u, b_desc + 4u, idesc, 1u);
+            umma_bf16(d_tmem, a_desc + 6u, b_desc + 6u, idesc, 1u);
           }
-          umma_commit(smem_u32(&bar_empty[stage]));
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          umma_commit(bar_empty0 + 8u * stage);
+          if (kb == num_kb - 1) umma_commit(bar_accf0 + 8u * acc);
         }
-        umma_commit(smem_u32(&bar_acc_full[acc]));
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        __syncwarp();
+        if (++stage == nstages) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
+      acc ^= 1u;
+      if (acc == 0) acc_phase ^= 1u;
     }
   } else {
     // ------------------------------ epilogue ------------------------------
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int q = warp & 3;                // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;      // which half of the tile's columns this warp owns
     const int row = q * 32 + lane;
     const int ly = row / p.bw, lx = row - ly * p.bw;
+    // column split between the two warps of a quarter (needs halves that are multiples of 16)
+    const int nsplit = (p.bn % 32 == 0) ? 2 : 1;
+    const int cb = nsplit == 2 ? half * (p.bn >> 1) : 0;
+    const int ce = nsplit == 2 ? cb + (p.bn >> 1) : (half == 0 ? p.bn : 0);
+    const float* sbias = bias_smem ? s_bias : nullptr;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -303,109 +216,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int ty = t.y0 + ly, tx = t.x0 + lx;
       const bool valid = ty < p.th && tx < p.tw;
       const int oy = ty * p.osy + p.ooy, ox = tx * p.osx + p.oox;
-      const int64_t pix = ((int64_t)t.img * p.out_h + oy) * p.out_w + ox;
-      mbar_wait(smem_u32(&bar_acc_full[acc]), acc_phase);
+      const int64_t pix = ((int64_t)t.img * p.e.out_h + oy) * p.e.out_w + ox;
+      mbar_wait(bar_accf0 + 8u * (uint32_t)acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
-      for (int c0 = 0; c0 < p.bn; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)c0, r);
-        tmem_ld_wait();
-        const int co0 = t.n0 + c0;
-        if (valid && co0 < p.cout) {
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-          const bool full16 = p.vec_ok && co0 + 16 <= p.cout;
-          if (p.bias_mode == 1) {
-            if (co0 + 16 <= p.cout) {
-              const float4* bp = reinterpret_cast<const float4*>(p.bias + co0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float4 b = __ldg(bp + j);
-                v[4 * j] += b.x;
-                v[4 * j + 1] += b.y;
-                v[4 * j + 2] += b.z;
-                v[4 * j + 3] += b.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (co0 + j < p.cout) v[j] += __ldg(p.bias + co0 + j);
-            }
-          } else if (p.bias_mode == 2) {
-            const float b = __ldg(p.bias + pix);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += b;
-          }
-          if (p.residual) {
-            const __nv_bfloat16* rp = p.residual + pix * p.y_cstride + co0;
-            if (full16) {
-              uint4 a = *reinterpret_cast<const uint4*>(rp);
-              uint4 b = *reinterpret_cast<const uint4*>(rp + 8);
-              const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                v[2 * j] += __uint_as_float(w[j] << 16);
-                v[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (co0 + j < p.cout) v[j] += __bfloat162float(rp[j]);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            v[j] = fmaf(v[j], p.out_scale, p.out_shift);
-            if (p.clamp) v[j] = fminf(fmaxf(v[j], p.clamp_lo), p.clamp_hi);
-          }
-          if (p.y_nchw) {
-            const int64_t plane = (int64_t)p.out_h * p.out_w;
-            const int64_t base = ((int64_t)t.img * p.cout + co0) * plane + (int64_t)oy * p.out_w + ox;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (co0 + j < p.cout) {
-                if (p.y_f32) reinterpret_cast<float*>(p.y)[base + j * plane] = v[j];
-                else reinterpret_cast<__nv_bfloat16*>(p.y)[base + j * plane] = __float2bfloat16_rn(v[j]);
-              }
-            }
-          } else if (p.y_f32) {
-            float* yp = reinterpret_cast<float*>(p.y) + pix * p.y_cstride + co0;
-            if (full16) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<float4*>(yp + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (co0 + j < p.cout) yp[j] = v[j];
-            }
-          } else {
-            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.y_cstride + co0;
-            if (full16) {
-              uint4 a, b;
-              a.x = pack_bf16x2(v[0], v[1]);
-              a.y = pack_bf16x2(v[2], v[3]);
-              a.z = pack_bf16x2(v[4], v[5]);
-              a.w = pack_bf16x2(v[6], v[7]);
-              b.x = pack_bf16x2(v[8], v[9]);
-              b.y = pack_bf16x2(v[10], v[11]);
-              b.z = pack_bf16x2(v[12], v[13]);
-              b.w = pack_bf16x2(v[14], v[15]);
-              *reinterpret_cast<uint4*>(yp) = a;
-              *reinterpret_cast<uint4*>(yp + 8) = b;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (co0 + j < p.cout) yp[j] = __float2bfloat16_rn(v[j]);
-            }
-          }
-        }
+      if (p.e.fast) {
+        if (p.e.residual)
+          epilogue_pixel_fast<true>(p.e, sbias, s_gamma, taddr, cb, ce, t.n0, valid, pix, &s_ss[acc][0][0], row, half,
+                                    nsplit, 1 + q);
+        else
+          epilogue_pixel_fast<false>(p.e, sbias, s_gamma, taddr, cb, ce, t.n0, valid, pix, &s_ss[acc][0][0], row, half,
+                                     nsplit, 1 + q);
+      } else {
+        epilogue_pixel(p.e, taddr, cb, ce, t.n0, valid, t.img, oy, ox, pix);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[acc]));
+      if (lane == 0) mbar_arrive(bar_acce0 + 8u * (uint32_t)acc);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -446,13 +273,15 @@ static int ensure_init() {
     RV_CUDA(cudaGetDeviceProperties(&prop, dev));
     RV_CHECK_ARG(prop.major == 10, "librgbavae needs an sm_100 GPU (found sm_%d%d); there is no fallback path", prop.major,
                  prop.minor);
-    RV_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 2048)));
+    RV_CUDA(cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 2048)));
+    RV_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 2048)));
+    RV_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 2048)));
     g_attr_set[dev] = true;
   }
   return 0;
 }
 
-static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+int tc_encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                       const cuuint32_t* box, CUtensorMapSwizzle sw) {
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
@@ -503,8 +332,46 @@ static void choose_bn(int cout, int* bn_out, int* n_tiles_out) {
   *n_tiles_out = best_t;
 }
 
+void fill_epi(EpiParams* e, const rv_conv_desc* d, const float* bias, const void* residual, void* y, const NormFuse* nf) {
+  e->out_h = d->oh;
+  e->out_w = d->ow;
+  e->cout = d->cout;
+  e->y_cstride = d->y_cstride;
+  e->y_nchw = d->y_nchw;
+  e->y_f32 = d->y_dtype == RV_F32;
+  e->bias_mode = d->bias_mode;
+  e->clamp = d->clamp;
+  e->alpha = d->alpha;
+  e->out_scale = d->out_scale;
+  e->out_shift = d->out_shift;
+  e->clamp_lo = d->clamp_lo;
+  e->clamp_hi = d->clamp_hi;
+  e->bias = bias;
+  e->residual = (const __nv_bfloat16*)residual;
+  e->y = y;
+  e->norm_gamma = nf ? nf->gamma_scaled : nullptr;
+  e->y_act = nf ? (__nv_bfloat16*)nf->y_act : nullptr;
+  e->norm_silu = nf ? nf->silu : 0;
+  e->fast = 0;  // decided by the launcher once the N tiling is known
+  e->vec_ok = (d->y_cstride % 8 == 0) && (!y || (uintptr_t)y % 16 == 0) && (!residual || (uintptr_t)residual % 16 == 0) &&
+              (!nf || (uintptr_t)nf->y_act % 16 == 0);
+}
+
+// preconditions of the lean epilogue (epilogue_pixel_fast)
+bool epi_fast_ok(const EpiParams& e, const rv_conv_desc* d, const float* bias, const NormFuse* nf, int covered_cols) {
+  return (d->bias_mode == 0 || d->cout <= TC_SMEM_BIAS) && e.vec_ok && !d->y_nchw && d->y_dtype == RV_BF16 &&
+         d->cout % 16 == 0 && covered_cols == d->cout && d->bias_mode != 2 && d->alpha == 1.0f && d->out_scale == 1.0f &&
+         d->out_shift == 0.0f && !d->clamp && (d->bias_mode == 0 || (uintptr_t)bias % 16 == 0) &&
+         (!nf || (uintptr_t)nf->gamma_scaled % 16 == 0);
+}
+
+bool halo_eligible(const rv_conv_desc* d, const EpiParams& e);  // rv_conv_halo.cu
+int launch_halo(const rv_conv_desc* d, const void* x, const void* w, int64_t w_ld, const float* bias, const void* residual,
+                void* y, cudaStream_t st, const NormFuse* nf);
+
 static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_t w_ld, const float* bias,
-                     const void* residual, void* y, cudaStream_t st, int phase /* -1: not upsample */) {
+                     const void* residual, void* y, cudaStream_t st, int phase /* -1: not upsample */,
+                     const NormFuse* nf = nullptr) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.n_img = d->n;
@@ -520,8 +387,6 @@ static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_
       p.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   p.layout_type = p.bk == 64 ? 2u : (p.bk == 32 ? 4u : 6u);
   p.sbo_bytes = 8u * (uint32_t)p.bk * 2u;
-  p.out_h = d->oh;
-  p.out_w = d->ow;
   p.osy = p.osx = 1;
   int k_extent;
   if (phase >= 0) {
@@ -563,21 +428,10 @@ static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_
   p.tiles_y = (p.th + p.bh - 1) / p.bh;
   p.m_tiles = d->n * p.tiles_x * p.tiles_y;
   choose_bn(d->cout, &p.bn, &p.n_tiles);
-  p.cout = d->cout;
-  p.y_cstride = d->y_cstride;
-  p.y_nchw = d->y_nchw;
-  p.y_f32 = d->y_dtype == RV_F32;
-  p.bias_mode = d->bias_mode;
-  p.clamp = d->clamp;
-  p.alpha = d->alpha;
-  p.out_scale = d->out_scale;
-  p.out_shift = d->out_shift;
-  p.clamp_lo = d->clamp_lo;
-  p.clamp_hi = d->clamp_hi;
-  p.bias = bias;
-  p.residual = (const __nv_bfloat16*)residual;
-  p.vec_ok = (d->y_cstride % 8 == 0) && ((uintptr_t)y % 16 == 0) && (!residual || (uintptr_t)residual % 16 == 0);
-  p.y = y;
+  RV_CHECK_ARG(!nf || p.n_tiles == 1, "conv_tc: fused norm needs all %d output channels in one tile (<= 256)", d->cout);
+  fill_epi(&p.e, d, bias, residual, y, nf);
+  p.e.fast = epi_fast_ok(p.e, d, bias, nf, p.bn * p.n_tiles);
+  RV_CHECK_ARG(!nf || p.e.fast, "conv_tc: fused norm needs cout %% 16 == 0, aligned NHWC bf16 tensors, per-channel bias, no affine");
   p.a_bytes = 128u * (uint32_t)p.bk * 2u;
   const uint32_t b_bytes = (uint32_t)p.bn * (uint32_t)p.bk * 2u;
   p.tx_bytes = p.a_bytes + b_bytes;
@@ -596,26 +450,28 @@ static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_
     cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
     cuuint64_t str[3] = {pitch_b, pitch_b * d->w, pitch_b * d->w * d->h};
     cuuint32_t box[4] = {(cuuint32_t)p.bk, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1};
-    if (int rc = encode_map(&map_a, x, 4, dims, str, box, sw)) return rc;
+    if (int rc = tc_encode_map(&map_a, x, 4, dims, str, box, sw)) return rc;
   } else {
     RV_CHECK_ARG(d->h % 2 == 0 && d->w % 2 == 0, "conv_tc: stride-2 conv needs even input size");
     cuuint64_t dims[5] = {(cuuint64_t)(2 * d->x_cstride), (cuuint64_t)(d->w / 2), 2, (cuuint64_t)(d->h / 2), (cuuint64_t)d->n};
     cuuint64_t str[4] = {2 * pitch_b, pitch_b * d->w, 2 * pitch_b * d->w, pitch_b * d->w * d->h};
     cuuint32_t box[5] = {(cuuint32_t)p.bk, (cuuint32_t)p.bw, 1, (cuuint32_t)p.bh, 1};
-    if (int rc = encode_map(&map_a, x, 5, dims, str, box, sw)) return rc;
+    if (int rc = tc_encode_map(&map_a, x, 5, dims, str, box, sw)) return rc;
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)k_extent, (cuuint64_t)d->cout};
     cuuint64_t str[1] = {(cuuint64_t)w_ld * 2u};
     cuuint32_t box[2] = {(cuuint32_t)p.bk, (cuuint32_t)p.bn};
-    if (int rc = encode_map(&map_b, w, 2, dims, str, box, sw)) return rc;
+    if (int rc = tc_encode_map(&map_b, w, 2, dims, str, box, sw)) return rc;
   }
   const int total_tiles = p.m_tiles * p.n_tiles;
   int grid = total_tiles < num_sms() ? total_tiles : num_sms();
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   const double flops = 2.0 * (double)d->n * d->oh * d->ow * d->cout * d->cin * d->ksize * d->ksize / (phase >= 0 ? 4.0 : 1.0);
   LaunchScope scope(CAT_CONV_TC, st, flops);
-  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+  if (p.bk == 64) conv_tc_kernel<4><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+  else if (p.bk == 32) conv_tc_kernel<2><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+  else conv_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
   RV_LAUNCH_CHECK();
   return 0;
 }
@@ -657,11 +513,11 @@ extern "C" {
 
 int rv_init(void) { return rv::ensure_init(); }
 
-int rv_conv2d_tc(const rv_conv_desc* d, const void* x, const void* w_packed, int64_t w_ld, const float* bias,
-                 const void* residual, void* y, void* stream) {
+static int conv2d_tc_impl(const rv_conv_desc* d, const void* x, const void* w_packed, int64_t w_ld, const float* bias,
+                          const void* residual, void* y, void* stream, const rv::NormFuse* nf) {
   if (int rc = rv::check_conv_desc(d)) return rc;
   if (int rc = rv::ensure_init()) return rc;
-  RV_CHECK_ARG(x && w_packed && y, "conv_tc: null tensor");
+  RV_CHECK_ARG(x && w_packed && (y || nf), "conv_tc: null tensor");
   RV_CHECK_ARG(d->x_dtype == RV_BF16 && !d->x_nchw, "conv_tc: x must be NHWC bf16");
   RV_CHECK_ARG(d->cin % 16 == 0, "conv_tc: cin (%d) must be a multiple of 16", d->cin);
   RV_CHECK_ARG(d->x_cstride % 8 == 0 && w_ld % 8 == 0, "conv_tc: x_cstride and w_ld must be multiples of 8");
@@ -671,13 +527,34 @@ int rv_conv2d_tc(const rv_conv_desc* d, const void* x, const void* w_packed, int
   RV_CHECK_ARG(!residual || (!d->y_nchw && d->y_dtype == RV_BF16), "conv_tc: residual needs an NHWC bf16 output");
   RV_CHECK_ARG(d->bias_mode != 1 || (uintptr_t)bias % 16 == 0, "conv_tc: bias must be 16-byte aligned");
   RV_CHECK_ARG(!(d->upsample && d->ksize != 3), "conv_tc: upsample requires ksize 3");
+  RV_CHECK_ARG(!nf || (nf->gamma_scaled && nf->y_act && !d->y_nchw && d->y_dtype == RV_BF16),
+               "conv_tc: fused norm needs gamma, y_act and an NHWC bf16 layout");
   cudaStream_t st = (cudaStream_t)stream;
   if (d->upsample) {
     for (int phase = 0; phase < 4; ++phase)
-      if (int rc = rv::launch_tc(d, x, w_packed, w_ld, bias, residual, y, st, phase)) return rc;
+      if (int rc = rv::launch_tc(d, x, w_packed, w_ld, bias, residual, y, st, phase, nf)) return rc;
     return 0;
   }
-  return rv::launch_tc(d, x, w_packed, w_ld, bias, residual, y, st, -1);
+  {
+    // narrow full-resolution 3x3 layers: halo-reuse kernel (rv_conv_halo.cu)
+    static const bool no_halo = getenv("RGBAVAE_DISABLE_HALO") != nullptr;
+    rv::EpiParams e;
+    rv::fill_epi(&e, d, bias, residual, y, nf);
+    e.fast = rv::epi_fast_ok(e, d, bias, nf, d->cout);
+    if (!no_halo && rv::halo_eligible(d, e)) return rv::launch_halo(d, x, w_packed, w_ld, bias, residual, y, st, nf);
+  }
+  return rv::launch_tc(d, x, w_packed, w_ld, bias, residual, y, st, -1, nf);
+}
+
+int rv_conv2d_tc(const rv_conv_desc* d, const void* x, const void* w_packed, int64_t w_ld, const float* bias,
+                 const void* residual, void* y, void* stream) {
+  return conv2d_tc_impl(d, x, w_packed, w_ld, bias, residual, y, stream, nullptr);
+}
+
+int rv_conv2d_tc_norm(const rv_conv_desc* d, const void* x, const void* w_packed, int64_t w_ld, const float* bias,
+                      const void* residual, void* y, void* y_act, const float* gamma_scaled, int apply_silu, void* stream) {
+  rv::NormFuse nf{gamma_scaled, y_act, apply_silu};
+  return conv2d_tc_impl(d, x, w_packed, w_ld, bias, residual, y, stream, &nf);
 }
 
 int rv_pack_conv_weights(const float* w, int cout, int cin, int ksize, int upsample, void* out_bf16, int64_t* w_ld,

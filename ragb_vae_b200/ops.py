@@ -96,6 +96,14 @@ def conv2d_tc(desc: ConvDesc, x, w_packed, w_ld: int, bias, residual, y) -> None
                                    _stream(x)), "rv_conv2d_tc")
 
 
+def conv2d_tc_norm(desc: ConvDesc, x, w_packed, w_ld: int, bias, residual, y, y_act, gamma_scaled, silu: bool) -> None:
+    """conv2d_tc with the consumer's RMS norm (+SiLU) fused into the epilogue; y may be None (activated output only)."""
+    _need_cuda(x, w_packed, bias, residual, y, y_act, gamma_scaled)
+    check(_lib.load().rv_conv2d_tc_norm(C.byref(desc), _ptr(x), _ptr(w_packed), int(w_ld), _ptr(bias), _ptr(residual),
+                                        _ptr(y), _ptr(y_act), _ptr(gamma_scaled), int(silu), _stream(x)),
+          "rv_conv2d_tc_norm")
+
+
 def pack_conv_weights_tc(w: torch.Tensor, upsample: bool = False) -> torch.Tensor:
     """fp32 [cout][cin][k][k] -> bf16 [cout][taps*cin] (upsample: [cout][16*cin], phase-folded)."""
     _need_cuda(w)

@@ -37,6 +37,7 @@ def d_sm(s, dt):
     return dict(shape=str(tuple(s.shape)), bytes=s.numel() * 6.0)
 
 ops.conv2d_tc = wrap("conv_tc", ops.conv2d_tc, d_conv)
+ops.conv2d_tc_norm = wrap("conv_tc+norm", ops.conv2d_tc_norm, d_conv)
 ops.conv2d_direct = wrap("conv_direct", ops.conv2d_direct, d_conv)
 ops.rmsnorm_silu = wrap("rmsnorm", ops.rmsnorm_silu, d_norm)
 ops.groupnorm_silu = wrap("groupnorm", ops.groupnorm_silu, d_gn)

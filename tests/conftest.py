@@ -15,8 +15,9 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def lib_built():
     """Builds librgbavae.so if nvcc is here and the library is stale (no-op on the GPU box)."""
-    from ragb_vae_b200 import build as B
+    import __graft_entry__ as G
 
+    B = G._load_builder()
     try:
         B.build()
     except RuntimeError:

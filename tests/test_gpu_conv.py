@@ -41,6 +41,10 @@ CASES = [  # n, h, w, cin, cout, k, stride, upsample
     (1, 32, 32, 96, 4, 3, 1, False),       # conv_out: Cout=4 padded to one 16-wide tile
     (1, 128, 130, 64, 32, 3, 1, False),    # 128-wide tiles with a ragged edge
     (3, 8, 8, 512, 512, 3, 1, False),      # two 256-wide N tiles, deep K
+    (2, 20, 200, 96, 96, 3, 1, False),     # halo-reuse kernel: two column blocks (ragged), SW128 + SW64 K blocks
+    (1, 9, 130, 96, 96, 3, 1, False),      # halo-reuse kernel: odd height (masked last row), 2-pixel second block
+    (1, 12, 256, 64, 128, 3, 1, False),    # halo-reuse kernel: Cin = 64 (no SW64 block), Cout = 128
+    (2, 70, 128, 96, 32, 3, 1, False),     # halo-reuse kernel: several strips per column, narrow Cout
 ]
 
 
@@ -129,3 +133,39 @@ def test_tc_rejects_bad_arguments(ops):
     d.oh = 7
     with pytest.raises(RvError):
         ops.conv2d_direct(d, x, w.float(), None, None, y)  # inconsistent output size
+
+
+@pytest.mark.parametrize("w", [40, 136])  # 136 columns: the halo-reuse kernel takes the Cout <= 128 cases
+@pytest.mark.parametrize("cout,want_raw,silu", [(96, True, True), (192, False, True), (96, True, False)])
+def test_tc_conv_fused_rmsnorm_epilogue(ops, cout, want_raw, silu, w):
+    """rv_conv2d_tc_norm: the consumer's QwenImageRMS_norm (+SiLU) applied in the conv epilogue."""
+    import math
+
+    g = torch.Generator().manual_seed(cout + int(want_raw))
+    n, h, cin = 2, 12, 96
+    x = torch.randn(n, cin, h, w, generator=g).bfloat16()
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).bfloat16().float()
+    b = torch.randn(cout, generator=g)
+    res = torch.randn(n, h, w, cout, generator=g).bfloat16()
+    gamma = torch.rand(cout, generator=g) + 0.5
+    raw_ref = (ref_conv(x.float(), wt, b, 3, 1, False) + res.float().permute(0, 3, 1, 2))
+    nrm = raw_ref / raw_ref.norm(dim=1, keepdim=True).clamp_min(1e-12) * math.sqrt(cout) * gamma.view(1, -1, 1, 1)
+    act_ref = F.silu(nrm) if silu else nrm
+    wp = ops.pack_conv_weights_tc(wt.cuda())
+    xh = x.permute(0, 2, 3, 1).contiguous().cuda()
+    y = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device="cuda") if want_raw else None
+    act = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device="cuda")
+    d = ops.make_desc(n, h, w, cin, cout, 3, 1, False, x_dtype=RV_BF16, y_dtype=RV_BF16)
+    ops.conv2d_tc_norm(d, xh, wp, wp.shape[1], b.cuda(), res.cuda(), y, act, (gamma * math.sqrt(cout)).cuda(), silu)
+    assert rel(act.float().permute(0, 3, 1, 2), act_ref) < 5e-3
+    if want_raw:
+        assert rel(y.float().permute(0, 3, 1, 2), raw_ref) < 4e-3
+    # more than 256 output channels cannot be fused (two accumulator tiles)
+    from ragb_vae_b200._lib import RvError
+
+    d2 = ops.make_desc(1, 8, 8, 96, 384, 3, 1, False, x_dtype=RV_BF16, y_dtype=RV_BF16)
+    w2 = torch.zeros(384, 9 * 96, dtype=torch.bfloat16, device="cuda")
+    y2 = torch.empty(1, 8, 8, 384, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(RvError):
+        ops.conv2d_tc_norm(d2, xh[:1, :8, :8].contiguous(), w2, 9 * 96, torch.zeros(384, device="cuda"), None, y2, y2.clone(),
+                           torch.ones(384, device="cuda"), True)

@@ -1,0 +1,59 @@
+"""The N>1 path on CPU: world_size-2 gloo processes shard bucket-pure batches with no data-path
+collective, agree on max-over-ranks time and gather ragged per-sample metrics."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ragb_vae_b200 import sharding as S
+
+    shapes = S.sample_bucket_batches(41, 8, seed=1234)
+    owned = S.assign_batches(shapes, world)
+    mine = owned[rank]
+    # every rank computes the same partition; it is disjoint and complete
+    flat = sorted(i for r in owned for i in r)
+    assert flat == list(range(len(shapes)))
+    # balanced within one batch of the mean
+    loads = [sum(S.batch_cost(shapes[i]) for i in r) for r in owned]
+    assert max(loads) - min(loads) <= max(S.batch_cost(s) for s in shapes) + 1e-9
+    # job time = slowest rank
+    t = S.max_over_ranks(10.0 + rank, torch.device("cpu"))
+    assert t == 10.0 + (world - 1)
+    # ragged per-sample gather: rank r contributes one value per owned batch
+    metric = torch.tensor([float(i) for i in mine])
+    allm = S.gather_per_sample(metric)
+    assert sorted(allm.tolist()) == [float(i) for i in range(len(shapes))]
+    # units processed by the whole job (the numerator of the weak-scaling metric)
+    pix = torch.tensor([sum(b * h * w for (b, h, w) in (shapes[i] for i in mine))], dtype=torch.float64)
+    dist.all_reduce(pix)
+    assert pix.item() == sum(b * h * w for (b, h, w) in shapes)
+    open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_sharding(tmp_path, lib_built):
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_assignment_properties(lib_built):
+    from ragb_vae_b200 import sharding as S
+
+    shapes = S.sample_bucket_batches(256, 8)
+    assert all(h % 32 == 0 and w % 32 == 0 and h * w <= 1048576 for _, h, w in shapes)
+    frac_1024 = sum(1 for _, h, w in shapes if h == 1024 and w == 1024) / len(shapes)
+    assert 0.7 < frac_1024 < 0.95
+    for world in (1, 2, 4, 8):
+        owned = S.assign_batches(shapes, world)
+        assert sorted(i for r in owned for i in r) == list(range(256))
+        loads = [sum(S.batch_cost(shapes[i]) for i in r) for r in owned]
+        assert max(loads) / (sum(loads) / world) < 1.05
+    with pytest.raises(ValueError):
+        S.assign_batches(shapes, 0)
