@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 3
+#define RV_ABI_VERSION 4
 #define RV_PROF_CATEGORIES 9
 
 int rv_abi_version(void);
@@ -129,6 +129,12 @@ int rv_nchw_to_nhwc(const void* x, void* y, int n, int c, int64_t hw, int c_pad,
                     int y_dtype, float scale, float shift, void* stream);
 int rv_nhwc_to_nchw(const void* x, void* y, int n, int c, int64_t hw, int x_cstride, int x_dtype,
                     int y_dtype, void* stream);
+
+/* 3x3 / pad-1 im2col of a few-channel NCHW boundary image (the 4-channel RGBA input of conv_in,
+ * src/models/rgba_vae.py:277 with _to_vae_range fused as scale/shift) into NHWC rows of `kpad` elements:
+ * y[n][h][w][tap*c + ch], zeros outside the image and past 9*c.  conv_in then is a K=kpad GEMM. */
+int rv_im2col3x3(const void* x, void* y, int n, int c, int h, int w, int kpad, int x_dtype, int y_dtype,
+                 float scale, float shift, void* stream);
 
 /* ---- posterior (diffusers DiagonalGaussianDistribution; src/models/rgba_vae.py:278) ------ */
 /* moments NCHW [n][2*zc][hw]; noise / z NCHW [n][zc][hw].

@@ -61,6 +61,7 @@ __device__ __forceinline__ StripCoord decode_strip(const HaloParams& p, int s) {
   return c;
 }
 
+template <int NK128, int HAS64>  // K blocks per tap: NK128 x 64 channels (+ 32 channels)
 __global__ void __launch_bounds__(HL_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a128, const __grid_constant__ CUtensorMap map_a64,
                  const __grid_constant__ CUtensorMap map_b128, const __grid_constant__ CUtensorMap map_b64,
@@ -106,10 +107,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a128, const __grid_cons
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (p.e.bias_mode == 1)
-    for (int i = threadIdx.x; i < p.bn; i += HL_THREADS) s_bias[i] = p.e.bias[i];
+  if (p.e.fast && p.e.bias_mode == 1)
+    for (int i = threadIdx.x; i < p.e.cout; i += HL_THREADS) s_bias[i] = p.e.bias[i];
   if (p.e.norm_gamma)
-    for (int i = threadIdx.x; i < p.bn; i += HL_THREADS) s_gamma[i] = p.e.norm_gamma[i];
+    for (int i = threadIdx.x; i < p.e.cout; i += HL_THREADS) s_gamma[i] = p.e.norm_gamma[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -163,46 +164,57 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a128, const __grid_cons
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
+    // Everything that can be hoisted is: the four live row-slot addresses per tile, the weight-slot address
+    // (advanced incrementally), descriptor high words; the 9 taps are unrolled so (dy, dx) are immediates.
+    // (Uniform-datapath integer ops cost ~10 cycles each when dependent: an un-hoisted loop body of ~77 of them
+    // per 6 MMAs made this warp, not the tensor pipe, the bound.)
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((128u >> 4) << 24);
     const uint64_t hi128 = make_smem_desc(0u, 1024u, 2u);
     const uint64_t hi64 = make_smem_desc(0u, 512u, 4u);
-    uint32_t g0 = 0, t = 0, tc = 0;
+    const uint32_t bn = (uint32_t)p.bn;
+    const uint32_t b64_lo = p.b64_off >> 4, r64_lo = p.r64_off >> 4;
+    uint32_t g0 = 0, tc = 0;
+    uint32_t bslot = 0, bpar = 0;
     for (int s = blockIdx.x; s < p.total_strips; s += gridDim.x) {
       const StripCoord c = decode_strip(p, s);
       const int ntiles = c.rows >> 1;
       for (int j = 0; j < ntiles; ++j) {
         const uint32_t buf = tc & 1u;
         mbar_wait(accempty0 + 8u * buf, ((tc >> 1) & 1u) ^ 1u);
-        for (int i = (j == 0 ? 0 : 2); i < 4; ++i) {
+        uint32_t a_lo[4], rslot[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
           const uint32_t g = g0 + 2u * j + i;
-          mbar_wait(rowfull0 + 8u * (g % HL_RING), (g / HL_RING) & 1u);
+          rslot[i] = g % HL_RING;
+          a_lo[i] = ((ring + rslot[i] * p.row_slot_bytes) & 0x3FFFFu) >> 4;
+          if (j == 0 || i >= 2) mbar_wait(rowfull0 + 8u * rslot[i], (g / HL_RING) & 1u);
         }
         tc_fence_after();
+        const uint32_t d0 = tmem_base + buf * 2u * bn, d1 = d0 + bn;
+#pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int dy = tap / 3, dx = tap - 3 * dy;
-          const uint32_t bslot = t % HL_BRING;
-          mbar_wait(bfull0 + 8u * bslot, (t / HL_BRING) & 1u);
+          mbar_wait(bfull0 + 8u * bslot, bpar);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t b_addr = bring + bslot * p.b_slot_bytes;
+            const uint32_t b_lo = ((bring + bslot * p.b_slot_bytes) & 0x3FFFFu) >> 4;
+#pragma unroll
             for (int r = 0; r < 2; ++r) {
-              const uint32_t g = g0 + 2u * j + r + dy;
-              const uint32_t a_addr = ring + (g % HL_RING) * p.row_slot_bytes;
-              const uint32_t d_tmem = tmem_base + buf * 2u * (uint32_t)p.bn + (uint32_t)r * (uint32_t)p.bn;
-              uint32_t first = (tap == 0) ? 0u : 1u;
-              for (int kb = 0; kb < p.nk128; ++kb) {
-                const uint64_t ad = hi128 | (uint64_t)(((a_addr + kb * HL_R128_BYTES + dx * 128u) & 0x3FFFFu) >> 4);
-                const uint64_t bd = hi128 | (uint64_t)(((b_addr + kb * (uint32_t)p.bn * 128u) & 0x3FFFFu) >> 4);
-                umma_bf16(d_tmem, ad, bd, idesc, first);
+              const uint32_t d_tmem = r ? d1 : d0;
+              const uint32_t ar = a_lo[dy + r];
+#pragma unroll
+              for (int kb = 0; kb < NK128; ++kb) {
+                const uint64_t ad = hi128 | (uint64_t)(ar + kb * (HL_R128_BYTES >> 4) + dx * 8u);
+                const uint64_t bd = hi128 | (uint64_t)(b_lo + kb * bn * 8u);
+                umma_bf16(d_tmem, ad, bd, idesc, (tap == 0 && kb == 0) ? 0u : 1u);
                 umma_bf16(d_tmem, ad + 2u, bd + 2u, idesc, 1u);
                 umma_bf16(d_tmem, ad + 4u, bd + 4u, idesc, 1u);
                 umma_bf16(d_tmem, ad + 6u, bd + 6u, idesc, 1u);
-                first = 1u;
               }
-              if (p.has64) {
-                const uint64_t ad = hi64 | (uint64_t)(((a_addr + p.r64_off + dx * 64u) & 0x3FFFFu) >> 4);
-                const uint64_t bd = hi64 | (uint64_t)(((b_addr + p.b64_off) & 0x3FFFFu) >> 4);
-                umma_bf16(d_tmem, ad, bd, idesc, first);
+              if (HAS64) {
+                const uint64_t ad = hi64 | (uint64_t)(ar + r64_lo + dx * 4u);
+                const uint64_t bd = hi64 | (uint64_t)(b_lo + b64_lo);
+                umma_bf16(d_tmem, ad, bd, idesc, (tap == 0 && NK128 == 0) ? 0u : 1u);
                 umma_bf16(d_tmem, ad + 2u, bd + 2u, idesc, 1u);
               }
             }
@@ -210,12 +222,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a128, const __grid_cons
             if (tap == 8) {
               umma_commit(accfull0 + 8u * buf);
               // rows y-1 and y of this tile are dead now; the strip's last tile frees its remaining two as well
-              const int nfree = (j == ntiles - 1) ? 4 : 2;
-              for (int i = 0; i < nfree; ++i) umma_commit(rowempty0 + 8u * ((g0 + 2u * j + i) % HL_RING));
+              umma_commit(rowempty0 + 8u * rslot[0]);
+              umma_commit(rowempty0 + 8u * rslot[1]);
+              if (j == ntiles - 1) {
+                umma_commit(rowempty0 + 8u * rslot[2]);
+                umma_commit(rowempty0 + 8u * rslot[3]);
+              }
             }
           }
           __syncwarp();
-          ++t;
+          if (++bslot == HL_BRING) {
+            bslot = 0;
+            bpar ^= 1u;
+          }
         }
         ++tc;
       }
@@ -244,7 +263,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a128, const __grid_cons
           const bool valid = x < p.w && y < p.h;
           const int64_t pix = ((int64_t)c.img * p.h + y) * p.w + x;
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2u * (uint32_t)p.bn + (uint32_t)r * (uint32_t)p.bn;
-          if (p.e.residual)
+          if (!p.e.fast)  // NCHW / fp32 / affine / clamp outputs (conv_out): generic epilogue
+            epilogue_pixel(p.e, taddr, cb, ce, 0, valid, c.img, y, x, pix);
+          else if (p.e.residual)
             epilogue_pixel_fast<true>(p.e, sbias, s_gamma, taddr, cb, ce, 0, valid, pix, &s_ss[buf][r][0][0], row, half, nsplit,
                                       1 + q);
           else
@@ -274,6 +295,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a128, const __grid_cons
 int tc_encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                   const cuuint32_t* box, CUtensorMapSwizzle sw);  // rv_conv_tc.cu
 void fill_epi(EpiParams* e, const rv_conv_desc* d, const float* bias, const void* residual, void* y, const NormFuse* nf);
+bool epi_fast_ok(const EpiParams& e, const rv_conv_desc* d, const float* bias, const NormFuse* nf, int covered_cols);
 
 static std::mutex g_halo_mu;
 static bool g_halo_attr[64] = {false};
@@ -282,11 +304,12 @@ constexpr uint32_t HL_SMEM_MAX = 227 * 1024 - 6144;  // dynamic budget next to ~
 // Can this convolution run on the halo kernel?  (3x3 stride-1, Cout <= 128, operands fit the rings.)
 bool halo_eligible(const rv_conv_desc* d, const EpiParams& e) {
   if (d->ksize != 3 || d->stride != 1 || d->upsample || d->pad_lo != 1) return false;
-  if (d->cin % 32 != 0 || d->cin < 64 || d->cout % 16 != 0 || d->cout > 128 || d->cout < 32) return false;
-  if (!e.fast || d->w < 64 || d->h < 2) return false;
+  if (!(d->cin == 64 || d->cin == 96 || d->cin == 128) || d->cout > 128) return false;
+  if (e.norm_gamma && !e.fast) return false;
+  if (d->bias_mode == 2 || d->w < 64 || d->h < 2) return false;
   const int nk128 = d->cin / 64, has64 = (d->cin % 64) ? 1 : 0;
   const uint32_t row_slot = nk128 * HL_R128_BYTES + has64 * HL_R64_BYTES;
-  const uint32_t b_slot = ((uint32_t)d->cout * (uint32_t)d->cin * 2u + 1023u) & ~1023u;
+  const uint32_t b_slot = ((uint32_t)((d->cout + 15) / 16 * 16) * (uint32_t)d->cin * 2u + 1023u) & ~1023u;
   return HL_RING * row_slot + HL_BRING * b_slot + 1024u <= HL_SMEM_MAX;
 }
 
@@ -298,14 +321,14 @@ int launch_halo(const rv_conv_desc* d, const void* x, const void* w, int64_t w_l
   p.h = d->h;
   p.w = d->w;
   p.cin = d->cin;
-  p.bn = d->cout;
+  p.bn = (d->cout + 15) / 16 * 16;
   p.nk128 = d->cin / 64;
   p.has64 = (d->cin % 64) ? 1 : 0;
   p.row_slot_bytes = p.nk128 * HL_R128_BYTES + p.has64 * HL_R64_BYTES;
   p.r64_off = p.nk128 * HL_R128_BYTES;
   p.row_tx_bytes = (uint32_t)HL_PIX * (uint32_t)(p.nk128 * 128 + p.has64 * 64);
   p.b64_off = (uint32_t)p.nk128 * (uint32_t)p.bn * 128u;
-  p.b_tx_bytes = (uint32_t)p.bn * (uint32_t)d->cin * 2u;
+  p.b_tx_bytes = (uint32_t)p.bn * (uint32_t)d->cin * 2u;  // full box bytes (rows past cout are zero-filled)
   p.b_slot_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
   p.bring_off = HL_RING * p.row_slot_bytes;
   p.col_blocks = (d->w + 127) / 128;
@@ -319,7 +342,7 @@ int launch_halo(const rv_conv_desc* d, const void* x, const void* w, int64_t w_l
   p.strips_per_col = (d->h + rows - 1) / rows;
   p.total_strips = (int)(cols * p.strips_per_col);
   fill_epi(&p.e, d, bias, residual, y, nf);
-  p.e.fast = 1;
+  p.e.fast = epi_fast_ok(p.e, d, bias, nf, p.bn) ? 1 : 0;
 
   CUtensorMap ma128, ma64, mb128, mb64;
   const uint64_t pitch_b = (uint64_t)d->x_cstride * 2u;
@@ -345,14 +368,18 @@ int launch_halo(const rv_conv_desc* d, const void* x, const void* w, int64_t w_l
     int dev = 0;
     RV_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !g_halo_attr[dev]) {
-      RV_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HL_SMEM_MAX));
+      RV_CUDA(cudaFuncSetAttribute(conv_halo_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HL_SMEM_MAX));
+      RV_CUDA(cudaFuncSetAttribute(conv_halo_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HL_SMEM_MAX));
+      RV_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HL_SMEM_MAX));
       g_halo_attr[dev] = true;
     }
   }
   int grid = p.total_strips < num_sms() ? p.total_strips : num_sms();
   const double flops = 2.0 * (double)d->n * d->oh * d->ow * d->cout * d->cin * 9.0;
   LaunchScope scope(CAT_CONV_TC, st, flops);
-  conv_halo_kernel<<<grid, HL_THREADS, smem, st>>>(ma128, ma64, mb128, mb64, p);
+  if (p.nk128 == 1 && !p.has64) conv_halo_kernel<1, 0><<<grid, HL_THREADS, smem, st>>>(ma128, ma64, mb128, mb64, p);
+  else if (p.nk128 == 1 && p.has64) conv_halo_kernel<1, 1><<<grid, HL_THREADS, smem, st>>>(ma128, ma64, mb128, mb64, p);
+  else conv_halo_kernel<2, 0><<<grid, HL_THREADS, smem, st>>>(ma128, ma64, mb128, mb64, p);
   RV_LAUNCH_CHECK();
   return 0;
 }

@@ -168,17 +168,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint64_t desc_hi = make_smem_desc(0u, p.sbo_bytes, p.layout_type);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     const uint32_t nstages = (uint32_t)p.stages;
+    // operand addresses advance incrementally (no multiplies / modulo in the issue loop)
+    const uint32_t a_lo0 = (smem_base & 0x3FFFFu) >> 4, stage_lo = p.stage_bytes >> 4, ab_lo = p.a_bytes >> 4;
+    uint32_t a_lo = a_lo0, full_bar = bar_full0, empty_bar = bar_empty0;
+    const int last_kb = num_kb - 1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       mbar_wait(bar_acce0 + 8u * acc, acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * 256u;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(bar_full0 + 8u * stage, phase);
+        mbar_wait(full_bar, phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t a_addr = smem_base + stage * p.stage_bytes;
-          const uint64_t a_desc = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
-          const uint64_t b_desc = desc_hi | (uint64_t)(((a_addr + p.a_bytes) & 0x3FFFFu) >> 4);
+          const uint64_t a_desc = desc_hi | (uint64_t)a_lo;
+          const uint64_t b_desc = desc_hi | (uint64_t)(a_lo + ab_lo);
           // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr>>4) field
           umma_bf16(d_tmem, a_desc, b_desc, idesc, (uint32_t)(kb != 0));
           if (KSTEPS > 1) umma_bf16(d_tmem, a_desc + 2u, b_desc + 2u, idesc, 1u);
@@ -186,13 +189,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             umma_bf16(d_tmem, a_desc + 4u, b_desc + 4u, idesc, 1u);
             umma_bf16(d_tmem, a_desc + 6u, b_desc + 6u, idesc, 1u);
           }
-          umma_commit(bar_empty0 + 8u * stage);
-          if (kb == num_kb - 1) umma_commit(bar_accf0 + 8u * acc);
+          umma_commit(empty_bar);
+          if (kb == last_kb) umma_commit(bar_accf0 + 8u * acc);
         }
         __syncwarp();
+        a_lo += stage_lo;
+        full_bar += 8u;
+        empty_bar += 8u;
         if (++stage == nstages) {
           stage = 0;
           phase ^= 1u;
+          a_lo = a_lo0;
+          full_bar = bar_full0;
+          empty_bar = bar_empty0;
         }
       }
       acc ^= 1u;

@@ -41,6 +41,10 @@ ops.conv2d_tc_norm = wrap("conv_tc+norm", ops.conv2d_tc_norm, d_conv)
 ops.conv2d_direct = wrap("conv_direct", ops.conv2d_direct, d_conv)
 ops.rmsnorm_silu = wrap("rmsnorm", ops.rmsnorm_silu, d_norm)
 ops.groupnorm_silu = wrap("groupnorm", ops.groupnorm_silu, d_gn)
+ops.im2col3x3 = wrap("im2col", ops.im2col3x3, lambda x, kpad, dt, *a: dict(shape=str(tuple(x.shape)), bytes=x.numel() * x.element_size() + x.numel() // x.shape[1] * kpad * 2.0))
+ops.nchw_to_nhwc = wrap("nchw2nhwc", ops.nchw_to_nhwc, lambda x, cp, dt, *a: dict(shape=str(tuple(x.shape)), bytes=x.numel() * x.element_size() * (1 + cp / x.shape[1])))
+ops.reparam = wrap("reparam", ops.reparam, lambda m, *a, **k: dict(shape=str(tuple(m.shape)), bytes=m.numel() * m.element_size() * 2.0))
+ops.composite_psnr = wrap("psnr", ops.composite_psnr, lambda r, t, b: dict(shape=str(tuple(r.shape)), bytes=2.0 * r.numel() * r.element_size()))
 ops.softmax_rows = wrap("softmax", ops.softmax_rows, d_sm)
 
 torch.manual_seed(0)
@@ -49,7 +53,8 @@ x = torch.rand(B, 4, S, S, device="cuda").bfloat16()
 noise = torch.randn(B, 16, S // 8, S // 8, device="cuda").bfloat16()
 for _ in range(2):
     recs.clear()
-    model(x, noise=noise)
+    recon, _ = model(x, noise=noise)
+    ops.composite_psnr(recon, x, [(1.0, 1.0, 1.0)])
 torch.cuda.synchronize()
 agg = {}
 tot = 0.0

@@ -45,6 +45,7 @@ CASES = [  # n, h, w, cin, cout, k, stride, upsample
     (1, 9, 130, 96, 96, 3, 1, False),      # halo-reuse kernel: odd height (masked last row), 2-pixel second block
     (1, 12, 256, 64, 128, 3, 1, False),    # halo-reuse kernel: Cin = 64 (no SW64 block), Cout = 128
     (2, 70, 128, 96, 32, 3, 1, False),     # halo-reuse kernel: several strips per column, narrow Cout
+    (1, 16, 192, 96, 4, 3, 1, False),      # halo-reuse kernel as conv_out: Cout = 4, generic (NCHW / clamp) epilogue
 ]
 
 
