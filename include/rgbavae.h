@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 4
+#define RV_ABI_VERSION 5
 #define RV_PROF_CATEGORIES 9
 
 int rv_abi_version(void);
@@ -122,6 +122,13 @@ int rv_groupnorm_silu(const void* x, const double* stats, const float* gamma, co
 /* Row softmax of fp32 scores [rows][cols] (already scaled) into probabilities of `dtype`. */
 int rv_softmax_rows(const float* s, void* p, int64_t rows, int64_t cols, int64_t ld_s, int64_t ld_p,
                     int dtype, void* stream);
+
+/* Fused single-head attention O = softmax(Q K^T / sqrt(d)) V for d = 384 (QwenImageAttentionBlock): scores and
+ * probabilities stay in TMEM / shared memory.  q, k: bf16 [n_img*tokens][ld_qk] (row pitch in elements; q and k may
+ * be column slices of one tensor); vt: bf16 V transposed, [n_img][d][tokens]; out: bf16 [n_img*tokens][ld_out].
+ * tokens % 128 == 0. */
+int rv_attention(const void* q, const void* k, int64_t ld_qk, const void* vt, void* out, int64_t ld_out,
+                 int n_img, int tokens, int d, void* stream);
 
 /* ---- layout plumbing at the NCHW boundary ----------------------------------------------- */
 /* y[n][hw][c_pad] = x[n][c][hw]*scale+shift (extra channels zero). */

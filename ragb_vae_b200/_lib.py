@@ -9,7 +9,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "librgbavae.so")
 
 RV_F32, RV_BF16 = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 PROF_CATEGORIES = 9
 PROF_NAMES = ("conv_tc", "conv_direct", "norm_silu", "softmax", "layout", "reparam", "recon_loss", "composite_psnr",
               "attention")
@@ -58,6 +58,7 @@ SIGNATURES = {
     "rv_groupnorm_stats": (_I, [_P, _P, _I, _L, _I, _I, _I, _P]),
     "rv_groupnorm_silu": (_I, [_P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _I, _I, _P]),
     "rv_softmax_rows": (_I, [_P, _P, _L, _L, _L, _L, _I, _P]),
+    "rv_attention": (_I, [_P, _P, _L, _P, _P, _L, _I, _I, _I, _P]),
     "rv_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _L, _I, _I, _I, _F, _F, _P]),
     "rv_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _L, _I, _I, _I, _P]),
     "rv_im2col3x3": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),

@@ -306,6 +306,7 @@ class RgbaAutoencoder(nn.Module):
         self.use_slicing = False
         self.gradient_checkpointing = False
         self.fuse_norm_residual = False
+        self.fused_attention = True
         self.im2col_stem = False  # measured slower (3.5 ms) than 16-channel padding + 9 narrow K blocks (2.6 ms) at 8x1024^2
         self.fuse_norm = True  # RMS norm + SiLU in the producing conv's epilogue where one tile holds all channels
         self._pack_cache: Dict[tuple, tuple] = {}
@@ -573,6 +574,22 @@ class RgbaAutoencoder(nn.Module):
             self._gemm(xn2, pk["wq"], rows=n * t, k=c, cols=c, x_ld=c, w_ld=c, y=q_all, y_ld=c, bias=pk["bq"], bias_mode=1)
             self._gemm(xn2, pk["wk"], rows=n * t, k=c, cols=c, x_ld=c, w_ld=c, y=k_all, y_ld=c, bias=pk["bk"], bias_mode=1)
             ld_qk = c
+        if tc and self.fused_attention and c == ops.FUSED_ATTENTION_D and t % 128 == 0:
+            # flash-style kernel: scores / probabilities never reach HBM
+            vt_all = torch.empty((n, c, t), dtype=act_dt, device=dev)
+            for i in range(n):
+                self._gemm(pk["wv"], xn2[i * t:(i + 1) * t], rows=c, k=c, cols=t, x_ld=c, w_ld=c, y=vt_all[i], y_ld=t,
+                           bias=pk["bv"], bias_mode=2)
+            o = ops.attention(q_all[:, :c], k_all[:, :c], vt_all, n, t)
+        else:
+            self._attention_unfused(pk, xn2, q_all, k_all, ld_qk, o, n, t, c, scale, act_dt, dev)
+        out = torch.empty_like(x)
+        self._gemm(o, pk["wo"], rows=n * t, k=c, cols=c, x_ld=c, w_ld=c, y=out.view(n * t, c), y_ld=c, bias=pk["bo"],
+                   bias_mode=1, residual=x.view(n * t, c))
+        return _Stream(out, None, None)
+
+    def _attention_unfused(self, pk, xn2, q_all, k_all, ld_qk, o, n, t, c, scale, act_dt, dev):
+        """QK^T GEMM -> fp32 scores -> softmax kernel -> PV GEMM (fp32 mode, d != 384, ragged token counts)."""
         vt = torch.empty((c, t), dtype=act_dt, device=dev)
         # bound the fp32 score block to ~1 GiB; chunks are multiples of 128 query rows
         q_chunk = max(128, min(t, ((1 << 28) // t) // 128 * 128))
@@ -589,10 +606,6 @@ class RgbaAutoencoder(nn.Module):
                 self._gemm(qi, ki, rows=rows, k=c, cols=t, x_ld=ld_qk, w_ld=ld_qk, y=sv, y_ld=t, alpha=scale)
                 p = ops.softmax_rows(sv, act_dt)
                 self._gemm(p, vt, rows=rows, k=t, cols=c, x_ld=t, w_ld=t, y=o[i * t + r0:i * t + r0 + rows], y_ld=c)
-        out = torch.empty_like(x)
-        self._gemm(o, pk["wo"], rows=n * t, k=c, cols=c, x_ld=c, w_ld=c, y=out.view(n * t, c), y_ld=c, bias=pk["bo"],
-                   bias_mode=1, residual=x.view(n * t, c))
-        return _Stream(out, None, None)
 
     def _mid(self, st, mid, next_norm=None):
         a = mid.attentions[0]

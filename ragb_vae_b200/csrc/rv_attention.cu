@@ -1,0 +1,365 @@
+// Fused single-head attention for the VAE mid block (sm_100a): O = softmax(Q K^T / sqrt(d)) V, d = 384.
+//
+// Replaces scaled_dot_product_attention inside diffusers' QwenImageAttentionBlock (mid block of
+// vae.encode / vae.decode; reference call sites src/models/rgba_vae.py:277,279).  The unfused path
+// (QK^T GEMM -> fp32 scores in HBM -> softmax kernel -> PV GEMM) moves ~3 GB per 16 384-token image;
+// here scores and probabilities never leave the SM.
+//
+// One CTA = 128 queries of one image; it walks the keys in blocks of 128:
+//   warp 0      TMA producer: Q once (6 x [128 x 64] SW128 chunks), then per key block the K chunks
+//               (6 x 16 KB) and V^T chunks (6 x [128 d x 64 keys] = 16 KB) through one 5-slot ring,
+//               in exactly the order the MMA warp consumes them
+//   warp 1      tcgen05.mma issuer: S = Q K^T into TMEM columns [384, 512), O += P V into [0, 384)
+//   warps 4-11  softmax (thread = query row; the two warps of a lane quarter split the 128 keys):
+//               S -> registers, running max with lazy rescale (O is only rescaled when the max grows by
+//               more than 2^8), P = exp2(...) written to shared memory as the bf16 K-major SW128 A
+//               operand of the PV MMA; finally O / l -> bf16 global
+// TMEM: O 384 fp32 columns + S 128 = 512.  Shared memory: Q 96 KB + ring 80 KB + P 32 KB.
+#include <cstring>
+#include <mutex>
+
+#include "rv_tc_common.cuh"
+
+namespace rv {
+
+constexpr int FA_D = 384;
+constexpr int FA_DCH = FA_D / 64;        // 64-wide chunks of d
+constexpr int FA_BQ = 128, FA_BK = 128;
+constexpr int FA_RING = 5;
+constexpr uint32_t FA_SLOT = 16384;      // ring slot: a K chunk [128 keys x 64 d] or a V^T chunk [128 d x 64 keys]
+constexpr uint32_t FA_Q_BYTES = FA_DCH * 16384;
+constexpr uint32_t FA_P_BYTES = 2 * 16384;
+constexpr int FA_THREADS = 384;          // warps: 0 TMA, 1 MMA, 2-3 idle, 4-11 softmax
+constexpr float FA_RESCALE_THRESHOLD = 8.0f;
+
+struct FaParams {
+  int tokens;          // per image, multiple of 128
+  int n_img;
+  int ld_out;          // row pitch of O in elements
+  float scale_log2;    // 1/sqrt(d) * log2(e)
+  __nv_bfloat16* out;  // [n_img*tokens][ld_out]
+};
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(FA_THREADS, 1)
+flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                  const __grid_constant__ CUtensorMap map_vt, const __grid_constant__ FaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_q, bar_full[FA_RING], bar_empty[FA_RING], bar_sfull, bar_sempty, bar_pfull, bar_pvdone;
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_xmax[2][2][128];  // [block parity][column half][row]
+  __shared__ float s_xsum[2][128];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_smem = base, ring = base + FA_Q_BYTES, p_smem = ring + FA_RING * FA_SLOT;
+  const int nb = p.tokens / FA_BK;
+  const int qblocks = p.tokens / FA_BQ;
+  const int img = blockIdx.x / qblocks;
+  const int q0 = (blockIdx.x - img * qblocks) * FA_BQ;
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(smem_u32(&bar_q), 1);
+    for (int s = 0; s < FA_RING; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bar_sfull), 1);
+    mbar_init(smem_u32(&bar_sempty), 8);
+    mbar_init(smem_u32(&bar_pfull), 8);
+    mbar_init(smem_u32(&bar_pvdone), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
+  const uint32_t sfull = smem_u32(&bar_sfull), sempty = smem_u32(&bar_sempty), pfull = smem_u32(&bar_pfull),
+                 pvdone = smem_u32(&bar_pvdone), qbar = smem_u32(&bar_q);
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (elect_one()) {
+      mbar_arrive_expect_tx(qbar, FA_Q_BYTES);
+      for (int c = 0; c < FA_DCH; ++c) tma_load_2d(q_smem + c * 16384u, &map_q, qbar, c * 64, img * p.tokens + q0);
+    }
+    __syncwarp();
+    uint32_t slot = 0, par = 0;
+    // consumption order: K(0), K(1), V(0), K(2), V(1), ..., K(nb-1), V(nb-2), V(nb-1)
+    for (int step = 0; step <= nb; ++step) {
+      if (step < nb) {
+        for (int c = 0; c < FA_DCH; ++c) {
+          mbar_wait(empty0 + 8u * slot, par ^ 1u);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(full0 + 8u * slot, 16384u);
+            tma_load_2d(ring + slot * FA_SLOT, &map_k, full0 + 8u * slot, c * 64, img * p.tokens + step * FA_BK);
+          }
+          __syncwarp();
+          if (++slot == FA_RING) { slot = 0; par ^= 1u; }
+        }
+      }
+      if (step >= 1) {
+        const int j = step - 1;
+        for (int kc = 0; kc < 2; ++kc)
+          for (int h = 0; h < 3; ++h) {
+            mbar_wait(empty0 + 8u * slot, par ^ 1u);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(full0 + 8u * slot, FA_SLOT);
+              tma_load_3d(ring + slot * FA_SLOT, &map_vt, full0 + 8u * slot, j * FA_BK + kc * 64, h * 128, img);
+            }
+            __syncwarp();
+            if (++slot == FA_RING) { slot = 0; par ^= 1u; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc_o = idesc_s;  // PV in three N = 128 thirds of d
+    const uint64_t hi = make_smem_desc(0u, 1024u, 2u);
+    const uint32_t q_lo = (q_smem & 0x3FFFFu) >> 4, p_lo = (p_smem & 0x3FFFFu) >> 4, ring_lo = (ring & 0x3FFFFu) >> 4;
+    const uint32_t s_tmem = tmem_base + 384u;
+    uint32_t slot = 0, par = 0;
+    mbar_wait(qbar, 0);
+    auto issue_qk = [&](int j) {
+      // S = Q K(j)^T : 6 chunks x 4 k-steps, N = 128
+      for (int c = 0; c < FA_DCH; ++c) {
+        mbar_wait(full0 + 8u * slot, par);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t ad = hi | (uint64_t)(q_lo + c * 1024u);
+          const uint64_t bd = hi | (uint64_t)(ring_lo + slot * (FA_SLOT >> 4));
+          umma_bf16(s_tmem, ad, bd, idesc_s, c == 0 ? 0u : 1u);
+          umma_bf16(s_tmem, ad + 2u, bd + 2u, idesc_s, 1u);
+          umma_bf16(s_tmem, ad + 4u, bd + 4u, idesc_s, 1u);
+          umma_bf16(s_tmem, ad + 6u, bd + 6u, idesc_s, 1u);
+          umma_commit(empty0 + 8u * slot);
+          if (c == FA_DCH - 1) umma_commit(sfull);
+        }
+        __syncwarp();
+        if (++slot == FA_RING) { slot = 0; par ^= 1u; }
+      }
+      (void)j;
+    };
+    issue_qk(0);
+    for (int j = 0; j < nb; ++j) {
+      if (j + 1 < nb) {
+        mbar_wait(sempty, (uint32_t)(j & 1));   // S(j) is in registers: the S columns may be overwritten
+        tc_fence_after();
+        issue_qk(j + 1);
+      }
+      mbar_wait(pfull, (uint32_t)(j & 1));      // P(j) is in shared memory (and O has been rescaled if needed)
+      tc_fence_after();
+      for (int kc = 0; kc < 2; ++kc)
+        for (int h = 0; h < 3; ++h) {
+          mbar_wait(full0 + 8u * slot, par);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t ad = hi | (uint64_t)(p_lo + kc * 1024u);
+            const uint64_t bd = hi | (uint64_t)(ring_lo + slot * (FA_SLOT >> 4));
+            const uint32_t d_tmem = tmem_base + (uint32_t)h * 128u;
+            umma_bf16(d_tmem, ad, bd, idesc_o, (j == 0 && kc == 0) ? 0u : 1u);
+            umma_bf16(d_tmem, ad + 2u, bd + 2u, idesc_o, 1u);
+            umma_bf16(d_tmem, ad + 4u, bd + 4u, idesc_o, 1u);
+            umma_bf16(d_tmem, ad + 6u, bd + 6u, idesc_o, 1u);
+            umma_commit(empty0 + 8u * slot);
+            if (kc == 1 && h == 2) umma_commit(pvdone);
+          }
+          __syncwarp();
+          if (++slot == FA_RING) { slot = 0; par ^= 1u; }
+        }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ softmax / correction / output ------------------------------
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t s_taddr = lane_addr + 384u + (uint32_t)half * 64u;
+    const uint32_t o_taddr = lane_addr + (uint32_t)half * 192u;
+    const int bar_id = 1 + q;
+    float m_used = -INFINITY, l = 0.f;
+    // P row base: key chunk `half`, row `row`; 16-byte unit u of the row lives at ((u ^ (row & 7)) * 16)
+    const uint32_t p_row = p_smem + (uint32_t)half * 16384u + (uint32_t)row * 128u;
+    const uint32_t sw = (uint32_t)(row & 7);
+    for (int j = 0; j < nb; ++j) {
+      mbar_wait(sfull, (uint32_t)(j & 1));
+      tc_fence_after();
+      uint32_t s0[32], s1[32];
+      tmem_ld32(s_taddr, s0);
+      tmem_ld32(s_taddr + 32u, s1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sempty);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
+      s_xmax[j & 1][half][row] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      mx = fmaxf(mx, s_xmax[j & 1][half ^ 1][row]) * p.scale_log2;
+      float alpha = 1.0f;
+      bool need = false;
+      if (j == 0) {
+        m_used = mx;
+      } else if (mx - m_used > FA_RESCALE_THRESHOLD) {
+        alpha = exp2f(m_used - mx);
+        m_used = mx;
+        l *= alpha;
+        need = true;
+      }
+      // probabilities (bf16) and their row sum
+      uint32_t pk[32];
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float a = exp2f(fmaf(__uint_as_float(s0[2 * i]), p.scale_log2, -m_used));
+        const float b = exp2f(fmaf(__uint_as_float(s0[2 * i + 1]), p.scale_log2, -m_used));
+        const __nv_bfloat162 ab = __floats2bfloat162_rn(a, b);
+        pk[i] = *reinterpret_cast<const uint32_t*>(&ab);
+        sum += __low2float(ab) + __high2float(ab);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float a = exp2f(fmaf(__uint_as_float(s1[2 * i]), p.scale_log2, -m_used));
+        const float b = exp2f(fmaf(__uint_as_float(s1[2 * i + 1]), p.scale_log2, -m_used));
+        const __nv_bfloat162 ab = __floats2bfloat162_rn(a, b);
+        pk[16 + i] = *reinterpret_cast<const uint32_t*>(&ab);
+        sum += __low2float(ab) + __high2float(ab);
+      }
+      l += sum;
+      // the previous PV must be complete before P is overwritten or O is rescaled
+      if (j > 0) {
+        mbar_wait(pvdone, (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {
+          for (int c = 0; c < 6; ++c) {
+            uint32_t o[32];
+            tmem_ld32(o_taddr + (uint32_t)c * 32u, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(o_taddr + (uint32_t)c * 32u, o);
+          }
+          tmem_st_wait();
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t addr = p_row + (((uint32_t)u ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]),
+                     "r"(pk[4 * u + 3])
+                     : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pfull);
+    }
+    // ---- output: O / l ----
+    s_xsum[half][row] = l;
+    mbar_wait(pvdone, (uint32_t)((nb - 1) & 1));
+    tc_fence_after();
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+    const float inv = 1.0f / (s_xsum[0][row] + s_xsum[1][row]);
+    __nv_bfloat16* orow = p.out + ((int64_t)img * p.tokens + q0 + row) * p.ld_out + half * 192;
+    for (int c = 0; c < 6; ++c) {
+      uint32_t o[32];
+      tmem_ld32(o_taddr + (uint32_t)c * 32u, o);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(o[i]) * inv;
+      fast_store<32>(orow + c * 32, v);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+int tc_encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                  const cuuint32_t* box, CUtensorMapSwizzle sw);  // rv_conv_tc.cu
+int tc_ensure_init();
+
+static std::mutex g_fa_mu;
+static bool g_fa_attr[64] = {false};
+
+}  // namespace rv
+
+extern "C" int rv_attention(const void* q, const void* k, int64_t ld_qk, const void* vt, void* out, int64_t ld_out, int n_img,
+                            int tokens, int d, void* stream) {
+  using namespace rv;
+  if (int rc = tc_ensure_init()) return rc;
+  RV_CHECK_ARG(q && k && vt && out && n_img > 0 && tokens > 0, "attention: bad argument");
+  RV_CHECK_ARG(d == FA_D, "attention: the fused kernel is built for d = %d (got %d)", FA_D, d);
+  RV_CHECK_ARG(tokens % 128 == 0, "attention: tokens (%d) must be a multiple of 128", tokens);
+  RV_CHECK_ARG(ld_qk % 8 == 0 && ld_out % 8 == 0 && ld_qk >= d && ld_out >= d, "attention: pitches must be multiples of 8 and >= d");
+  RV_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)vt % 16 == 0) && ((uintptr_t)out % 16 == 0),
+               "attention: tensors must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap mq, mk, mv;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)((int64_t)n_img * tokens)};
+    cuuint64_t str[1] = {(cuuint64_t)ld_qk * 2u};
+    cuuint32_t box[2] = {64, 128};
+    if (int rc = tc_encode_map(&mq, q, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = tc_encode_map(&mk, k, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)tokens, (cuuint64_t)d, (cuuint64_t)n_img};
+    cuuint64_t str[2] = {(cuuint64_t)tokens * 2u, (cuuint64_t)tokens * 2u * d};
+    cuuint32_t box[3] = {64, 128, 1};
+    if (int rc = tc_encode_map(&mv, vt, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  }
+  const size_t smem = FA_Q_BYTES + FA_RING * FA_SLOT + FA_P_BYTES + 1024;
+  {
+    std::lock_guard<std::mutex> lk(g_fa_mu);
+    int dev = 0;
+    RV_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !g_fa_attr[dev]) {
+      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      g_fa_attr[dev] = true;
+    }
+  }
+  FaParams p;
+  p.tokens = tokens;
+  p.n_img = n_img;
+  p.ld_out = (int)ld_out;
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
+  p.out = (__nv_bfloat16*)out;
+  const int grid = n_img * (tokens / FA_BQ);
+  LaunchScope scope(CAT_ATTN, st, 4.0 * (double)n_img * tokens * tokens * d);
+  flash_attn_kernel<<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, p);
+  RV_LAUNCH_CHECK();
+  return 0;
+}

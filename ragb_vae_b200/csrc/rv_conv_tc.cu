@@ -266,7 +266,7 @@ static EncodeTiledFn g_encode = nullptr;
 static std::mutex g_init_mu;
 static bool g_attr_set[64] = {false};
 
-static int ensure_init() {
+int tc_ensure_init() {
   std::lock_guard<std::mutex> lk(g_init_mu);
   if (!g_encode) {
     void* fn = nullptr;
@@ -520,12 +520,12 @@ __global__ void pack_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __res
 
 extern "C" {
 
-int rv_init(void) { return rv::ensure_init(); }
+int rv_init(void) { return rv::tc_ensure_init(); }
 
 static int conv2d_tc_impl(const rv_conv_desc* d, const void* x, const void* w_packed, int64_t w_ld, const float* bias,
                           const void* residual, void* y, void* stream, const rv::NormFuse* nf) {
   if (int rc = rv::check_conv_desc(d)) return rc;
-  if (int rc = rv::ensure_init()) return rc;
+  if (int rc = rv::tc_ensure_init()) return rc;
   RV_CHECK_ARG(x && w_packed && (y || nf), "conv_tc: null tensor");
   RV_CHECK_ARG(d->x_dtype == RV_BF16 && !d->x_nchw, "conv_tc: x must be NHWC bf16");
   RV_CHECK_ARG(d->cin % 16 == 0, "conv_tc: cin (%d) must be a multiple of 16", d->cin);

@@ -157,6 +157,22 @@ def groupnorm_silu(x: torch.Tensor, gamma, beta, groups: int = 32, eps: float = 
     return y
 
 
+FUSED_ATTENTION_D = 384
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, n_img: int, tokens: int) -> torch.Tensor:
+    """Fused softmax(Q K^T / sqrt(d)) V.  q, k: bf16 [n_img*tokens, d] row views (may be column slices of one
+    tensor, same row stride); vt: bf16 [n_img, d, tokens].  Returns bf16 [n_img*tokens, d]."""
+    _need_cuda(q, k, vt)
+    d = vt.shape[1]
+    if q.stride(0) != k.stride(0) or q.stride(1) != 1 or k.stride(1) != 1 or not vt.is_contiguous():
+        raise ValueError("attention: q/k must share a row stride and be unit-stride in d; vt must be contiguous")
+    out = torch.empty((n_img * tokens, d), dtype=torch.bfloat16, device=q.device)
+    check(_lib.load().rv_attention(_ptr(q), _ptr(k), q.stride(0), _ptr(vt), _ptr(out), d, n_img, tokens, d, _stream(q)),
+          "rv_attention")
+    return out
+
+
 def softmax_rows(s: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
     _need_cuda(s)
     rows, cols = s.shape

@@ -170,3 +170,22 @@ def test_tc_conv_fused_rmsnorm_epilogue(ops, cout, want_raw, silu, w):
     with pytest.raises(RvError):
         ops.conv2d_tc_norm(d2, xh[:1, :8, :8].contiguous(), w2, 9 * 96, torch.zeros(384, device="cuda"), None, y2, y2.clone(),
                            torch.ones(384, device="cuda"), True)
+
+
+@pytest.mark.parametrize("n_img,tokens", [(1, 128), (2, 512), (1, 2048)])
+@pytest.mark.parametrize("scale_up", [1.0, 6.0])  # larger scores exercise the lazy-rescale path
+def test_fused_attention(ops, n_img, tokens, scale_up):
+    d = 384
+    g = torch.Generator().manual_seed(tokens + n_img)
+    qk = (torch.randn(n_img * tokens, 2 * d, generator=g) * scale_up).bfloat16()
+    # make the row maxima grow along the key axis so that several rescales happen
+    qk[:, d:] *= torch.linspace(0.2, 1.5, n_img * tokens).view(-1, 1).bfloat16()
+    v = torch.randn(n_img, tokens, d, generator=g).bfloat16()
+    vt = v.transpose(1, 2).contiguous()
+    q = qk[:, :d].float().view(n_img, tokens, d)
+    k = qk[:, d:].float().view(n_img, tokens, d)
+    ref = F.scaled_dot_product_attention(q.unsqueeze(1), k.unsqueeze(1), v.float().unsqueeze(1)).squeeze(1)
+    qkc = qk.cuda()
+    out = ops.attention(qkc[:, :d], qkc[:, d:], vt.cuda(), n_img, tokens)
+    assert out.shape == (n_img * tokens, d)
+    assert rel(out.float().view(n_img, tokens, d), ref) < 1e-2
