@@ -15,8 +15,11 @@ torch.manual_seed(0)
 model = R.RgbaVAE(R.RgbaAutoencoder(arch).to("cuda", torch.bfloat16))
 x = torch.rand(B, 4, S, S, device="cuda").bfloat16()
 noise = torch.randn(B, 16, S // 8, S // 8, device="cuda").bfloat16()
+per_step = 0
 for _ in range(iters):
+    l0 = ops.launch_count()
     recon, _ = model(x, noise=noise)
     m = ops.composite_psnr(recon, x, [(1.0, 1.0, 1.0)])
+    per_step = ops.launch_count() - l0
 torch.cuda.synchronize()
-print("psnr_white", m[:, 0].tolist(), "launches", ops.launch_count())
+print("psnr_white", m[:, 0].tolist(), "launches_total", ops.launch_count(), "launches_last_step", per_step)
