@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 5
+#define RV_ABI_VERSION 7
 #define RV_PROF_CATEGORIES 9
 
 int rv_abi_version(void);
@@ -142,6 +142,26 @@ int rv_nhwc_to_nchw(const void* x, void* y, int n, int c, int64_t hw, int x_cstr
  * y[n][h][w][tap*c + ch], zeros outside the image and past 9*c.  conv_in then is a K=kpad GEMM. */
 int rv_im2col3x3(const void* x, void* y, int n, int c, int h, int w, int kpad, int x_dtype, int y_dtype,
                  float scale, float shift, void* stream);
+
+/* ---- data formats either side of the VAE ----------------------------------- */
+/* build_detail_augmented_triplet (src/training/rgba_vae_stage.py:606-625): target NCHW [b][4][hw] in [-1,1] ->
+ * out [3b][4][hw] = [target | on black, alpha 1 | on white, alpha 1]. */
+int rv_triplet_augment(const void* target, void* out, int b, int64_t hw, int dtype, void* stream);
+/* FluxPipeline._pack_latents / _unpack_latents (src/models/flux_kontext_textalpha.py:334-349): (n,c,h,w) <->
+ * (n, (h/2)(w/2), 4c) with feature order (c, dy, dx).  unpack = 0: y = (pack(x) - shift) * scale;
+ * unpack = 1: y = unpack(x) * scale + shift. */
+int rv_pack_latents(const void* x, void* y, int n, int c, int h, int w, int dtype, float shift, float scale,
+                    int unpack, void* stream);
+/* blend_v / blend_h of diffusers' tiled encode / decode (enable_tiling, src/training/rgba_vae_stage.py:296-299):
+ * the first `extent` rows (vertical = 1) or columns of every plane of b become a linear ramp from the last `extent`
+ * rows / columns of a to b.  a: [planes][ah][aw], b: [planes][bh][bw], modified in place. */
+int rv_blend_tiles(const void* a, void* b, int planes, int ah, int aw, int bh, int bw, int extent, int vertical,
+                   int dtype, void* stream);
+/* uint8 RGBA, HWC per image (inference_rgba_flux.py:15-26) <-> NCHW float: y = x/255*scale+shift; and back
+ * (clamp to [0,1], *255, truncate). */
+int rv_rgba_u8_to_nchw(const void* x_u8, void* y, int n, int64_t hw, int y_dtype, float scale, float shift,
+                       void* stream);
+int rv_nchw_to_rgba_u8(const void* x, void* y_u8, int n, int64_t hw, int x_dtype, void* stream);
 
 /* ---- posterior (diffusers DiagonalGaussianDistribution; src/models/rgba_vae.py:278) ------ */
 /* moments NCHW [n][2*zc][hw]; noise / z NCHW [n][zc][hw].

@@ -592,3 +592,99 @@ def synthetic_rgba(batch: int, h: int, w: int, seed: int = 1, structured: bool =
         a = torch.clamp((0.75 - r) / 0.4 - 0.35, 0.0, 1.0)
         x[:, 3] = a
     return x
+
+
+# --------------------------------------------------------------------------- #
+# Flux latent plumbing and image I/O conversions
+# --------------------------------------------------------------------------- #
+def pack_latents(latents):
+    """diffusers FluxPipeline._pack_latents, as called by src/models/flux_kontext_textalpha.py:334-341."""
+    b, c, h, w = latents.shape
+    x = latents.view(b, c, h // 2, 2, w // 2, 2).permute(0, 2, 4, 1, 3, 5)
+    return x.reshape(b, (h // 2) * (w // 2), c * 4)
+
+
+def unpack_latents(tokens, height, width, vae_scale_factor=8):
+    """diffusers FluxPipeline._unpack_latents (flux_kontext_textalpha.py:343-349)."""
+    b, _, f = tokens.shape
+    h = 2 * (int(height) // (vae_scale_factor * 2))
+    w = 2 * (int(width) // (vae_scale_factor * 2))
+    x = tokens.view(b, h // 2, w // 2, f // 4, 2, 2).permute(0, 3, 1, 4, 2, 5)
+    return x.reshape(b, f // 4, h, w)
+
+
+def load_rgba_u8(arr_u8):
+    """inference_rgba_flux.py:15-20 after PIL: uint8 (H,W,4) -> float CHW in [0,1]."""
+    return arr_u8.float().permute(2, 0, 1) / 255.0
+
+
+def save_rgba_u8(tensor):
+    """inference_rgba_flux.py:23-26 before PIL: CHW in [0,1] -> uint8 (H,W,4), truncating."""
+    return (tensor.clamp(0, 1).float().permute(1, 2, 0) * 255).to(torch.uint8)
+
+
+# --------------------------------------------------------------------------- #
+# Tiled encode / decode (diffusers enable_tiling; SURVEY App. A.1 / A.2, 8f rank 2)
+# --------------------------------------------------------------------------- #
+def _blend_v(a, b, extent):
+    extent = min(a.shape[2], b.shape[2], extent)
+    for y in range(extent):
+        b[:, :, y, :] = a[:, :, -extent + y, :] * (1 - y / extent) + b[:, :, y, :] * (y / extent)
+    return b
+
+
+def _blend_h(a, b, extent):
+    extent = min(a.shape[3], b.shape[3], extent)
+    for x in range(extent):
+        b[:, :, :, x] = a[:, :, :, -extent + x] * (1 - x / extent) + b[:, :, :, x] * (x / extent)
+    return b
+
+
+def _tiled(t, fn, tile, stride, blend, limit):
+    """Row-major, in-place blending exactly like diffusers' tiled_encode / tiled_decode loops."""
+    rows = []
+    for i in range(0, t.shape[2], stride):
+        rows.append([fn(t[:, :, i:i + tile, j:j + tile]).clone() for j in range(0, t.shape[3], stride)])
+    result_rows = []
+    for i, row in enumerate(rows):
+        result_row = []
+        for j, tile_ in enumerate(row):
+            if i > 0:
+                tile_ = _blend_v(rows[i - 1][j], tile_, blend)
+            if j > 0:
+                tile_ = _blend_h(row[j - 1], tile_, blend)
+            result_row.append(tile_[:, :, :limit, :limit])
+        result_rows.append(torch.cat(result_row, dim=3))
+    return torch.cat(result_rows, dim=2)
+
+
+def tiling_params(vae: "OracleVAE"):
+    """(sample tile, sample stride, latent tile, latent stride, enc blend, enc limit, dec blend, dec limit)."""
+    if vae.arch == "flux":  # AutoencoderKL: tile = sample_size, tile_overlap_factor = 0.25
+        ts = int(vae.config.sample_size)
+        tl = int(ts / (2 ** (len(vae.config.block_out_channels) - 1)))
+        eb, db = int(tl * 0.25), int(ts * 0.25)
+        return ts, int(ts * 0.75), tl, int(tl * 0.75), eb, tl - eb, db, ts - db
+    ts, ss = 256, 192          # AutoencoderKLQwenImage defaults
+    tl, sl = ts // 8, ss // 8
+    return ts, ss, tl, sl, tl - sl, sl, ts - ss, ss
+
+
+def tiled_encode_moments(vae: "OracleVAE", x):
+    ts, ss, tl, sl, eb, el, _, _ = tiling_params(vae)
+    if x.shape[-1] <= ts and x.shape[-2] <= ts:
+        return vae.encode_moments(x)
+    m = _tiled(x, vae.encode_moments, ts, ss, eb, el)
+    return m[:, :, :x.shape[2] // 8, :x.shape[3] // 8]
+
+
+def tiled_decode(vae: "OracleVAE", z):
+    ts, ss, tl, sl, _, _, db, dl = tiling_params(vae)
+    if z.shape[-1] <= tl and z.shape[-2] <= tl:
+        return vae.decode(z).sample
+    if vae.arch == "qwen":  # tiled_decode returns the blended tiles without the clamp of _decode
+        fn = lambda t: vae.decoder(vae.post_quant_conv.forward_frame(t))
+    else:
+        fn = lambda t: vae.decoder(t)
+    y = _tiled(z, fn, tl, sl, db, dl)
+    return y[:, :, :z.shape[2] * 8, :z.shape[3] * 8]

@@ -323,8 +323,39 @@ class RgbaAutoencoder(nn.Module):
         return next(self.parameters()).device
 
     def enable_tiling(self, *a, **k):
-        # Tiled encode/decode is not built yet: the untiled path is the parity target.
+        """diffusers tiling: inputs larger than the tile are processed in overlapping tiles whose seams are blended
+        linearly (rgba_vae_stage.py:296-299 turns this on for training; results differ from the untiled path)."""
         self.use_tiling = True
+
+    def _tiling(self):
+        """(sample tile, sample stride, latent tile, latent stride) as the diffusers classes derive them."""
+        if self.arch == "flux":   # AutoencoderKL: tile = sample_size, overlap factor 0.25
+            ts = int(self.config.sample_size)
+            tl = int(ts / (2 ** (len(self.config.block_out_channels) - 1)))
+            return ts, int(ts * 0.75), tl, int(tl * 0.75)
+        ts = int(getattr(self.config, "tile_sample_min_size", 256))   # AutoencoderKLQwenImage: 256 / stride 192
+        st = int(getattr(self.config, "tile_sample_stride", 192))
+        return ts, st, ts // 8, st // 8
+
+    def _tiled(self, t: torch.Tensor, fn, tile: int, stride: int, blend: int, limit: int) -> torch.Tensor:
+        """Overlapping tiles -> fn -> blend_v / blend_h in row-major order (in place, like diffusers) -> crop -> concat."""
+        rows = []
+        for i in range(0, t.shape[2], stride):
+            row = []
+            for j in range(0, t.shape[3], stride):
+                row.append(fn(t[:, :, i:i + tile, j:j + tile].contiguous()))
+            rows.append(row)
+        out_rows = []
+        for i, row in enumerate(rows):
+            out_row = []
+            for j, tl in enumerate(row):
+                if i > 0:
+                    ops.blend_tiles(rows[i - 1][j], tl, blend, vertical=True)
+                if j > 0:
+                    ops.blend_tiles(row[j - 1], tl, blend, vertical=False)
+                out_row.append(tl[:, :, :limit, :limit])
+            out_rows.append(torch.cat(out_row, dim=3))
+        return torch.cat(out_rows, dim=2)
 
     def disable_tiling(self):
         self.use_tiling = False
@@ -341,13 +372,40 @@ class RgbaAutoencoder(nn.Module):
     def disable_gradient_checkpointing(self):
         self.gradient_checkpointing = False
 
+    def _encode_maybe_tiled(self, x: torch.Tensor) -> torch.Tensor:
+        ts, ss, tl, sl = self._tiling()
+        if self.use_tiling and isinstance(x, torch.Tensor) and x.dim() == 4 and (x.shape[-1] > ts or x.shape[-2] > ts):
+            if self.arch == "flux":   # blend_extent = int(latent_tile * 0.25), row_limit = latent_tile - blend_extent
+                blend = int(tl * 0.25)
+                limit = tl - blend
+            else:                      # blend = latent_tile - latent_stride, crop to the latent stride
+                blend, limit = tl - sl, sl
+            m = self._tiled(x, self._encode_moments, ts, ss, blend, limit)
+            return m[:, :, :x.shape[2] // 8, :x.shape[3] // 8].contiguous()
+        return self._encode_moments(x)
+
+    def _decode_maybe_tiled(self, z: torch.Tensor) -> torch.Tensor:
+        ts, ss, tl, sl = self._tiling()
+        if self.use_tiling and isinstance(z, torch.Tensor) and z.dim() == 4 and (z.shape[-1] > tl or z.shape[-2] > tl):
+            if self.arch == "flux":
+                blend = int(ts * 0.25)
+                limit = ts - blend
+                fn = self._decode_image
+            else:
+                blend, limit = ts - ss, ss
+                # AutoencoderKLQwenImage.tiled_decode returns the blended tiles without the clamp of _decode
+                fn = lambda t: self._decode_image(t, model_clamp=False)
+            y = self._tiled(z, fn, tl, sl, blend, limit)
+            return y[:, :, :z.shape[2] * 8, :z.shape[3] * 8].contiguous()
+        return self._decode_image(z)
+
     def encode(self, x: torch.Tensor, return_dict: bool = True):
-        moments = self._run_sliced(self._encode_moments, x)
+        moments = self._run_sliced(self._encode_maybe_tiled, x)
         post = DiagonalGaussianDistribution(moments)
         return AutoencoderKLOutput(latent_dist=post) if return_dict else (post,)
 
     def decode(self, z: torch.Tensor, return_dict: bool = True, generator=None):
-        y = self._run_sliced(self._decode_image, z)
+        y = self._run_sliced(self._decode_maybe_tiled, z)
         return DecoderOutput(sample=y) if return_dict else (y,)
 
     def forward(self, sample: torch.Tensor, sample_posterior: bool = False, return_dict: bool = True, generator=None):
@@ -701,7 +759,7 @@ class RgbaAutoencoder(nn.Module):
         raise AssertionError(kind)
 
     def _decode_image(self, z: torch.Tensor, out_scale: float = 1.0, out_shift: float = 0.0, clamp=None,
-                      z_scale: float = 1.0, z_shift: float = 0.0) -> torch.Tensor:
+                      z_scale: float = 1.0, z_shift: float = 0.0, model_clamp: bool = True) -> torch.Tensor:
         """latents (B,Z,h,w) -> image (B,Cout,8h,8w) in the model dtype (optionally y*out_scale+out_shift, clamped)."""
         dec = self.decoder
         self._check_image(z, dec.conv_in.in_channels, "decode() input", 1)
@@ -724,8 +782,10 @@ class RgbaAutoencoder(nn.Module):
         st = self._conv_fused(st.raw, dec.conv_in, next_norm=self._first_norm(items[0]))
         st = self._run_ops_until_head(st, items)
         # AutoencoderKLQwenImage._decode clamps to [-1, 1]; composed with the caller's affine + clamp
-        lo, hi = -1.0 * out_scale + out_shift, 1.0 * out_scale + out_shift
-        if clamp is not None:
-            lo, hi = max(lo, clamp[0]), min(hi, clamp[1])
+        if model_clamp:
+            lo, hi = -1.0 * out_scale + out_shift, 1.0 * out_scale + out_shift
+            if clamp is not None:
+                lo, hi = max(lo, clamp[0]), min(hi, clamp[1])
+            clamp = (lo, hi)
         return self._conv(self._normed(st, head[0]), head[1], y_nchw=True, out_scale=out_scale, out_shift=out_shift,
-                          clamp=(lo, hi))
+                          clamp=clamp)

@@ -279,5 +279,16 @@ def composite_psnr(recon: torch.Tensor, target: torch.Tensor, backgrounds: Seque
     return out
 
 
+def blend_tiles(a: torch.Tensor, b: torch.Tensor, extent: int, vertical: bool) -> torch.Tensor:
+    """diffusers blend_v / blend_h on contiguous NCHW tiles; b is modified in place and returned."""
+    _need_cuda(a, b)
+    if not (a.is_contiguous() and b.is_contiguous()) or a.dtype != b.dtype or a.shape[:2] != b.shape[:2]:
+        raise ValueError("blend_tiles needs two contiguous NCHW tiles of the same dtype, batch and channels")
+    planes = a.shape[0] * a.shape[1]
+    check(_lib.load().rv_blend_tiles(_ptr(a), _ptr(b), planes, a.shape[2], a.shape[3], b.shape[2], b.shape[3], int(extent),
+                                     int(vertical), _dt(a), _stream(a)), "rv_blend_tiles")
+    return b
+
+
 def attn_scale(c: int) -> float:
     return 1.0 / math.sqrt(c)

@@ -165,3 +165,33 @@ def test_three_channel_input_and_flux_latent_plumbing(R, oracle_model):
     a = vae32._decode_image(zn, z_scale=1.0 / 0.3611, z_shift=0.1159)
     b = vae32.decode(z).sample
     assert rel(a, b) < 1e-4
+
+
+@pytest.mark.parametrize("arch", ["qwen", "flux"])
+def test_tiled_encode_decode_matches_oracle_tiling(R, oracle_model, arch):
+    """enable_tiling(): overlapping tiles + linear seam blending (the reference's training default).  Flux is run
+    with sample_size 256 so that the CPU oracle stays cheap; 320 x 448 gives a 2 x 3 tile grid with ragged edges."""
+    oracle = oracle_model(arch)
+    old = oracle.config.sample_size
+    oracle.config.sample_size = 256
+    try:
+        x = O.synthetic_rgba(1, 320, 448, seed=11, structured=True) * 2 - 1
+        ref_m = O.tiled_encode_moments(oracle, x)
+        z = ref_m[:, :16].contiguous()
+        ref_d = O.tiled_decode(oracle, z)
+        untiled = oracle.encode_moments(x)
+        assert rel(ref_m, untiled) > 1e-3          # tiling really changes the result
+        vae = R.RgbaAutoencoder(arch, sample_size=256)
+        vae.load_state_dict(oracle.state_dict())
+        vae = vae.to("cuda", torch.float32)
+        vae.enable_tiling()
+        got_m = vae.encode(x.cuda()).latent_dist.parameters
+        assert got_m.shape == ref_m.shape
+        assert record(f"tiled/{arch}/moments", rel(got_m, ref_m)) < 1e-4
+        got_d = vae.decode(z.cuda()).sample
+        assert got_d.shape == ref_d.shape == (1, 4, 320, 448)
+        assert record(f"tiled/{arch}/decoded", rel(got_d, ref_d)) < 1e-4
+        vae.disable_tiling()
+        assert rel(vae.encode(x.cuda()).latent_dist.parameters, untiled) < 1e-4
+    finally:
+        oracle.config.sample_size = old
