@@ -257,6 +257,209 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2).  Why: with cta_group::1 and SS operands every M = 128 MMA reads 4 KB of A plus
+// 32*N bytes of B from shared memory per K = 16 step, and the measured MMA time tracks (4096 + 32 N) / 64 cycles
+// for every N -- the SM's operand read path, not the tensor pipe, is the ceiling (67 % of peak at N = 256, 43 % at
+// N = 96).  A pair of CTAs on adjacent M tiles issues ONE M = 256 MMA: each SM still reads its own 128 rows of A but
+// only HALF of B (the pair's B tile is split between the two shared memories), and the weight traffic through L2
+// halves as well.  Roles per CTA are as in conv_tc_kernel; differences:
+//   * both CTAs' TMA loads complete on the LEADER's full barrier (arrival count 1: the leader's producer posts the
+//     expected bytes of both CTAs);
+//   * only the leader's MMA warp issues; tcgen05.commit multicasts the arrive to the same barrier in both CTAs
+//     (stage-empty and accumulator-full);
+//   * the peer's epilogue warps release the accumulator on the leader's barrier through a remote mbarrier arrive;
+//   * TMEM is allocated / freed with the cta_group::2 forms; cluster barriers fence set-up and tear-down.
+// ---------------------------------------------------------------------------------------
+template <int KSTEPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_acc_full[2];
+  __shared__ __align__(8) uint64_t bar_acc_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_bias[TC_SMEM_BIAS];
+  __shared__ __align__(16) float s_gamma[256];
+  __shared__ float s_ss[2][2][128];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int m_pairs = (p.m_tiles + 1) >> 1;
+  const int total_pt = m_pairs * p.n_tiles;  // pair tiles: two adjacent M tiles x one N tile
+  const int npairs = (int)gridDim.x >> 1, pair0 = (int)blockIdx.x >> 1;
+  const int num_kb = p.ntaps * p.kc_per_tap;
+  const int bn_half = p.bn >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&bar_acc_full[a]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[a]), 2 * TC_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
+  }
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  const bool bias_smem = p.e.fast && p.e.bias_mode == 1;
+  if (bias_smem)
+    for (int i = threadIdx.x; i < p.e.cout; i += TC_THREADS) s_bias[i] = p.e.bias[i];
+  if (p.e.norm_gamma)
+    for (int i = threadIdx.x; i < p.e.cout; i += TC_THREADS) s_gamma[i] = p.e.norm_gamma[i];
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const uint32_t bar_full0 = smem_u32(&bar_full[0]);
+  const uint32_t bar_empty0 = smem_u32(&bar_empty[0]);
+  const uint32_t bar_accf0 = smem_u32(&bar_acc_full[0]);
+  const uint32_t bar_acce0 = smem_u32(&bar_acc_empty[0]);
+  const uint32_t lead_full0 = mapa_rank(bar_full0, 0);   // the leader's barriers, as cluster addresses
+  const uint32_t lead_acce0 = mapa_rank(bar_acce0, 0);
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------------------
+    uint32_t stage = 0, phase = 0;
+    const uint32_t nstages = (uint32_t)p.stages;
+    for (int pt = pair0; pt < total_pt; pt += npairs) {
+      const int mp = pt / p.n_tiles, nt = pt - mp * p.n_tiles;
+      const TileCoord t = decode_tile(p, (2 * mp + (int)rank) * p.n_tiles + nt);
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        const int ax = t.x0 + p.tap_dx[tap], ay = t.y0 + p.tap_dy[tap];
+        const int kcol = p.w_k_base + tap * p.cin;
+        const int c5 = p.tap_wp[tap] * p.cin_pitch, hp = p.tap_hp[tap];
+        for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+          mbar_wait(bar_empty0 + 8u * stage, phase ^ 1u);
+          if (elect_one()) {
+            const uint32_t full = lead_full0 + 8u * stage;
+            const uint32_t a_dst = smem_base + stage * p.stage_bytes;
+            if (leader) mbar_arrive_expect_tx(bar_full0 + 8u * stage, 2u * p.tx_bytes);
+            if (p.mode == 0) tma2_load_4d(a_dst, &map_a, full, kc * p.bk, ax, ay, t.img);
+            else tma2_load_5d(a_dst, &map_a, full, c5 + kc * p.bk, ax, hp, ay, t.img);
+            tma2_load_2d(a_dst + p.a_bytes, &map_b, full, kcol + kc * p.bk, t.n0 + (int)rank * bn_half);
+          }
+          __syncwarp();
+          if (++stage == nstages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader CTA only) ------------------------------
+    if (leader) {
+      // M = 256 across the pair: m_dim field = 256 >> 4
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((256u >> 4) << 24);
+      const uint64_t desc_hi = make_smem_desc(0u, p.sbo_bytes, p.layout_type);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      const uint32_t nstages = (uint32_t)p.stages;
+      const uint32_t a_lo0 = (smem_base & 0x3FFFFu) >> 4, stage_lo = p.stage_bytes >> 4, ab_lo = p.a_bytes >> 4;
+      uint32_t a_lo = a_lo0, full_bar = bar_full0, empty_bar = bar_empty0;
+      const int last_kb = num_kb - 1;
+      for (int pt = pair0; pt < total_pt; pt += npairs) {
+        mbar_wait(bar_acce0 + 8u * acc, acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256u;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar, phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t a_desc = desc_hi | (uint64_t)a_lo;
+            const uint64_t b_desc = desc_hi | (uint64_t)(a_lo + ab_lo);
+            umma2_bf16(d_tmem, a_desc, b_desc, idesc, (uint32_t)(kb != 0));
+            if (KSTEPS > 1) umma2_bf16(d_tmem, a_desc + 2u, b_desc + 2u, idesc, 1u);
+            if (KSTEPS > 2) {
+              umma2_bf16(d_tmem, a_desc + 4u, b_desc + 4u, idesc, 1u);
+              umma2_bf16(d_tmem, a_desc + 6u, b_desc + 6u, idesc, 1u);
+            }
+            umma2_commit_both(empty_bar);
+            if (kb == last_kb) umma2_commit_both(bar_accf0 + 8u * acc);
+          }
+          __syncwarp();
+          a_lo += stage_lo;
+          full_bar += 8u;
+          empty_bar += 8u;
+          if (++stage == nstages) {
+            stage = 0;
+            phase ^= 1u;
+            a_lo = a_lo0;
+            full_bar = bar_full0;
+            empty_bar = bar_empty0;
+          }
+        }
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (both CTAs, own 128 rows) ------------------------------
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int ly = row / p.bw, lx = row - ly * p.bw;
+    const int nsplit = (p.bn % 32 == 0) ? 2 : 1;
+    const int cb = nsplit == 2 ? half * (p.bn >> 1) : 0;
+    const int ce = nsplit == 2 ? cb + (p.bn >> 1) : (half == 0 ? p.bn : 0);
+    const float* sbias = bias_smem ? s_bias : nullptr;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int pt = pair0; pt < total_pt; pt += npairs) {
+      const int mp = pt / p.n_tiles, nt = pt - mp * p.n_tiles;
+      const int m_tile = 2 * mp + (int)rank;
+      const TileCoord t = decode_tile(p, m_tile * p.n_tiles + nt);
+      const int ty = t.y0 + ly, tx = t.x0 + lx;
+      const bool valid = m_tile < p.m_tiles && ty < p.th && tx < p.tw;
+      const int oy = ty * p.osy + p.ooy, ox = tx * p.osx + p.oox;
+      const int64_t pix = ((int64_t)t.img * p.e.out_h + oy) * p.e.out_w + ox;
+      mbar_wait(bar_accf0 + 8u * (uint32_t)acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
+      if (p.e.fast) {
+        if (p.e.residual)
+          epilogue_pixel_fast<true>(p.e, sbias, s_gamma, taddr, cb, ce, t.n0, valid, pix, &s_ss[acc][0][0], row, half, nsplit,
+                                    1 + q);
+        else
+          epilogue_pixel_fast<false>(p.e, sbias, s_gamma, taddr, cb, ce, t.n0, valid, pix, &s_ss[acc][0][0], row, half, nsplit,
+                                     1 + q);
+      } else {
+        epilogue_pixel(p.e, taddr, cb, ce, t.n0, valid, t.img, oy, ox, pix);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(lead_acce0 + 8u * (uint32_t)acc);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody frees TMEM or exits while the peer may still signal / read
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Host side: tensor maps, tiling choice, launch
 // ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -285,6 +488,8 @@ int tc_ensure_init() {
     RV_CUDA(cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 2048)));
     RV_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 2048)));
     RV_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 2048)));
+    RV_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 2048)));
+    RV_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 2048)));
     g_attr_set[dev] = true;
   }
   return 0;
@@ -441,8 +646,12 @@ static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_
   fill_epi(&p.e, d, bias, residual, y, nf);
   p.e.fast = epi_fast_ok(p.e, d, bias, nf, p.bn * p.n_tiles);
   RV_CHECK_ARG(!nf || p.e.fast, "conv_tc: fused norm needs cout %% 16 == 0, aligned NHWC bf16 tensors, per-channel bias, no affine");
+  // CTA pairs (cta_group::2) whenever the B tile splits into two swizzle-aligned halves
+  static const bool no_pair = getenv("RGBAVAE_DISABLE_PAIR") != nullptr;
+  const bool pair = !no_pair && p.bn % 32 == 0 && p.bk >= 32 && p.m_tiles >= 2;
   p.a_bytes = 128u * (uint32_t)p.bk * 2u;
-  const uint32_t b_bytes = (uint32_t)p.bn * (uint32_t)p.bk * 2u;
+  const uint32_t b_rows = pair ? (uint32_t)p.bn / 2u : (uint32_t)p.bn;
+  const uint32_t b_bytes = b_rows * (uint32_t)p.bk * 2u;
   p.tx_bytes = p.a_bytes + b_bytes;
   p.stage_bytes = (p.a_bytes + b_bytes + 1023u) & ~1023u;
   if (p.a_bytes % 1024u) {  // bk == 16: keep B 1024-aligned too
@@ -470,17 +679,25 @@ static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_
   {
     cuuint64_t dims[2] = {(cuuint64_t)k_extent, (cuuint64_t)d->cout};
     cuuint64_t str[1] = {(cuuint64_t)w_ld * 2u};
-    cuuint32_t box[2] = {(cuuint32_t)p.bk, (cuuint32_t)p.bn};
+    cuuint32_t box[2] = {(cuuint32_t)p.bk, b_rows};
     if (int rc = tc_encode_map(&map_b, w, 2, dims, str, box, sw)) return rc;
   }
-  const int total_tiles = p.m_tiles * p.n_tiles;
-  int grid = total_tiles < num_sms() ? total_tiles : num_sms();
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   const double flops = 2.0 * (double)d->n * d->oh * d->ow * d->cout * d->cin * d->ksize * d->ksize / (phase >= 0 ? 4.0 : 1.0);
   LaunchScope scope(CAT_CONV_TC, st, flops);
-  if (p.bk == 64) conv_tc_kernel<4><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
-  else if (p.bk == 32) conv_tc_kernel<2><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
-  else conv_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+  if (pair) {
+    const int total_pt = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    const int max_pairs = num_sms() / 2;
+    const int grid = 2 * (total_pt < max_pairs ? total_pt : max_pairs);
+    if (p.bk == 64) conv_tc2_kernel<4><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+    else conv_tc2_kernel<2><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+  } else {
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+    if (p.bk == 64) conv_tc_kernel<4><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+    else if (p.bk == 32) conv_tc_kernel<2><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+    else conv_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+  }
   RV_LAUNCH_CHECK();
   return 0;
 }
