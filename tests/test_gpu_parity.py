@@ -195,3 +195,16 @@ def test_tiled_encode_decode_matches_oracle_tiling(R, oracle_model, arch):
         assert rel(vae.encode(x.cuda()).latent_dist.parameters, untiled) < 1e-4
     finally:
         oracle.config.sample_size = old
+
+
+def test_cuda_graph_replay_equals_eager(R, oracle_model):
+    model = R.RgbaVAE(gpu_model(R, oracle_model, "qwen", torch.bfloat16))
+    for seed in (1, 2):  # second call replays the captured graph with new inputs
+        x = O.synthetic_rgba(2, 128, 192, seed=seed).cuda().bfloat16()
+        noise = torch.randn(2, 16, 16, 24, generator=torch.Generator().manual_seed(seed)).cuda().bfloat16()
+        recon_e, post_e = model(x, noise=noise)
+        m_e = R.validation_metrics(recon_e, x, ("white",))
+        recon_g, mom_g, met_g = model.forward_graphed(x, noise)
+        assert torch.equal(recon_g, recon_e) and torch.equal(mom_g, post_e.parameters)
+        assert torch.equal(met_g[:, 0], m_e["psnr_white"])
+    model.reset_graphs()
