@@ -281,7 +281,7 @@ def gpu_arm(a):
     e2e_value = mpix_step * a.steps / (ms_e2e / 1e3)
     conv = prof["conv_tc"]
     ach = conv["work"] / 1e12 / (conv["ms"] / 1e3) if conv["ms"] > 0 else 0.0
-    roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv / GEMM, all launches of one step)",
+    roof = {"bound": "tensor", "kernel": "conv_tc_kernel / conv_tc2_kernel (CTA pairs) / conv_halo_kernel: every tcgen05 implicit-GEMM conv and GEMM launch of one step",
             "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
             "peak_source": f"{pk['source']} bf16_tflops_sustained", "launches_per_step": conv["launches"],
             "ms_per_step": conv["ms"], "algorithmic_tflop_per_step": conv["work"] / 1e12}

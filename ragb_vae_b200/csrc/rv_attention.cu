@@ -10,11 +10,12 @@
 //               (6 x 16 KB) and V^T chunks (6 x [128 d x 64 keys] = 16 KB) through one 5-slot ring,
 //               in exactly the order the MMA warp consumes them
 //   warp 1      tcgen05.mma issuer: S = Q K^T into TMEM columns [384, 512), O += P V into [0, 384)
-//   warps 4-11  softmax (thread = query row; the two warps of a lane quarter split the 128 keys):
+//   warps 2-17  softmax (thread = query row; the four warps of a lane quarter split the 128 keys):
 //               S -> registers, running max with lazy rescale (O is only rescaled when the max grows by
 //               more than 2^8), P = exp2(...) written to shared memory as the bf16 K-major SW128 A
 //               operand of the PV MMA; finally O / l -> bf16 global
 // TMEM: O 384 fp32 columns + S 128 = 512.  Shared memory: Q 96 KB + ring 80 KB + P 32 KB.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -27,9 +28,14 @@ constexpr int FA_DCH = FA_D / 64;        // 64-wide chunks of d
 constexpr int FA_BQ = 128, FA_BK = 128;
 constexpr int FA_RING = 5;
 constexpr uint32_t FA_SLOT = 16384;      // ring slot: a K chunk [128 keys x 64 d] or a V^T chunk [128 d x 64 keys]
+                                         // (CTA pairs: each CTA holds half of the 128 rows, 8 KB)
 constexpr uint32_t FA_Q_BYTES = FA_DCH * 16384;
 constexpr uint32_t FA_P_BYTES = 2 * 16384;
-constexpr int FA_THREADS = 384;          // warps: 0 TMA, 1 MMA, 2-3 idle, 4-11 softmax
+constexpr int FA_NSPLIT = 4;             // softmax warps per TMEM lane quarter (each owns 128/NSPLIT keys of a block)
+constexpr int FA_SM_WARPS = 4 * FA_NSPLIT;
+constexpr int FA_THREADS = 64 + 32 * FA_SM_WARPS;   // warps: 0 TMA, 1 MMA, 2.. softmax
+constexpr int FA_KCOLS = 128 / FA_NSPLIT;  // S columns per softmax thread
+constexpr int FA_OCOLS = FA_D / FA_NSPLIT; // O columns per softmax thread (rescale / output)
 constexpr float FA_RESCALE_THRESHOLD = 8.0f;
 
 struct FaParams {
@@ -50,6 +56,11 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
@@ -59,14 +70,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+// PAIR: two CTAs (256 queries) issue M = 256 MMAs and split every K / V^T chunk between their shared memories
+// (cta_group::2), which halves the B-operand reads that bound the single-CTA form.
+template <bool PAIR>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                   const __grid_constant__ CUtensorMap map_vt, const __grid_constant__ FaParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_q, bar_full[FA_RING], bar_empty[FA_RING], bar_sfull, bar_sempty, bar_pfull, bar_pvdone;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_xmax[2][2][128];  // [block parity][column half][row]
-  __shared__ float s_xsum[2][128];
+  __shared__ float s_xmax[2][FA_NSPLIT][128];  // [block parity][column part][row]
+  __shared__ float s_xsum[FA_NSPLIT][128];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -74,7 +88,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const int nb = p.tokens / FA_BK;
   const int qblocks = p.tokens / FA_BQ;
   const int img = blockIdx.x / qblocks;
-  const int q0 = (blockIdx.x - img * qblocks) * FA_BQ;
+  const int q0 = (blockIdx.x - img * qblocks) * FA_BQ;   // consecutive blocks = the two CTAs of a pair
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const uint32_t slot_bytes = PAIR ? FA_SLOT / 2 : FA_SLOT;
+  const int nshare = PAIR ? 2 : 1;
 
   if (warp == 0 && lane == 0) {
     mbar_init(smem_u32(&bar_q), 1);
@@ -83,30 +101,45 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     mbar_init(smem_u32(&bar_sfull), 1);
-    mbar_init(smem_u32(&bar_sempty), 8);
-    mbar_init(smem_u32(&bar_pfull), 8);
+    mbar_init(smem_u32(&bar_sempty), FA_SM_WARPS * nshare);
+    mbar_init(smem_u32(&bar_pfull), FA_SM_WARPS * nshare);
     mbar_init(smem_u32(&bar_pvdone), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
   const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
   const uint32_t sfull = smem_u32(&bar_sfull), sempty = smem_u32(&bar_sempty), pfull = smem_u32(&bar_pfull),
                  pvdone = smem_u32(&bar_pvdone), qbar = smem_u32(&bar_q);
+  // barriers the MMA issuer (leader CTA) waits on, as cluster addresses, for signals that come from both CTAs
+  const uint32_t lead_full0 = PAIR ? mapa_rank(full0, 0) : full0;
+  const uint32_t lead_q = PAIR ? mapa_rank(qbar, 0) : qbar;
+  const uint32_t lead_sempty = PAIR ? mapa_rank(sempty, 0) : sempty;
+  const uint32_t lead_pfull = PAIR ? mapa_rank(pfull, 0) : pfull;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
-      mbar_arrive_expect_tx(qbar, FA_Q_BYTES);
-      for (int c = 0; c < FA_DCH; ++c) tma_load_2d(q_smem + c * 16384u, &map_q, qbar, c * 64, img * p.tokens + q0);
+      if (leader) mbar_arrive_expect_tx(qbar, FA_Q_BYTES * nshare);
+      for (int c = 0; c < FA_DCH; ++c) {
+        if (PAIR) tma2_load_2d(q_smem + c * 16384u, &map_q, lead_q, c * 64, img * p.tokens + q0);
+        else tma_load_2d(q_smem + c * 16384u, &map_q, qbar, c * 64, img * p.tokens + q0);
+      }
     }
     __syncwarp();
     uint32_t slot = 0, par = 0;
@@ -116,8 +149,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int c = 0; c < FA_DCH; ++c) {
           mbar_wait(empty0 + 8u * slot, par ^ 1u);
           if (elect_one()) {
-            mbar_arrive_expect_tx(full0 + 8u * slot, 16384u);
-            tma_load_2d(ring + slot * FA_SLOT, &map_k, full0 + 8u * slot, c * 64, img * p.tokens + step * FA_BK);
+            if (leader) mbar_arrive_expect_tx(full0 + 8u * slot, slot_bytes * nshare);
+            if (PAIR)   // this CTA's 64 of the block's 128 keys
+              tma2_load_2d(ring + slot * slot_bytes, &map_k, lead_full0 + 8u * slot, c * 64,
+                           img * p.tokens + step * FA_BK + (int)rank * 64);
+            else
+              tma_load_2d(ring + slot * slot_bytes, &map_k, full0 + 8u * slot, c * 64, img * p.tokens + step * FA_BK);
           }
           __syncwarp();
           if (++slot == FA_RING) { slot = 0; par ^= 1u; }
@@ -129,8 +166,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           for (int h = 0; h < 3; ++h) {
             mbar_wait(empty0 + 8u * slot, par ^ 1u);
             if (elect_one()) {
-              mbar_arrive_expect_tx(full0 + 8u * slot, FA_SLOT);
-              tma_load_3d(ring + slot * FA_SLOT, &map_vt, full0 + 8u * slot, j * FA_BK + kc * 64, h * 128, img);
+              if (leader) mbar_arrive_expect_tx(full0 + 8u * slot, slot_bytes * nshare);
+              if (PAIR)  // this CTA's 64 of the 128 d-rows of the chunk
+                tma2_load_3d(ring + slot * slot_bytes, &map_vt, lead_full0 + 8u * slot, j * FA_BK + kc * 64,
+                             h * 128 + (int)rank * 64, img);
+              else
+                tma_load_3d(ring + slot * slot_bytes, &map_vt, full0 + 8u * slot, j * FA_BK + kc * 64, h * 128, img);
             }
             __syncwarp();
             if (++slot == FA_RING) { slot = 0; par ^= 1u; }
@@ -139,12 +180,21 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
     const uint32_t idesc_o = idesc_s;  // PV in three N = 128 thirds of d
     const uint64_t hi = make_smem_desc(0u, 1024u, 2u);
     const uint32_t q_lo = (q_smem & 0x3FFFFu) >> 4, p_lo = (p_smem & 0x3FFFFu) >> 4, ring_lo = (ring & 0x3FFFFu) >> 4;
     const uint32_t s_tmem = tmem_base + 384u;
     uint32_t slot = 0, par = 0;
+    auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accf) {
+      if (PAIR) umma2_bf16(d, a, b, idesc, accf);
+      else umma_bf16(d, a, b, idesc, accf);
+    };
+    auto commit = [&](uint32_t bar) {
+      if (PAIR) umma2_commit_both(bar);
+      else umma_commit(bar);
+    };
+    if (leader) {
     mbar_wait(qbar, 0);
     auto issue_qk = [&](int j) {
       // S = Q K(j)^T : 6 chunks x 4 k-steps, N = 128
@@ -153,13 +203,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         tc_fence_after();
         if (elect_one()) {
           const uint64_t ad = hi | (uint64_t)(q_lo + c * 1024u);
-          const uint64_t bd = hi | (uint64_t)(ring_lo + slot * (FA_SLOT >> 4));
-          umma_bf16(s_tmem, ad, bd, idesc_s, c == 0 ? 0u : 1u);
-          umma_bf16(s_tmem, ad + 2u, bd + 2u, idesc_s, 1u);
-          umma_bf16(s_tmem, ad + 4u, bd + 4u, idesc_s, 1u);
-          umma_bf16(s_tmem, ad + 6u, bd + 6u, idesc_s, 1u);
-          umma_commit(empty0 + 8u * slot);
-          if (c == FA_DCH - 1) umma_commit(sfull);
+          const uint64_t bd = hi | (uint64_t)(ring_lo + slot * (slot_bytes >> 4));
+          mma(s_tmem, ad, bd, idesc_s, c == 0 ? 0u : 1u);
+          mma(s_tmem, ad + 2u, bd + 2u, idesc_s, 1u);
+          mma(s_tmem, ad + 4u, bd + 4u, idesc_s, 1u);
+          mma(s_tmem, ad + 6u, bd + 6u, idesc_s, 1u);
+          commit(empty0 + 8u * slot);
+          if (c == FA_DCH - 1) commit(sfull);
         }
         __syncwarp();
         if (++slot == FA_RING) { slot = 0; par ^= 1u; }
@@ -181,75 +231,69 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           tc_fence_after();
           if (elect_one()) {
             const uint64_t ad = hi | (uint64_t)(p_lo + kc * 1024u);
-            const uint64_t bd = hi | (uint64_t)(ring_lo + slot * (FA_SLOT >> 4));
+            const uint64_t bd = hi | (uint64_t)(ring_lo + slot * (slot_bytes >> 4));
             const uint32_t d_tmem = tmem_base + (uint32_t)h * 128u;
-            umma_bf16(d_tmem, ad, bd, idesc_o, (j == 0 && kc == 0) ? 0u : 1u);
-            umma_bf16(d_tmem, ad + 2u, bd + 2u, idesc_o, 1u);
-            umma_bf16(d_tmem, ad + 4u, bd + 4u, idesc_o, 1u);
-            umma_bf16(d_tmem, ad + 6u, bd + 6u, idesc_o, 1u);
-            umma_commit(empty0 + 8u * slot);
-            if (kc == 1 && h == 2) umma_commit(pvdone);
+            mma(d_tmem, ad, bd, idesc_o, (j == 0 && kc == 0) ? 0u : 1u);
+            mma(d_tmem, ad + 2u, bd + 2u, idesc_o, 1u);
+            mma(d_tmem, ad + 4u, bd + 4u, idesc_o, 1u);
+            mma(d_tmem, ad + 6u, bd + 6u, idesc_o, 1u);
+            commit(empty0 + 8u * slot);
+            if (kc == 1 && h == 2) commit(pvdone);
           }
           __syncwarp();
           if (++slot == FA_RING) { slot = 0; par ^= 1u; }
         }
     }
-  } else if (warp >= 4) {
+    }  // leader
+  } else if (warp >= 2) {
     // ------------------------------ softmax / correction / output ------------------------------
-    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int q = warp & 3, part = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t s_taddr = lane_addr + 384u + (uint32_t)half * 64u;
-    const uint32_t o_taddr = lane_addr + (uint32_t)half * 192u;
+    const uint32_t s_taddr = lane_addr + 384u + (uint32_t)part * FA_KCOLS;
+    const uint32_t o_taddr = lane_addr + (uint32_t)part * FA_OCOLS;
     const int bar_id = 1 + q;
     float m_used = -INFINITY, l = 0.f;
-    // P row base: key chunk `half`, row `row`; 16-byte unit u of the row lives at ((u ^ (row & 7)) * 16)
-    const uint32_t p_row = p_smem + (uint32_t)half * 16384u + (uint32_t)row * 128u;
+    // P row: key chunk (64 keys, 16 KB) part/2, 16-byte units (part%2)*4 .. +4 of the row; unit u lives at ((u ^ (row & 7)) * 16)
+    const uint32_t p_row = p_smem + (uint32_t)(part >> 1) * 16384u + (uint32_t)row * 128u;
+    const uint32_t u0 = (uint32_t)(part & 1) * 4u;
     const uint32_t sw = (uint32_t)(row & 7);
     for (int j = 0; j < nb; ++j) {
       mbar_wait(sfull, (uint32_t)(j & 1));
       tc_fence_after();
-      uint32_t s0[32], s1[32];
+      uint32_t s0[FA_KCOLS];
       tmem_ld32(s_taddr, s0);
-      tmem_ld32(s_taddr + 32u, s1);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(sempty);
+      if (lane == 0) { if (PAIR) mbar_arrive_cluster(lead_sempty); else mbar_arrive(sempty); }
       float mx = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
-      s_xmax[j & 1][half][row] = mx;
-      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-      mx = fmaxf(mx, s_xmax[j & 1][half ^ 1][row]) * p.scale_log2;
+      for (int i = 0; i < FA_KCOLS; ++i) mx = fmaxf(mx, __uint_as_float(s0[i]));
+      s_xmax[j & 1][part][row] = mx;
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * FA_NSPLIT) : "memory");
+#pragma unroll
+      for (int pp = 0; pp < FA_NSPLIT; ++pp) mx = fmaxf(mx, s_xmax[j & 1][pp][row]);
+      mx *= p.scale_log2;
       float alpha = 1.0f;
       bool need = false;
       if (j == 0) {
         m_used = mx;
       } else if (mx - m_used > FA_RESCALE_THRESHOLD) {
-        alpha = exp2f(m_used - mx);
+        alpha = fast_exp2(m_used - mx);
         m_used = mx;
         l *= alpha;
         need = true;
       }
       // probabilities (bf16) and their row sum
-      uint32_t pk[32];
+      uint32_t pk[FA_KCOLS / 2];
       float sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float a = exp2f(fmaf(__uint_as_float(s0[2 * i]), p.scale_log2, -m_used));
-        const float b = exp2f(fmaf(__uint_as_float(s0[2 * i + 1]), p.scale_log2, -m_used));
-        const __nv_bfloat162 ab = __floats2bfloat162_rn(a, b);
-        pk[i] = *reinterpret_cast<const uint32_t*>(&ab);
-        sum += __low2float(ab) + __high2float(ab);
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float a = exp2f(fmaf(__uint_as_float(s1[2 * i]), p.scale_log2, -m_used));
-        const float b = exp2f(fmaf(__uint_as_float(s1[2 * i + 1]), p.scale_log2, -m_used));
-        const __nv_bfloat162 ab = __floats2bfloat162_rn(a, b);
-        pk[16 + i] = *reinterpret_cast<const uint32_t*>(&ab);
-        sum += __low2float(ab) + __high2float(ab);
+      for (int i = 0; i < FA_KCOLS / 2; ++i) {
+        const float a = fast_exp2(fmaf(__uint_as_float(s0[2 * i]), p.scale_log2, -m_used));
+        const float b = fast_exp2(fmaf(__uint_as_float(s0[2 * i + 1]), p.scale_log2, -m_used));
+        pk[i] = pack_bf16x2(a, b);
+        sum += a + b;
       }
       l += sum;
       // the previous PV must be complete before P is overwritten or O is rescaled
@@ -257,7 +301,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         mbar_wait(pvdone, (uint32_t)((j - 1) & 1));
         tc_fence_after();
         if (__any_sync(0xffffffffu, need)) {
-          for (int c = 0; c < 6; ++c) {
+          for (int c = 0; c < FA_OCOLS / 32; ++c) {
             uint32_t o[32];
             tmem_ld32(o_taddr + (uint32_t)c * 32u, o);
             tmem_ld_wait();
@@ -269,25 +313,29 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         }
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const uint32_t addr = p_row + (((uint32_t)u ^ sw) << 4);
+      for (int u = 0; u < FA_KCOLS / 8; ++u) {
+        const uint32_t addr = p_row + (((u0 + (uint32_t)u) ^ sw) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]),
                      "r"(pk[4 * u + 3])
                      : "memory");
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (PAIR) asm volatile("fence.proxy.async;" ::: "memory");
+      else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pfull);
+      if (lane == 0) { if (PAIR) mbar_arrive_cluster(lead_pfull); else mbar_arrive(pfull); }
     }
     // ---- output: O / l ----
-    s_xsum[half][row] = l;
+    s_xsum[part][row] = l;
     mbar_wait(pvdone, (uint32_t)((nb - 1) & 1));
     tc_fence_after();
-    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-    const float inv = 1.0f / (s_xsum[0][row] + s_xsum[1][row]);
-    __nv_bfloat16* orow = p.out + ((int64_t)img * p.tokens + q0 + row) * p.ld_out + half * 192;
-    for (int c = 0; c < 6; ++c) {
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * FA_NSPLIT) : "memory");
+    float lt = 0.f;
+#pragma unroll
+    for (int pp = 0; pp < FA_NSPLIT; ++pp) lt += s_xsum[pp][row];
+    const float inv = 1.0f / lt;
+    __nv_bfloat16* orow = p.out + ((int64_t)img * p.tokens + q0 + row) * p.ld_out + part * FA_OCOLS;
+    for (int c = 0; c < FA_OCOLS / 32; ++c) {
       uint32_t o[32];
       tmem_ld32(o_taddr + (uint32_t)c * 32u, o);
       tmem_ld_wait();
@@ -300,10 +348,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -327,18 +377,24 @@ extern "C" int rv_attention(const void* q, const void* k, int64_t ld_qk, const v
   RV_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)vt % 16 == 0) && ((uintptr_t)out % 16 == 0),
                "attention: tensors must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  // CTA pairs are built (template PAIR) but off by default: measured 7.9 ms vs 7.4 ms per step for the single-CTA
+  // form -- the kernel is bound by the softmax warps, not by the B-operand reads a pair would halve.
+  static const bool want_pair = getenv("RGBAVAE_ATTN_PAIR") != nullptr;
+  const bool pair = want_pair && tokens % 256 == 0;  // the two CTAs of a pair take adjacent query blocks of one image
+  const cuuint32_t share = pair ? 2u : 1u;
   CUtensorMap mq, mk, mv;
   {
     cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)((int64_t)n_img * tokens)};
     cuuint64_t str[1] = {(cuuint64_t)ld_qk * 2u};
     cuuint32_t box[2] = {64, 128};
     if (int rc = tc_encode_map(&mq, q, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    if (int rc = tc_encode_map(&mk, k, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    cuuint32_t boxk[2] = {64, 128u / share};
+    if (int rc = tc_encode_map(&mk, k, 2, dims, str, boxk, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   }
   {
     cuuint64_t dims[3] = {(cuuint64_t)tokens, (cuuint64_t)d, (cuuint64_t)n_img};
     cuuint64_t str[2] = {(cuuint64_t)tokens * 2u, (cuuint64_t)tokens * 2u * d};
-    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t box[3] = {64, 128u / share, 1};
     if (int rc = tc_encode_map(&mv, vt, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   }
   const size_t smem = FA_Q_BYTES + FA_RING * FA_SLOT + FA_P_BYTES + 1024;
@@ -347,7 +403,8 @@ extern "C" int rv_attention(const void* q, const void* k, int64_t ld_qk, const v
     int dev = 0;
     RV_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !g_fa_attr[dev]) {
-      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       g_fa_attr[dev] = true;
     }
   }
@@ -359,7 +416,23 @@ extern "C" int rv_attention(const void* q, const void* k, int64_t ld_qk, const v
   p.out = (__nv_bfloat16*)out;
   const int grid = n_img * (tokens / FA_BQ);
   LaunchScope scope(CAT_ATTN, st, 4.0 * (double)n_img * tokens * tokens * d);
-  flash_attn_kernel<<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, p);
+  if (pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(FA_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RV_CUDA(cudaLaunchKernelEx(&cfg, flash_attn_kernel<true>, mq, mk, mv, p));
+  } else {
+    flash_attn_kernel<false><<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, p);
+  }
   RV_LAUNCH_CHECK();
   return 0;
 }

@@ -44,48 +44,60 @@ struct LossParams {
 
 // AlphaVaeLoss.reconstruction_loss (reference src/models/losses.py:67-83; oracle
 // reconstruction_loss): d = t_rgb*at - p_rgb*ap, da = at - ap, l = d^2 - 2*Eb*d*da + Eb2*da^2.
+// Raw 16-byte vectors are kept in registers (4 per tensor per vector index) and converted element by element, two
+// independent vector indices per sweep: 16 loads in flight per thread at ~64 registers, so 8 blocks stay resident per SM.
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256) recon_loss_kernel(const T* __restrict__ pred, const T* __restrict__ target,
+struct PlaneVec {
+  Vec16<T> v[4];
+  float s[4];
+  __device__ __forceinline__ void load(const T* base, int64_t hw, int64_t i, bool ok) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (VEC == 1) s[c] = ok ? ldf(base + c * hw + i) : 0.f;
+      else if (ok) v[c].load(base + c * hw + i * VEC);
+      else v[c].zero();
+    }
+  }
+  __device__ __forceinline__ float get(int c, int j) const { return VEC == 1 ? s[c] : v[c].get(j); }
+};
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256, 4) recon_loss_kernel(const T* __restrict__ pred, const T* __restrict__ target,
                                                         double* __restrict__ partial, int64_t hw, LossParams lp) {
   const int n = blockIdx.y;
   const T* p = pred + (int64_t)n * 4 * hw;
   const T* t = target + (int64_t)n * 4 * hw;
   float acc[1] = {0.f};
   const int64_t nvec = hw / VEC;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    float pv[4][VEC], tv[4][VEC];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  constexpr int UN = 1;
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < nvec; i0 += UN * stride) {
+    PlaneVec<T, VEC> pv[UN], tv[UN];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      if (VEC == 1) {
-        pv[c][0] = ldf(p + c * hw + i);
-        tv[c][0] = ldf(t + c * hw + i);
-      } else {
-        Vec16<T> a, b;
-        a.load(p + c * hw + i * VEC);
-        b.load(t + c * hw + i * VEC);
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          pv[c][j] = a.get(j);
-          tv[c][j] = b.get(j);
-        }
-      }
+    for (int u = 0; u < UN; ++u) {
+      const int64_t i = i0 + u * stride;
+      pv[u].load(p, hw, i, i < nvec);
+      tv[u].load(t, hw, i, i < nvec);
     }
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      if (lp.naive) {
+    for (int u = 0; u < UN; ++u) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float d = pv[c][j] - tv[c][j];
-          acc[0] = fmaf(d, d, acc[0]);
-        }
-      } else {
-        float at = (tv[3][j] + 1.0f) * 0.5f, ap = (pv[3][j] + 1.0f) * 0.5f;
-        float da = at - ap;
+      for (int j = 0; j < VEC; ++j) {
+        if (lp.naive) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          // separately rounded products (no fma contraction): identical inputs give exactly 0
-          float d = __fsub_rn(__fmul_rn(tv[c][j], at), __fmul_rn(pv[c][j], ap));
-          acc[0] += d * d - 2.0f * lp.eb[c] * d * da + lp.eb2[c] * da * da;
+          for (int c = 0; c < 4; ++c) {
+            float d = pv[u].get(c, j) - tv[u].get(c, j);
+            acc[0] = fmaf(d, d, acc[0]);
+          }
+        } else {
+          float at = (tv[u].get(3, j) + 1.0f) * 0.5f, ap = (pv[u].get(3, j) + 1.0f) * 0.5f;
+          float da = at - ap;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            // separately rounded products (no fma contraction): identical inputs give exactly 0
+            float d = __fsub_rn(__fmul_rn(tv[u].get(c, j), at), __fmul_rn(pv[u].get(c, j), ap));
+            acc[0] += d * d - 2.0f * lp.eb[c] * d * da + lp.eb2[c] * da * da;
+          }
         }
       }
     }
@@ -112,7 +124,7 @@ struct PsnrParams {
 // background, squared error summed over (3,H,W) (compute_psnr, rgba_vae_stage.py:712-715) and
 // |alpha_recon - alpha_target| (rgba_vae_stage.py:749-753).
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256) composite_psnr_kernel(const T* __restrict__ recon, const T* __restrict__ target,
+__global__ void __launch_bounds__(256, 4) composite_psnr_kernel(const T* __restrict__ recon, const T* __restrict__ target,
                                                             double* __restrict__ partial, int64_t hw, PsnrParams pp) {
   const int n = blockIdx.y;
   const T* p = recon + (int64_t)n * 4 * hw;
@@ -121,37 +133,38 @@ __global__ void __launch_bounds__(256) composite_psnr_kernel(const T* __restrict
 #pragma unroll
   for (int k = 0; k <= MAX_BG; ++k) acc[k] = 0.f;
   const int64_t nvec = hw / VEC;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    float pv[4][VEC], tv[4][VEC];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  constexpr int UN = 1;
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < nvec; i0 += UN * stride) {
+    PlaneVec<T, VEC> pv[UN], tv[UN];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      if (VEC == 1) {
-        pv[c][0] = ldf(p + c * hw + i);
-        tv[c][0] = ldf(t + c * hw + i);
-      } else {
-        Vec16<T> a, b;
-        a.load(p + c * hw + i * VEC);
-        b.load(t + c * hw + i * VEC);
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          pv[c][j] = a.get(j);
-          tv[c][j] = b.get(j);
-        }
-      }
+    for (int u = 0; u < UN; ++u) {
+      const int64_t i = i0 + u * stride;
+      pv[u].load(p, hw, i, i < nvec);
+      tv[u].load(t, hw, i, i < nvec);
     }
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      const float ap = pv[3][j], at = tv[3][j];
-      acc[MAX_BG] += fabsf(ap - at);
+    for (int u = 0; u < UN; ++u) {
 #pragma unroll
-      for (int b = 0; b < MAX_BG; ++b) {
-        if (b < pp.nbg) {
+      for (int j = 0; j < VEC; ++j) {
+        const float ap = pv[u].get(3, j), at = tv[u].get(3, j);
+        acc[MAX_BG] += fabsf(ap - at);
+        float pr[3], tr[3];
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float cp = pv[c][j] * ap + pp.bg[b][c] * (1.0f - ap);
-            float ct = tv[c][j] * at + pp.bg[b][c] * (1.0f - at);
-            float d = cp - ct;
-            acc[b] = fmaf(d, d, acc[b]);
+        for (int c = 0; c < 3; ++c) {
+          pr[c] = pv[u].get(c, j);
+          tr[c] = tv[u].get(c, j);
+        }
+#pragma unroll
+        for (int b = 0; b < MAX_BG; ++b) {
+          if (b < pp.nbg) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float cp = pr[c] * ap + pp.bg[b][c] * (1.0f - ap);
+              float ct = tr[c] * at + pp.bg[b][c] * (1.0f - at);
+              float d = cp - ct;
+              acc[b] = fmaf(d, d, acc[b]);
+            }
           }
         }
       }
