@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 7
+#define RV_ABI_VERSION 8
 #define RV_PROF_CATEGORIES 9
 
 int rv_abi_version(void);
@@ -186,6 +186,28 @@ int rv_composite_psnr(const void* recon, const void* target, const float* bgs_ho
                       float* out, double* partial, int n, int64_t hw, int dtype, void* stream);
 /* number of partial blocks per sample the two reductions above use for `hw` pixels */
 int rv_reduce_blocks(int64_t hw);
+
+/* ---- training-step building blocks (src/training/rgba_vae_stage.py:433-523) ------------------ */
+/* d loss / d pred of AlphaVaeLoss.reconstruction_loss (losses.py:67-83); grad_scale = upstream gradient times the
+ * reduction factor (1/(B*3*HW) for reduce_mean -- 1/(B*4*HW) for the naive MSE -- else 1/B).  NCHW [n][4][hw]. */
+int rv_recon_loss_bwd(const void* pred, const void* target, const float* eb_host, const float* eb2_host,
+                      int naive_mse, float grad_scale, void* dpred, int n, int64_t hw, int dtype, void* stream);
+/* Backward of posterior.sample() (+ kl_weight * posterior.kl()): dmoments NCHW [n][2*zc][hw] from dz [n][zc][hw]
+ * (dz / noise may both be NULL for the KL term alone); the logvar gradient is zero outside the clamp range. */
+int rv_reparam_bwd(const void* moments, const void* noise, const void* dz, void* dmoments, int n, int zc,
+                   int64_t hw, int dtype, float kl_weight, void* stream);
+/* Backward of rv_rmsnorm_silu: dx, and dgamma_scaled[c] += d loss / d (gamma*sqrt(C)) (fp32, caller zeroes it;
+ * d loss / d gamma = sqrt(C) * dgamma_scaled).  gamma_scaled = gamma * sqrt(C).  c in {96, 192, 384}. */
+int rv_rmsnorm_silu_bwd(const void* x, const float* gamma_scaled, const void* dy, void* dx, float* dgamma_scaled,
+                        int64_t pixels, int c, int dtype, int apply_silu, void* stream);
+/* *out += sum(g^2) over a flat fp32 gradient buffer (accelerator.clip_grad_norm_, rgba_vae_stage.py:520-521). */
+int rv_grad_sqnorm(const float* g, int64_t n, float* out, void* stream);
+/* torch.optim.AdamW step (rgba_vae_stage.py:321-331, 522) over flat fp32 buffers, fused with the gradient scaling
+ * of a data-parallel SUM all-reduce (grad_scale = 1/world) and with clip_grad_norm_ (sqnorm = device pointer to the
+ * squared norm of the UNscaled gradient, max_norm <= 0 disables).  p_bf16 (optional) receives the bf16 copy. */
+int rv_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, float grad_scale, const float* sqnorm,
+                  float max_norm, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,270 @@
+// Building blocks of the rgba_vae training step (reference src/training/rgba_vae_stage.py:433-523) that are not
+// convolutions: backward of the AlphaVAE reconstruction loss, of the reparameterisation (+KL), of RMS-norm + SiLU,
+// the global gradient norm, and the fused clip + AdamW update over flat parameter buffers.
+// All HBM-bound streaming kernels; fp32 arithmetic.
+#include "rv_common.cuh"
+
+namespace rv {
+
+struct LossBwdParams {
+  float eb[3], eb2[3];
+  int naive;
+  float scale;  // upstream gradient x reduction factor (1/(B*3*HW) for reduce_mean, 1/B otherwise)
+};
+
+// d loss / d pred for AlphaVaeLoss.reconstruction_loss (src/models/losses.py:67-83):
+//   ap = (p3+1)/2, at = (t3+1)/2, d_c = t_c*at - p_c*ap, da = at - ap, l_c = d_c^2 - 2 Eb_c d_c da + Eb2_c da^2
+template <typename T>
+__global__ void __launch_bounds__(256) recon_loss_bwd_kernel(const T* __restrict__ pred, const T* __restrict__ target,
+                                                            T* __restrict__ dpred, int64_t hw, LossBwdParams lp) {
+  const int n = blockIdx.y;
+  const T* p = pred + (int64_t)n * 4 * hw;
+  const T* t = target + (int64_t)n * 4 * hw;
+  T* g = dpred + (int64_t)n * 4 * hw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hw; i += (int64_t)gridDim.x * blockDim.x) {
+    float pv[4], tv[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      pv[c] = ldf(p + c * hw + i);
+      tv[c] = ldf(t + c * hw + i);
+    }
+    if (lp.naive) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) stf(g + c * hw + i, 2.0f * (pv[c] - tv[c]) * lp.scale);
+    } else {
+      const float at = (tv[3] + 1.0f) * 0.5f, ap = (pv[3] + 1.0f) * 0.5f;
+      const float da = at - ap;
+      float dalpha = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float d = tv[c] * at - pv[c] * ap;
+        stf(g + c * hw + i, (2.0f * d - 2.0f * lp.eb[c] * da) * (-ap) * lp.scale);
+        dalpha += -2.0f * d * pv[c] + 2.0f * lp.eb[c] * (pv[c] * da + d) - 2.0f * lp.eb2[c] * da;
+      }
+      stf(g + 3 * hw + i, 0.5f * dalpha * lp.scale);
+    }
+  }
+}
+
+// z = mean + exp(0.5*clamp(logvar,-30,20))*eps ; loss += kl_w * 0.5*sum(mean^2 + var - 1 - logvar)
+// dmoments = [dz + kl_w*mean | (dz*eps*0.5*std + kl_w*0.5*(var-1)) inside the clamp range, else 0]
+template <typename T>
+__global__ void __launch_bounds__(256) reparam_bwd_kernel(const T* __restrict__ moments, const T* __restrict__ noise,
+                                                         const T* __restrict__ dz, T* __restrict__ dmoments, int zc, int64_t hw,
+                                                         float kl_w) {
+  const int n = blockIdx.y;
+  const int64_t per = (int64_t)zc * hw;
+  const T* mean = moments + (int64_t)n * 2 * per;
+  const T* logv = mean + per;
+  T* dmean = dmoments + (int64_t)n * 2 * per;
+  T* dlogv = dmean + per;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
+    const float mu = ldf(mean + i), lv_raw = ldf(logv + i);
+    const float lv = fminf(fmaxf(lv_raw, -30.f), 20.f);
+    const float sd = expf(0.5f * lv);
+    const float gz = dz ? ldf(dz + (int64_t)n * per + i) : 0.f;
+    const float e = noise ? ldf(noise + (int64_t)n * per + i) : 0.f;
+    stf(dmean + i, gz + kl_w * mu);
+    const bool inside = lv_raw >= -30.f && lv_raw <= 20.f;
+    stf(dlogv + i, inside ? (gz * e * 0.5f * sd + kl_w * 0.5f * (sd * sd - 1.0f)) : 0.f);
+  }
+}
+
+// Backward of y = act(x * r * g), r = 1/max(||x||_2, 1e-12), g = gamma*sqrt(C), act = SiLU or identity.
+// One warp walks pixels; a lane owns fixed channels (lane + 32*k), so dgamma accumulates in registers and is
+// flushed with one atomicAdd per (warp, channel) at the end.  dgamma_scaled receives d loss / d g (= d gamma / sqrt(C)).
+template <typename T, int CPL>  // CPL = channels per lane = C / 32
+__global__ void __launch_bounds__(256) rmsnorm_silu_bwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma_scaled,
+                                                              const T* __restrict__ dy, T* __restrict__ dx,
+                                                              float* __restrict__ dgamma_scaled, int64_t pixels, int silu_on) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  constexpr int C = CPL * 32;
+  float g[CPL], dg[CPL];
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) {
+    g[k] = gamma_scaled[lane + 32 * k];
+    dg[k] = 0.f;
+  }
+  for (int64_t p = warp_global; p < pixels; p += warps_total) {
+    float xv[CPL], du[CPL];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      xv[k] = ldf(x + p * C + lane + 32 * k);
+      ss = fmaf(xv[k], xv[k], ss);
+    }
+    ss = warp_sum(ss);
+    const float nrm = sqrtf(ss);
+    const bool clamped = nrm < 1e-12f;
+    const float r = 1.0f / fmaxf(nrm, 1e-12f);
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const float u = xv[k] * r * g[k];
+      float d = ldf(dy + p * C + lane + 32 * k);
+      if (silu_on) {
+        const float s = 1.0f / (1.0f + expf(-u));
+        d *= s * (1.0f + u * (1.0f - s));
+      }
+      du[k] = d;
+      dg[k] = fmaf(xv[k] * r, d, dg[k]);
+      dot = fmaf(xv[k] * g[k], d, dot);
+    }
+    dot = warp_sum(dot);
+    const float corr = clamped ? 0.f : dot * r * r * r;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) stf(dx + p * C + lane + 32 * k, r * g[k] * du[k] - xv[k] * corr);
+  }
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) atomicAdd(dgamma_scaled + lane + 32 * k, dg[k]);
+}
+
+__global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc = fmaf(g[i], g[i], acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(out, v);
+  }
+}
+
+// torch.optim.AdamW semantics (decoupled weight decay, bias correction), gradients scaled by
+// min(1, max_norm / (sqrt(*sqnorm) + 1e-6)) (clip_grad_norm_) and by grad_scale (1/world for an all-reduce SUM).
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, __nv_bfloat16* __restrict__ p_bf16, int64_t n, float lr,
+                                                   float beta1, float beta2, float eps, float wd, float bc1, float bc2,
+                                                   float grad_scale, const float* __restrict__ sqnorm, float max_norm) {
+  float clip = 1.0f;
+  if (sqnorm != nullptr && max_norm > 0.f) {
+    const float nrm = sqrtf(*sqnorm) * grad_scale;
+    clip = fminf(1.0f, max_norm / (nrm + 1e-6f));
+  }
+  const float gs = grad_scale * clip;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gs;
+    float pi = p[i] * (1.0f - lr * wd);
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p[i] = pi;
+    if (p_bf16) p_bf16[i] = __float2bfloat16_rn(pi);
+  }
+}
+
+static inline dim3 train_grid(int64_t items, int n) {
+  unsigned bx = (unsigned)((items + 255) / 256);
+  if (bx > 2048) bx = 2048;
+  if (bx < 1) bx = 1;
+  return dim3(bx, (unsigned)n);
+}
+
+}  // namespace rv
+
+extern "C" {
+
+int rv_recon_loss_bwd(const void* pred, const void* target, const float* eb_host, const float* eb2_host, int naive_mse,
+                      float grad_scale, void* dpred, int n, int64_t hw, int dtype, void* stream) {
+  RV_CHECK_ARG(pred && target && dpred && n > 0 && hw > 0, "recon_loss_bwd: bad argument");
+  RV_CHECK_ARG(naive_mse || (eb_host && eb2_host), "recon_loss_bwd: Eb / Eb2 missing");
+  rv::LossBwdParams lp;
+  for (int c = 0; c < 3; ++c) {
+    lp.eb[c] = eb_host ? eb_host[c] : 0.f;
+    lp.eb2[c] = eb2_host ? eb2_host[c] : 0.f;
+  }
+  lp.naive = naive_mse;
+  lp.scale = grad_scale;
+  cudaStream_t st = (cudaStream_t)stream;
+  rv::LaunchScope scope(rv::CAT_LOSS, st, 12.0 * n * hw * (dtype == RV_F32 ? 4 : 2));
+  if (dtype == RV_F32)
+    rv::recon_loss_bwd_kernel<float><<<rv::train_grid(hw, n), 256, 0, st>>>((const float*)pred, (const float*)target, (float*)dpred, hw, lp);
+  else if (dtype == RV_BF16)
+    rv::recon_loss_bwd_kernel<__nv_bfloat16><<<rv::train_grid(hw, n), 256, 0, st>>>((const __nv_bfloat16*)pred, (const __nv_bfloat16*)target,
+                                                                                (__nv_bfloat16*)dpred, hw, lp);
+  else RV_CHECK_ARG(false, "recon_loss_bwd: bad dtype %d", dtype);
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+int rv_reparam_bwd(const void* moments, const void* noise, const void* dz, void* dmoments, int n, int zc, int64_t hw, int dtype,
+                   float kl_weight, void* stream) {
+  RV_CHECK_ARG(moments && dmoments && n > 0 && zc > 0 && hw > 0, "reparam_bwd: bad argument");
+  RV_CHECK_ARG((dz == nullptr) == (noise == nullptr), "reparam_bwd: dz and noise must be given together");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t per = (int64_t)zc * hw;
+  rv::LaunchScope scope(rv::CAT_REPARAM, st, 6.0 * n * per * (dtype == RV_F32 ? 4 : 2));
+  if (dtype == RV_F32)
+    rv::reparam_bwd_kernel<float><<<rv::train_grid(per, n), 256, 0, st>>>((const float*)moments, (const float*)noise, (const float*)dz,
+                                                                       (float*)dmoments, zc, hw, kl_weight);
+  else if (dtype == RV_BF16)
+    rv::reparam_bwd_kernel<__nv_bfloat16><<<rv::train_grid(per, n), 256, 0, st>>>((const __nv_bfloat16*)moments, (const __nv_bfloat16*)noise,
+                                                                               (const __nv_bfloat16*)dz, (__nv_bfloat16*)dmoments, zc, hw,
+                                                                               kl_weight);
+  else RV_CHECK_ARG(false, "reparam_bwd: bad dtype %d", dtype);
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+int rv_rmsnorm_silu_bwd(const void* x, const float* gamma_scaled, const void* dy, void* dx, float* dgamma_scaled, int64_t pixels,
+                        int c, int dtype, int apply_silu, void* stream) {
+  RV_CHECK_ARG(x && gamma_scaled && dy && dx && dgamma_scaled && pixels > 0, "rmsnorm_silu_bwd: bad argument");
+  RV_CHECK_ARG(c == 96 || c == 192 || c == 384, "rmsnorm_silu_bwd: channels must be 96, 192 or 384 (got %d)", c);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t blocks = (pixels + 63) / 64;
+  const int64_t cap = (int64_t)rv::num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  rv::LaunchScope scope(rv::CAT_NORM, st, 3.0 * pixels * c * (dtype == RV_F32 ? 4 : 2));
+#define RV_NB(T, CPL)                                                                                                     \
+  rv::rmsnorm_silu_bwd_kernel<T, CPL><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, gamma_scaled, (const T*)dy, (T*)dx, \
+                                                                        dgamma_scaled, pixels, apply_silu)
+  if (dtype == RV_F32) {
+    if (c == 96) RV_NB(float, 3);
+    else if (c == 192) RV_NB(float, 6);
+    else RV_NB(float, 12);
+  } else if (dtype == RV_BF16) {
+    if (c == 96) RV_NB(__nv_bfloat16, 3);
+    else if (c == 192) RV_NB(__nv_bfloat16, 6);
+    else RV_NB(__nv_bfloat16, 12);
+  } else {
+    RV_CHECK_ARG(false, "rmsnorm_silu_bwd: bad dtype %d", dtype);
+  }
+#undef RV_NB
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+int rv_grad_sqnorm(const float* g, int64_t n, float* out, void* stream) {
+  RV_CHECK_ARG(g && out && n > 0, "grad_sqnorm: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+  if (blocks > 2048) blocks = 2048;
+  rv::LaunchScope scope(rv::CAT_LAYOUT, st, 4.0 * n);
+  rv::sqnorm_kernel<<<(unsigned)blocks, 256, 0, st>>>(g, n, out);
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+int rv_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, float grad_scale, const float* sqnorm, float max_norm, void* stream) {
+  RV_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "adamw_step: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+  int64_t blocks = (n + 256 * 4 - 1) / (256 * 4);
+  if (blocks > 4096) blocks = 4096;
+  rv::LaunchScope scope(rv::CAT_LAYOUT, st, 28.0 * n);
+  rv::adamw_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2,
+                                                     grad_scale, sqnorm, max_norm);
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+"""Building blocks of the ``rgba_vae`` training step (reference src/training/rgba_vae_stage.py:433-523) on the GPU.
+
+What is here: backward of the AlphaVAE reconstruction loss, of the posterior sample (+KL), of RMS-norm + SiLU, the
+data gradient of the stride-1 convolutions (the forward tcgen05 kernels run on flipped/transposed weights), the
+flat-buffer AdamW with fused gradient scaling and ``clip_grad_norm_``, and the bucketed data-parallel gradient
+all-reduce (NCCL over NVLink on the GPUs; the only collective of the whole path).  What is NOT here yet: the weight
+gradient of the convolutions, attention backward and the tape that strings a full backward pass together.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Iterable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from ._lib import RV_BF16, check
+from .ops import _dt, _need_cuda, _ptr, _stream
+
+
+# ------------------------------------------------------------------------------------------
+# backward of the non-conv pieces
+# ------------------------------------------------------------------------------------------
+def recon_loss_backward(pred: torch.Tensor, target: torch.Tensor, eb: Sequence[float], eb2: Sequence[float],
+                        reduce_mean: bool = False, naive_mse: bool = False, grad_output: float = 1.0) -> torch.Tensor:
+    """d reconstruction_loss / d pred (losses.py:67-83 with the reduce rule of :117-123)."""
+    pred, target = ops._pair(pred, target)
+    n, _, h, w = pred.shape
+    ch = 4 if naive_mse else 3
+    scale = grad_output / (n * ch * h * w) if reduce_mean else grad_output / n
+    out = torch.empty_like(pred)
+    ebv = (C.c_float * 3)(*[float(v) for v in eb])
+    eb2v = (C.c_float * 3)(*[float(v) for v in eb2])
+    check(_lib.load().rv_recon_loss_bwd(_ptr(pred), _ptr(target), ebv, eb2v, int(naive_mse), scale, _ptr(out), n, h * w,
+                                        _dt(pred), _stream(pred)), "rv_recon_loss_bwd")
+    return out
+
+
+def reparam_backward(moments: torch.Tensor, noise: Optional[torch.Tensor], dz: Optional[torch.Tensor],
+                     kl_weight: float = 0.0) -> torch.Tensor:
+    """d / d moments of  <dz, posterior.sample(noise)> + kl_weight * sum_b posterior.kl()[b]."""
+    _need_cuda(moments, noise, dz)
+    moments = moments.contiguous()
+    n, c2, h, w = moments.shape
+    if (dz is None) != (noise is None):
+        raise ValueError("dz and noise must be given together")
+    if dz is not None:
+        dz, noise = dz.to(moments.dtype).contiguous(), noise.to(moments.dtype).contiguous()
+    out = torch.empty_like(moments)
+    check(_lib.load().rv_reparam_bwd(_ptr(moments), _ptr(noise), _ptr(dz), _ptr(out), n, c2 // 2, h * w, _dt(moments),
+                                     float(kl_weight), _stream(moments)), "rv_reparam_bwd")
+    return out
+
+
+def rmsnorm_silu_backward(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, silu: bool = True):
+    """Backward of ops.rmsnorm_silu: returns (dx, dgamma) with dgamma shaped like ``gamma`` (fp32)."""
+    _need_cuda(x, gamma, dy)
+    c = x.shape[-1]
+    x, dy = x.contiguous(), dy.to(x.dtype).contiguous()
+    g_scaled = (gamma.detach().to(torch.float32).reshape(-1) * math.sqrt(c)).contiguous()
+    dx = torch.empty_like(x)
+    dg = torch.zeros(c, dtype=torch.float32, device=x.device)
+    check(_lib.load().rv_rmsnorm_silu_bwd(_ptr(x), _ptr(g_scaled), _ptr(dy), _ptr(dx), _ptr(dg), x.numel() // c, c, _dt(x),
+                                          int(silu), _stream(x)), "rv_rmsnorm_silu_bwd")
+    return dx, (dg * math.sqrt(c)).reshape(gamma.shape)
+
+
+def conv_dgrad_weights(weight2d: torch.Tensor) -> torch.Tensor:
+    """[cout][cin][k][k] -> packed bf16 weights of the convolution that maps dY to dX for a stride-1 'same' conv:
+    W'[cin][cout][k-1-dy][k-1-dx] = W[cout][cin][dy][dx]."""
+    return ops.pack_conv_weights_tc(weight2d.detach().to(torch.float32).flip(2, 3).permute(1, 0, 2, 3).contiguous())
+
+
+def conv_dgrad(dy: torch.Tensor, weight2d: torch.Tensor) -> torch.Tensor:
+    """dX (NHWC bf16) of a stride-1 3x3 pad-1 (or 1x1) convolution from dY (NHWC bf16): the forward tensor-core
+    kernel on the flipped, transposed weights (no bias)."""
+    _need_cuda(dy, weight2d)
+    n, h, w, cout = dy.shape
+    cin, k = weight2d.shape[1], weight2d.shape[2]
+    wp = conv_dgrad_weights(weight2d)
+    dx = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device=dy.device)
+    desc = ops.make_desc(n, h, w, cout, cin, k, 1, False, x_dtype=RV_BF16, y_dtype=RV_BF16, bias_mode=0)
+    ops.conv2d_tc(desc, dy.contiguous(), wp, wp.shape[1], None, None, dx)
+    return dx
+
+
+# ------------------------------------------------------------------------------------------
+# optimizer + gradient all-reduce
+# ------------------------------------------------------------------------------------------
+class FlatAdamW:
+    """AdamW (torch.optim.AdamW semantics; rgba_vae_stage.py:321-331 uses betas (0.5, 0.9), lr 1e-5) over ONE flat fp32
+    master buffer.  Parameters become views of a flat buffer in the model dtype, gradients are written into the flat
+    fp32 ``grad`` buffer; ``step`` = squared-norm kernel + one fused clip/scale/update kernel."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-5, betas=(0.5, 0.9), eps: float = 1e-8,
+                 weight_decay: float = 0.01, max_grad_norm: Optional[float] = 1.0):
+        self.params: List[torch.nn.Parameter] = [p for p in params]
+        if not self.params:
+            raise ValueError("no parameters")
+        dev, dt = self.params[0].device, self.params[0].dtype
+        _need_cuda(self.params[0])
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
+        self.sizes = [p.numel() for p in self.params]
+        self.offsets = [0]
+        for s in self.sizes:
+            self.offsets.append(self.offsets[-1] + s)
+        n = self.offsets[-1]
+        self.master = torch.empty(n, dtype=torch.float32, device=dev)
+        for p, o, s in zip(self.params, self.offsets, self.sizes):
+            self.master[o:o + s].copy_(p.detach().reshape(-1))
+        self.model_flat = self.master if dt == torch.float32 else self.master.to(dt)
+        for p, o, s in zip(self.params, self.offsets, self.sizes):  # parameters now alias the flat buffer
+            p.data = self.model_flat[o:o + s].view(p.shape)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m = torch.zeros_like(self.master)
+        self.v = torch.zeros_like(self.master)
+        self.sqnorm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.t = 0
+
+    def grad_view(self, i: int) -> torch.Tensor:
+        return self.grad[self.offsets[i]:self.offsets[i + 1]].view(self.params[i].shape)
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+
+    def step(self, grad_scale: float = 1.0) -> None:
+        """``grad_scale`` = 1/world_size after a SUM all-reduce."""
+        self.t += 1
+        lib = _lib.load()
+        st = _stream(self.master)
+        sq = None
+        mx = 0.0
+        if self.max_grad_norm is not None and self.max_grad_norm > 0:
+            self.sqnorm.zero_()
+            check(lib.rv_grad_sqnorm(_ptr(self.grad), self.grad.numel(), _ptr(self.sqnorm), st), "rv_grad_sqnorm")
+            sq, mx = _ptr(self.sqnorm), float(self.max_grad_norm)
+        pb = None if self.model_flat is self.master else _ptr(self.model_flat)
+        check(lib.rv_adamw_step(_ptr(self.master), _ptr(self.grad), _ptr(self.m), _ptr(self.v), pb, self.master.numel(),
+                                self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.t, grad_scale, sq, mx,
+                                st), "rv_adamw_step")
+
+
+class GradientAllReducer:
+    """Data-parallel gradient synchronisation: the flat gradient buffer is cut into ``num_buckets`` contiguous buckets
+    in REVERSE parameter order (the decoder's gradients are produced first by backward), each bucket is all-reduced
+    (SUM) asynchronously as soon as it is marked ready, and ``wait`` joins them before the optimizer step.  On the GPUs
+    this is one NCCL all-reduce per bucket over NVLink/NVSwitch; the division by the world size is fused into AdamW."""
+
+    def __init__(self, flat_grad: torch.Tensor, num_buckets: int = 4, group=None):
+        self.grad, self.group = flat_grad, group
+        n = flat_grad.numel()
+        num_buckets = max(1, min(num_buckets, n))
+        edges = [n - (n * i) // num_buckets for i in range(num_buckets + 1)]  # n ... 0
+        self.buckets = [(edges[i + 1], edges[i]) for i in range(num_buckets)]  # last parameters first
+        self._work = []
+
+    def world(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def ready(self, bucket: int) -> None:
+        lo, hi = self.buckets[bucket]
+        if self.world() > 1:
+            self._work.append(dist.all_reduce(self.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def reduce_all(self) -> None:
+        for b in range(len(self.buckets)):
+            self.ready(b)
+
+    def wait(self) -> float:
+        """Joins outstanding all-reduces; returns the gradient scale (1/world) to hand to ``FlatAdamW.step``."""
+        for w in self._work:
+            w.wait()
+        self._work = []
+        return 1.0 / self.world()

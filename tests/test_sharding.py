@@ -57,3 +57,26 @@ def test_assignment_properties(lib_built):
         assert max(loads) / (sum(loads) / world) < 1.05
     with pytest.raises(ValueError):
         S.assign_batches(shapes, 0)
+
+
+def _allreduce_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ragb_vae_b200.training import GradientAllReducer
+
+    g = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    red = GradientAllReducer(g, num_buckets=4)
+    assert [hi - lo for lo, hi in red.buckets] == [250] * 4 and red.buckets[0] == (750, 1000)  # last parameters first
+    for b in range(4):      # buckets become ready in backward order
+        red.ready(b)
+    scale = red.wait()
+    assert scale == 1.0 / world
+    assert torch.allclose(g * scale, torch.arange(1000, dtype=torch.float32) * (sum(range(1, world + 1)) / world))
+    open(os.path.join(tmp, f"ar{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_gradient_allreduce(tmp_path, lib_built):
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_allreduce_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ar0").exists() and (tmp_path / "ar1").exists()
