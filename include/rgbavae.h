@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 8
+#define RV_ABI_VERSION 9
 #define RV_PROF_CATEGORIES 9
 
 int rv_abi_version(void);
@@ -200,6 +200,11 @@ int rv_reparam_bwd(const void* moments, const void* noise, const void* dz, void*
  * d loss / d gamma = sqrt(C) * dgamma_scaled).  gamma_scaled = gamma * sqrt(C).  c in {96, 192, 384}. */
 int rv_rmsnorm_silu_bwd(const void* x, const float* gamma_scaled, const void* dy, void* dx, float* dgamma_scaled,
                         int64_t pixels, int c, int dtype, int apply_silu, void* stream);
+/* Weight (and bias) gradient of a stride-1 'same' 3x3 or 1x1 convolution on the tensor cores: x NHWC bf16 [n][h][w][cin],
+ * dy NHWC bf16 [n][h][w][cout]; dw fp32 [cout][ksize*ksize][cin] and dbias fp32 [cout] (optional) are ACCUMULATED
+ * (the caller zeroes them).  cin % 16 == 0, cout % 8 == 0. */
+int rv_conv2d_wgrad(const void* x, const void* dy, float* dw, float* dbias, int n, int h, int w, int cin, int cout,
+                    int ksize, void* stream);
 /* *out += sum(g^2) over a flat fp32 gradient buffer (accelerator.clip_grad_norm_, rgba_vae_stage.py:520-521). */
 int rv_grad_sqnorm(const float* g, int64_t n, float* out, void* stream);
 /* torch.optim.AdamW step (rgba_vae_stage.py:321-331, 522) over flat fp32 buffers, fused with the gradient scaling

@@ -1,0 +1,247 @@
+// Weight gradient of the 3x3 (stride 1, pad 1) and 1x1 convolutions on the tensor cores (sm_100a):
+//   dW[co][tap][ci] = sum over (n, y, x) of dY[n][y][x][co] * X[n][y+dy-pad][x+dx-pad][ci]
+// i.e. per tap a GEMM D[co x ci] = A[co x P] * B[P x ci] whose reduction dimension is the PIXEL index.  In NHWC both
+// operands have the reduction index as their slow dimension, so they are "MN-major" UMMA operands: a TMA box of
+// (64 channels x KP pixels) lands in shared memory as KP rows of 128 swizzled bytes, which is exactly the canonical
+// MN-major SWIZZLE_128B layout (64-element MN blocks LBO apart, 8-row K groups 1024 B apart).  The tap shift of X is a
+// TMA coordinate offset; image borders are out-of-bounds zero fill.
+//
+// One CTA = (tap, 128-row Cout tile, Cin tile, pixel split): it streams its image rows through a TMA ring, accumulates
+// in TMEM (fp32) and adds the tile to dW with fp32 atomics (split-K over pixels).  Warps: 0 TMA, 1 MMA, 2-5 epilogue.
+#include <cstring>
+#include <mutex>
+
+#include "rv_tc_common.cuh"
+
+namespace rv {
+
+constexpr int WG_THREADS = 192;
+constexpr int WG_KP = 64;            // pixels per K block (4 MMAs of K = 16)
+constexpr int WG_MAX_STAGES = 8;
+constexpr uint32_t WG_BOX_BYTES = WG_KP * 128;  // one (64 channels x KP pixels) box
+
+struct WgParams {
+  int n_img, h, w;
+  int cin, cout, ksize, pad;
+  int co_tiles, ci_tiles, bn, nboxes_b;  // bn: Cin columns per tile (multiple of 16, <= 256)
+  int splits, rows_per_split, x_blocks;
+  float* dw;      // [cout][taps*cin] fp32, accumulated
+  int dw_ld;
+  int stages;
+  uint32_t stage_bytes, tx_bytes;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                  const __grid_constant__ WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[WG_MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[WG_MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_done;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // unit decode
+  int u = blockIdx.x;
+  const int split = u % p.splits;
+  u /= p.splits;
+  const int ci_t = u % p.ci_tiles;
+  u /= p.ci_tiles;
+  const int co_t = u % p.co_tiles;
+  const int tap = u / p.co_tiles;
+  const int dy = tap / p.ksize - p.pad, dx = tap % p.ksize - p.pad;
+  const int co0 = co_t * 128, ci0 = ci_t * p.bn;
+  const int total_rows = p.n_img * p.h;
+  const int row_lo = split * p.rows_per_split;
+  const int row_hi = min(total_rows, row_lo + p.rows_per_split);
+  const int num_kb = max(0, row_hi - row_lo) * p.x_blocks;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bar_done), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]), done = smem_u32(&bar_done);
+  const uint32_t a_bytes = 2u * WG_BOX_BYTES;
+
+  if (warp == 0) {
+    uint32_t stage = 0, phase = 0;
+    for (int row = row_lo; row < row_hi; ++row) {
+      const int n = row / p.h, y = row - n * p.h;
+      for (int xb = 0; xb < p.x_blocks; ++xb) {
+        mbar_wait(empty0 + 8u * stage, phase ^ 1u);
+        if (elect_one()) {
+          const uint32_t full = full0 + 8u * stage;
+          const uint32_t dst = smem_base + stage * p.stage_bytes;
+          mbar_arrive_expect_tx(full, p.tx_bytes);
+          tma_load_4d(dst, &map_dy, full, co0, xb * WG_KP, y, n);
+          tma_load_4d(dst + WG_BOX_BYTES, &map_dy, full, co0 + 64, xb * WG_KP, y, n);
+          for (int b = 0; b < p.nboxes_b; ++b)
+            tma_load_4d(dst + a_bytes + b * WG_BOX_BYTES, &map_x, full, ci0 + 64 * b, xb * WG_KP + dx, y + dy, n);
+        }
+        __syncwarp();
+        if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // D fp32, A/B bf16, both MN-major (bits 15, 16), N = bn, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.bn >> 3) << 17) |
+                           ((128u >> 4) << 24);
+    // MN-major SW128 descriptor: LBO = distance between 64-element MN blocks (one box), SBO = 8 K-rows = 1024 B
+    uint64_t hi = 0;
+    hi |= (uint64_t)(WG_BOX_BYTES >> 4) << 16;
+    hi |= (uint64_t)(1024u >> 4) << 32;
+    hi |= (uint64_t)1 << 46;
+    hi |= (uint64_t)2 << 61;
+    uint32_t stage = 0, phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(full0 + 8u * stage, phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_lo = ((smem_base + stage * p.stage_bytes) & 0x3FFFFu) >> 4;
+        const uint32_t b_lo = a_lo + (a_bytes >> 4);
+#pragma unroll
+        for (int ks = 0; ks < WG_KP / 16; ++ks) {
+          // 16 pixels = two 8-row groups = 2048 bytes further down the box
+          umma_bf16(tmem_base, hi | (uint64_t)(a_lo + ks * 128u), hi | (uint64_t)(b_lo + ks * 128u), idesc, (kb | ks) ? 1u : 0u);
+        }
+        umma_commit(empty0 + 8u * stage);
+        if (kb == num_kb - 1) umma_commit(done);
+      }
+      __syncwarp();
+      if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (num_kb > 0) {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* out = p.dw + (int64_t)co * p.dw_ld + tap * p.cin + ci0;
+    for (int c0 = 0; c0 < p.bn; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(taddr + (uint32_t)c0, r);
+      tmem_ld_wait();
+      if (co < p.cout) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (ci0 + c0 + j < p.cin) atomicAdd(out + c0 + j, __uint_as_float(r[j]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+// per-channel sum over pixels (bias gradient): x [pixels][c] bf16 -> out[c] += sum
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int64_t pixels, int c) {
+  // thread t owns channel (t % c) of pixel rows t / c, t / c + rows_per_iter, ...
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t total_threads = (int64_t)gridDim.x * blockDim.x;
+  const int64_t lanes = total_threads / c * c;  // threads beyond the last full pixel row idle
+  if (t >= lanes) return;
+  const int ch = (int)(t % c);
+  float acc = 0.f;
+  for (int64_t r = t / c; r < pixels; r += lanes / c) acc += __bfloat162float(x[r * c + ch]);
+  atomicAdd(out + ch, acc);
+}
+
+int tc_encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                  const cuuint32_t* box, CUtensorMapSwizzle sw);
+int tc_ensure_init();
+static std::mutex g_wg_mu;
+static bool g_wg_attr[64] = {false};
+
+}  // namespace rv
+
+extern "C" int rv_conv2d_wgrad(const void* x, const void* dy, float* dw, float* dbias, int n, int h, int w, int cin, int cout,
+                               int ksize, void* stream) {
+  using namespace rv;
+  if (int rc = tc_ensure_init()) return rc;
+  RV_CHECK_ARG(x && dy && dw && n > 0 && h > 0 && w > 0, "conv2d_wgrad: bad argument");
+  RV_CHECK_ARG(ksize == 1 || ksize == 3, "conv2d_wgrad: ksize must be 1 or 3");
+  RV_CHECK_ARG(cin % 16 == 0 && cout % 8 == 0, "conv2d_wgrad: cin %% 16 and cout %% 8 must be 0 (got %d, %d)", cin, cout);
+  RV_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0), "conv2d_wgrad: tensors must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_img = n; p.h = h; p.w = w; p.cin = cin; p.cout = cout; p.ksize = ksize; p.pad = ksize / 2;
+  p.co_tiles = (cout + 127) / 128;
+  const int c16 = (cin + 15) / 16 * 16;
+  p.ci_tiles = (c16 + 255) / 256;
+  p.bn = ((c16 + p.ci_tiles - 1) / p.ci_tiles + 15) / 16 * 16;
+  p.nboxes_b = (p.bn + 63) / 64;
+  p.x_blocks = (w + WG_KP - 1) / WG_KP;
+  const int taps = ksize * ksize;
+  const int tiles = taps * p.co_tiles * p.ci_tiles;
+  const int total_rows = n * h;
+  int splits = (num_sms() * 2 + tiles - 1) / tiles;
+  if (splits > total_rows) splits = total_rows;
+  if (splits < 1) splits = 1;
+  p.rows_per_split = (total_rows + splits - 1) / splits;
+  p.splits = (total_rows + p.rows_per_split - 1) / p.rows_per_split;
+  p.dw = dw;
+  p.dw_ld = taps * cin;
+  p.tx_bytes = (2u + (uint32_t)p.nboxes_b) * WG_BOX_BYTES;
+  p.stage_bytes = p.tx_bytes;
+  p.stages = (int)((200u * 1024u) / p.stage_bytes);
+  if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
+  CUtensorMap mdy, mx;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)cout, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t str[3] = {(cuuint64_t)cout * 2u, (cuuint64_t)cout * 2u * w, (cuuint64_t)cout * 2u * w * h};
+    cuuint32_t box[4] = {64, (cuuint32_t)WG_KP, 1, 1};
+    if (int rc = tc_encode_map(&mdy, dy, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t str[3] = {(cuuint64_t)cin * 2u, (cuuint64_t)cin * 2u * w, (cuuint64_t)cin * 2u * w * h};
+    cuuint32_t box[4] = {64, (cuuint32_t)WG_KP, 1, 1};
+    if (int rc = tc_encode_map(&mx, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  }
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  {
+    std::lock_guard<std::mutex> lk(g_wg_mu);
+    int dev = 0;
+    RV_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !g_wg_attr[dev]) {
+      RV_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      g_wg_attr[dev] = true;
+    }
+  }
+  {
+    LaunchScope scope(CAT_CONV_TC, st, 2.0 * (double)n * h * w * cout * cin * taps);
+    conv_wgrad_kernel<<<tiles * p.splits, WG_THREADS, smem, st>>>(mdy, mx, p);
+    RV_LAUNCH_CHECK();
+  }
+  if (dbias) {
+    const int64_t pixels = (int64_t)n * h * w;
+    LaunchScope scope(CAT_NORM, st, (double)pixels * cout * 2.0);
+    int64_t blocks = (pixels * cout + 256 * 64 - 1) / (256 * 64);
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    if (blocks < 1) blocks = 1;
+    while (blocks * 256 < cout) ++blocks;
+    colsum_kernel<<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, dbias, pixels, cout);
+    RV_LAUNCH_CHECK();
+  }
+  return 0;
+}

@@ -86,6 +86,19 @@ def conv_dgrad(dy: torch.Tensor, weight2d: torch.Tensor) -> torch.Tensor:
     return dx
 
 
+def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, want_bias: bool = True):
+    """(dW [cout][cin][k][k], dbias [cout]) in fp32 of a stride-1 'same' convolution from x and dY (NHWC bf16)."""
+    _need_cuda(x, dy)
+    n, h, w, cin = x.shape
+    cout = dy.shape[-1]
+    taps = ksize * ksize
+    dw = torch.zeros((cout, taps * cin), dtype=torch.float32, device=x.device)
+    db = torch.zeros(cout, dtype=torch.float32, device=x.device) if want_bias else None
+    check(_lib.load().rv_conv2d_wgrad(_ptr(x.contiguous()), _ptr(dy.contiguous()), _ptr(dw), _ptr(db), n, h, w, cin, cout, ksize,
+                                      _stream(x)), "rv_conv2d_wgrad")
+    return dw.view(cout, ksize, ksize, cin).permute(0, 3, 1, 2).contiguous(), db
+
+
 # ------------------------------------------------------------------------------------------
 # optimizer + gradient all-reduce
 # ------------------------------------------------------------------------------------------

@@ -108,3 +108,18 @@ def test_flat_adamw_matches_torch(T):
     ob.step()
     assert pb[0].dtype == torch.bfloat16 and not torch.equal(pb[0], before)
     assert torch.equal(pb[0].detach().reshape(-1), ob.master.bfloat16())
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k", [(1, 8, 64, 64, 64, 3), (2, 12, 136, 96, 96, 3), (1, 16, 70, 192, 96, 3),
+                                              (2, 9, 64, 96, 192, 1), (1, 8, 128, 384, 384, 3)])
+def test_conv_wgrad_matches_autograd(T, n, h, w, cin, cout, k):
+    g = torch.Generator().manual_seed(n + h + w + cin + cout)
+    x = torch.randn(n, cin, h, w, generator=g).bfloat16().float()
+    wt = torch.zeros(cout, cin, k, k, requires_grad=True)
+    bias = torch.zeros(cout, requires_grad=True)
+    dy = torch.randn(n, cout, h, w, generator=g).bfloat16().float()
+    F.conv2d(x, wt, bias, padding=k // 2).backward(dy)
+    dw, db = T.conv_wgrad(x.permute(0, 2, 3, 1).contiguous().cuda().bfloat16(), dy.permute(0, 2, 3, 1).contiguous().cuda().bfloat16(), k)
+    assert dw.shape == wt.shape
+    assert rel(dw, wt.grad) < 2e-3
+    assert rel(db, bias.grad) < 1e-4
