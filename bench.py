@@ -42,8 +42,11 @@ def parse():
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
-                    help="c2: fixed 1024^2 batches (the headline); c3: mixed-aspect bucket-pure batches sharded across ranks")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
+                    help="c2: fixed 1024^2 batches (the headline); c3: mixed-aspect bucket-pure batches sharded across ranks; "
+                         "c4: the rgba_vae training step (fwd + bwd + gradient all-reduce + AdamW), data parallel")
+    ap.add_argument("--train-size", type=int, default=512, help="c4: image side")
+    ap.add_argument("--train-batch", type=int, default=4, help="c4: per-GPU batch (configs/flux_vae.yaml: 4)")
     ap.add_argument("--batches", type=int, default=64, help="c3: bucket-pure batches in the whole job")
     return ap.parse_args()
 
@@ -384,10 +387,84 @@ def c3_arm(a):
         dist.destroy_process_group()
 
 
+def c4_arm(a):
+    """Config c4: the rgba_vae training step (src/training/rgba_vae_stage.py:433-523 without LPIPS): triplet, encode,
+    sample, decode, AlphaVAE loss (loss_reduce_mean like configs/flux_vae.yaml) + 1e-6 KL, hand-written backward,
+    bucketed NCCL gradient all-reduce, clip_grad_norm_(1.0) and AdamW(1e-5, betas (0.5, 0.9)).  Weak scaling: every
+    rank trains on its own batch.  value = trained pixels per second over all ranks (inputs resident in HBM)."""
+    import torch
+    import torch.distributed as dist
+
+    import ragb_vae_b200 as R
+    from ragb_vae_b200 import ops, sharding
+    from ragb_vae_b200.trainer import VaeTrainStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    vae = R.RgbaAutoencoder("qwen").to(dev, torch.bfloat16)
+    step = VaeTrainStep(vae, lr=1e-5, kl_scale=1e-6, loss_module=R.AlphaVaeLoss(reduce_mean=True))
+    B, S = a.train_batch, a.train_size
+    g = torch.Generator().manual_seed(100 + rank)
+    x_host = torch.rand(B, 4, S, S, generator=g).pin_memory()
+    n_host = torch.randn(B, 16, S // 8, S // 8, generator=g).pin_memory()
+    x, noise = x_host.to(dev), n_host.to(dev)
+    warm = max(a.warmup, 3)
+    for _ in range(warm):
+        m = step.step(x, noise)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = ops.launch_count()
+    ops.prof_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        m = step.step(x, noise)
+    e1.record()
+    torch.cuda.synchronize()
+    prof = ops.prof_end()
+    launches = ops.launch_count() - l0
+    ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+    # end to end: host batch in, loss out
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        m = step.step(x_host.to(dev, non_blocking=True), n_host.to(dev, non_blocking=True))
+        loss_host = float(m["train/loss"])
+    torch.cuda.synchronize()
+    ms_e2e = sharding.max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
+    if rank == 0:
+        mpix = world * B * S * S / 1e6
+        kernels = {k: {"ms": round(v["ms"], 3), "launches": v["launches"]} for k, v in prof.items() if v["launches"]}
+        line = {"metric": "rgba_vae_train_step_mpix_per_s", "value": mpix * a.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+                "steps": a.steps, "warmup": warm, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"c4: rgba_vae training step, batch {B} x {S}x{S} per GPU, recon (reduce_mean) + 1e-6 KL, "
+                                       "no LPIPS, bucketed NCCL gradient all-reduce, clip 1.0, AdamW",
+                           "arch": "qwen", "parallelism": f"data parallel x{world}"},
+                "e2e": {"value": mpix * a.steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
+                        "h2d_bytes_per_step": (x_host.numel() + n_host.numel()) * 4 * world, "d2h_bytes_per_step": 4 * world},
+                "gpu_launches": int(launches), "kernels": kernels, "loss": loss_host}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     a = parse()
     if a.impl == "ours" and a.workload == "c3":
         c3_arm(a)
+        return
+    if a.impl == "ours" and a.workload == "c4":
+        c4_arm(a)
         return
     if a.impl == "reference":
         reference_arm(a)

@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 9
+#define RV_ABI_VERSION 10
 #define RV_PROF_CATEGORIES 9
 
 int rv_abi_version(void);
@@ -189,9 +189,11 @@ int rv_reduce_blocks(int64_t hw);
 
 /* ---- training-step building blocks (src/training/rgba_vae_stage.py:433-523) ------------------ */
 /* d loss / d pred of AlphaVaeLoss.reconstruction_loss (losses.py:67-83); grad_scale = upstream gradient times the
- * reduction factor (1/(B*3*HW) for reduce_mean -- 1/(B*4*HW) for the naive MSE -- else 1/B).  NCHW [n][4][hw]. */
+ * reduction factor (1/(B*3*HW) for reduce_mean -- 1/(B*4*HW) for the naive MSE -- else 1/B).  NCHW [n][4][hw].
+ * clamp_lo < clamp_hi: pred is the decoder's clamped output, the gradient is zero where it sits on either bound. */
 int rv_recon_loss_bwd(const void* pred, const void* target, const float* eb_host, const float* eb2_host,
-                      int naive_mse, float grad_scale, void* dpred, int n, int64_t hw, int dtype, void* stream);
+                      int naive_mse, float grad_scale, float clamp_lo, float clamp_hi, void* dpred, int n, int64_t hw,
+                      int dtype, void* stream);
 /* Backward of posterior.sample() (+ kl_weight * posterior.kl()): dmoments NCHW [n][2*zc][hw] from dz [n][zc][hw]
  * (dz / noise may both be NULL for the KL term alone); the logvar gradient is zero outside the clamp range. */
 int rv_reparam_bwd(const void* moments, const void* noise, const void* dz, void* dmoments, int n, int zc,
@@ -202,9 +204,19 @@ int rv_rmsnorm_silu_bwd(const void* x, const float* gamma_scaled, const void* dy
                         int64_t pixels, int c, int dtype, int apply_silu, void* stream);
 /* Weight (and bias) gradient of a stride-1 'same' 3x3 or 1x1 convolution on the tensor cores: x NHWC bf16 [n][h][w][cin],
  * dy NHWC bf16 [n][h][w][cout]; dw fp32 [cout][ksize*ksize][cin] and dbias fp32 [cout] (optional) are ACCUMULATED
- * (the caller zeroes them).  cin % 16 == 0, cout % 8 == 0. */
+ * (the caller zeroes them).  cin % 16 == 0, cout % 8 == 0.  pad = ksize/2 for a 'same' conv; pad = 0 with a
+ * zero-inserted dy gives the weight gradient of the stride-2 (0,1,0,1)-padded down-sampling conv. */
 int rv_conv2d_wgrad(const void* x, const void* dy, float* dw, float* dbias, int n, int h, int w, int cin, int cout,
-                    int ksize, void* stream);
+                    int ksize, int pad, void* stream);
+/* Spatial helpers of the backward pass, NHWC bf16, c % 8 == 0.  mode 0: zero-insert x2 (dY of a stride-2 conv onto
+ * the input grid); mode 1: nearest x2 upsample; mode 2: 2x2 sum pool (backward of the nearest upsample). */
+int rv_resample2x(const void* x, void* y, int n, int h, int w, int c, int mode, void* stream);
+/* y = a + b over n bf16 elements (n % 8 == 0): gradient accumulation where two branches meet. */
+int rv_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream);
+/* Softmax backward for a block of `rows` query rows: dS = P * (dP - rowsum(dP*P)) * scale as bf16 [rows][cols] and as
+ * its transpose written into ds_t [cols][ld_t] at column offset row0.  p bf16 [rows][cols], dp fp32 [rows][cols]. */
+int rv_softmax_bwd(const void* p, const float* dp, void* ds, void* ds_t, int64_t rows, int64_t cols, int64_t ld_t,
+                   int64_t row0, float scale, void* stream);
 /* *out += sum(g^2) over a flat fp32 gradient buffer (accelerator.clip_grad_norm_, rgba_vae_stage.py:520-521). */
 int rv_grad_sqnorm(const float* g, int64_t n, float* out, void* stream);
 /* torch.optim.AdamW step (rgba_vae_stage.py:321-331, 522) over flat fp32 buffers, fused with the gradient scaling

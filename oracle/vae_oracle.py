@@ -543,6 +543,34 @@ def kl_loss(posterior, reference=None, reduce_mean=False):  # losses.py:109-115
     return reduce_loss(posterior.kl(reference), reduce_mean)
 
 
+def training_step(vae: OracleVAE, inputs: torch.Tensor, noise: torch.Tensor, kl_scale: Optional[float] = 1e-6,
+                  reduce_mean: bool = False, use_naive_mse: bool = False):
+    """One ``rgba_vae`` step up to ``accelerator.backward`` (src/training/rgba_vae_stage.py:433-518) with
+    ``lpips_scale = 0`` and no reference VAE: returns (metrics, {parameter name: gradient}).  ``inputs`` in [0,1];
+    ``noise`` is the posterior sample's eps for the first third of the triplet batch (reproducible ``sample()``)."""
+    vae.requires_grad_(True)
+    vae.zero_grad(set_to_none=True)
+    target = torch.clamp(inputs, 0.0, 1.0)
+    target_vae = target * 2.0 - 1.0
+    composed = build_detail_augmented_triplet(target_vae)
+    posterior_all = vae.encode(composed).latent_dist
+    posterior, _, _ = split_triplet_distribution(posterior_all)
+    z = posterior.sample(noise=noise)
+    pred = vae.decode(z).sample
+    recon = reconstruction_loss(pred, target_vae, reduce_mean, use_naive_mse)
+    metrics = {"train/recon": recon.detach()}
+    total = recon
+    if kl_scale is not None and kl_scale > 0.0:
+        kl = kl_loss(posterior, None, reduce_mean)
+        metrics["train/kl"] = kl.detach()
+        total = total + kl_scale * kl
+    metrics["train/loss"] = total.detach()
+    total.backward()
+    grads = {n: p.grad.detach().clone() for n, p in vae.named_parameters() if p.grad is not None}
+    vae.requires_grad_(False)
+    return metrics, grads
+
+
 def compute_psnr(pred, target):  # src/training/rgba_vae_stage.py:712-715
     mse = torch.clamp(torch.mean((pred - target) ** 2, dim=(1, 2, 3)), min=1e-8)
     return -10.0 * torch.log10(mse)

@@ -155,7 +155,9 @@ int check_conv_desc(const rv_conv_desc* d) {
   RV_CHECK_ARG(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2 (got %d)", d->stride);
   RV_CHECK_ARG(!(d->upsample && d->stride != 1), "conv: upsample requires stride 1");
   int heff = d->upsample ? 2 * d->h : d->h, weff = d->upsample ? 2 * d->w : d->w;
-  int pad_hi = (d->ksize == 3 && d->stride == 1) ? 1 : (d->ksize == 3 ? 1 - d->pad_lo : 0);
+  // 3x3 stride 1 is always 'same' (pad_lo + pad_hi = 2; pad_lo = 2 is the data gradient of the stride-2 conv)
+  RV_CHECK_ARG(d->pad_lo >= 0 && d->pad_lo <= (d->ksize == 3 ? 2 : 0), "conv: bad pad_lo %d", d->pad_lo);
+  int pad_hi = (d->ksize == 3 && d->stride == 1) ? 2 - d->pad_lo : (d->ksize == 3 ? 1 - d->pad_lo : 0);
   int oh = (heff + d->pad_lo + pad_hi - d->ksize) / d->stride + 1;
   int ow = (weff + d->pad_lo + pad_hi - d->ksize) / d->stride + 1;
   RV_CHECK_ARG(oh == d->oh && ow == d->ow, "conv: output size %dx%d inconsistent with input (expected %dx%d)",

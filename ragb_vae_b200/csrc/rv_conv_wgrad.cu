@@ -174,7 +174,7 @@ static bool g_wg_attr[64] = {false};
 }  // namespace rv
 
 extern "C" int rv_conv2d_wgrad(const void* x, const void* dy, float* dw, float* dbias, int n, int h, int w, int cin, int cout,
-                               int ksize, void* stream) {
+                               int ksize, int pad, void* stream) {
   using namespace rv;
   if (int rc = tc_ensure_init()) return rc;
   RV_CHECK_ARG(x && dy && dw && n > 0 && h > 0 && w > 0, "conv2d_wgrad: bad argument");
@@ -184,7 +184,7 @@ extern "C" int rv_conv2d_wgrad(const void* x, const void* dy, float* dw, float* 
   cudaStream_t st = (cudaStream_t)stream;
   WgParams p;
   memset(&p, 0, sizeof(p));
-  p.n_img = n; p.h = h; p.w = w; p.cin = cin; p.cout = cout; p.ksize = ksize; p.pad = ksize / 2;
+  p.n_img = n; p.h = h; p.w = w; p.cin = cin; p.cout = cout; p.ksize = ksize; p.pad = pad;
   p.co_tiles = (cout + 127) / 128;
   const int c16 = (cin + 15) / 16 * 16;
   p.ci_tiles = (c16 + 255) / 256;

@@ -10,6 +10,7 @@ struct LossBwdParams {
   float eb[3], eb2[3];
   int naive;
   float scale;  // upstream gradient x reduction factor (1/(B*3*HW) for reduce_mean, 1/B otherwise)
+  float clamp_lo, clamp_hi;  // zero gradient where pred sits on the clamp (lo >= hi: no clamp)
 };
 
 // d loss / d pred for AlphaVaeLoss.reconstruction_loss (src/models/losses.py:67-83):
@@ -28,9 +29,12 @@ __global__ void __launch_bounds__(256) recon_loss_bwd_kernel(const T* __restrict
       pv[c] = ldf(p + c * hw + i);
       tv[c] = ldf(t + c * hw + i);
     }
+    float m[4];  // gradient mask of the decoder's output clamp (AutoencoderKLQwenImage._decode clamps to [-1,1])
+#pragma unroll
+    for (int c = 0; c < 4; ++c) m[c] = (lp.clamp_lo < lp.clamp_hi && (pv[c] <= lp.clamp_lo || pv[c] >= lp.clamp_hi)) ? 0.f : lp.scale;
     if (lp.naive) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) stf(g + c * hw + i, 2.0f * (pv[c] - tv[c]) * lp.scale);
+      for (int c = 0; c < 4; ++c) stf(g + c * hw + i, 2.0f * (pv[c] - tv[c]) * m[c]);
     } else {
       const float at = (tv[3] + 1.0f) * 0.5f, ap = (pv[3] + 1.0f) * 0.5f;
       const float da = at - ap;
@@ -38,10 +42,10 @@ __global__ void __launch_bounds__(256) recon_loss_bwd_kernel(const T* __restrict
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float d = tv[c] * at - pv[c] * ap;
-        stf(g + c * hw + i, (2.0f * d - 2.0f * lp.eb[c] * da) * (-ap) * lp.scale);
+        stf(g + c * hw + i, (2.0f * d - 2.0f * lp.eb[c] * da) * (-ap) * m[c]);
         dalpha += -2.0f * d * pv[c] + 2.0f * lp.eb[c] * (pv[c] * da + d) - 2.0f * lp.eb2[c] * da;
       }
-      stf(g + 3 * hw + i, 0.5f * dalpha * lp.scale);
+      stf(g + 3 * hw + i, 0.5f * dalpha * m[3]);
     }
   }
 }
@@ -161,6 +165,83 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   }
 }
 
+
+// ---- spatial helpers of the backward pass (NHWC bf16, 16-byte vectors along channels) --------------------------------
+// mode 0: zero-insert x2   y[n][2h][2w][c]: y[2i][2j] = x[i][j], 0 elsewhere      (dY of a stride-2 conv -> full grid)
+// mode 1: nearest x2       y[n][2h][2w][c]: y[i][j] = x[i/2][j/2]                  (forward input of the upsample conv)
+// mode 2: 2x2 sum pool     y[n][h/2][w/2][c] = sum of the 2x2 block of x           (dX of the nearest upsample)
+__global__ void __launch_bounds__(256) resample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h,
+                                                        int w, int c, int mode) {
+  using V = Vec16<__nv_bfloat16>;
+  const int cv = c / 8;
+  const int oh = mode == 2 ? h / 2 : 2 * h, ow = mode == 2 ? w / 2 : 2 * w;
+  const int64_t total = (int64_t)n * oh * ow * cv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % cv);
+    int64_t r = i / cv;
+    const int ox = (int)(r % ow);
+    r /= ow;
+    const int oy = (int)(r % oh);
+    const int img = (int)(r / oh);
+    V o;
+    if (mode == 0) {
+      if ((oy & 1) || (ox & 1)) o.zero();
+      else o.load(x + (((int64_t)img * h + (oy >> 1)) * w + (ox >> 1)) * c + k * 8);
+    } else if (mode == 1) {
+      o.load(x + (((int64_t)img * h + (oy >> 1)) * w + (ox >> 1)) * c + k * 8);
+    } else {
+      V a, b, d, e;
+      const __nv_bfloat16* base = x + (((int64_t)img * h + 2 * oy) * w + 2 * ox) * c + k * 8;
+      a.load(base);
+      b.load(base + c);
+      d.load(base + (int64_t)w * c);
+      e.load(base + (int64_t)w * c + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.set(j, a.get(j) + b.get(j) + d.get(j) + e.get(j));
+    }
+    o.store(y + i * 8);
+  }
+}
+
+// y = a + b (bf16, flat): gradient accumulation where two branches meet
+__global__ void __launch_bounds__(256) add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                                 __nv_bfloat16* __restrict__ y, int64_t nvec) {
+  using V = Vec16<__nv_bfloat16>;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    V p, q, o;
+    p.load(a + i * 8);
+    q.load(b + i * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.set(j, p.get(j) + q.get(j));
+    o.store(y + i * 8);
+  }
+}
+
+// softmax backward on one block of rows: dS = P * (dP - sum_k(dP*P)) * scale, written as dS [rows][cols] and as its
+// transpose dSt [cols][ldt] (column offset = first row of the block) for the GEMMs that need keys as the slow index.
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p, const float* __restrict__ dp,
+                                                         __nv_bfloat16* __restrict__ ds, __nv_bfloat16* __restrict__ dst, int64_t cols,
+                                                         int64_t ldt, int64_t row0, float scale) {
+  __shared__ float red[8];
+  const int64_t row = blockIdx.x;
+  const __nv_bfloat16* pr = p + row * cols;
+  const float* dr = dp + row * cols;
+  float acc = 0.f;
+  for (int64_t i = threadIdx.x; i < cols; i += 256) acc = fmaf(__bfloat162float(pr[i]), dr[i], acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  for (int64_t i = threadIdx.x; i < cols; i += 256) {
+    const float v = __bfloat162float(pr[i]) * (dr[i] - tot) * scale;
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    ds[row * cols + i] = b;
+    dst[i * ldt + row0 + row] = b;
+  }
+}
+
 static inline dim3 train_grid(int64_t items, int n) {
   unsigned bx = (unsigned)((items + 255) / 256);
   if (bx > 2048) bx = 2048;
@@ -173,7 +254,7 @@ static inline dim3 train_grid(int64_t items, int n) {
 extern "C" {
 
 int rv_recon_loss_bwd(const void* pred, const void* target, const float* eb_host, const float* eb2_host, int naive_mse,
-                      float grad_scale, void* dpred, int n, int64_t hw, int dtype, void* stream) {
+                      float grad_scale, float clamp_lo, float clamp_hi, void* dpred, int n, int64_t hw, int dtype, void* stream) {
   RV_CHECK_ARG(pred && target && dpred && n > 0 && hw > 0, "recon_loss_bwd: bad argument");
   RV_CHECK_ARG(naive_mse || (eb_host && eb2_host), "recon_loss_bwd: Eb / Eb2 missing");
   rv::LossBwdParams lp;
@@ -183,6 +264,8 @@ int rv_recon_loss_bwd(const void* pred, const void* target, const float* eb_host
   }
   lp.naive = naive_mse;
   lp.scale = grad_scale;
+  lp.clamp_lo = clamp_lo;
+  lp.clamp_hi = clamp_hi;
   cudaStream_t st = (cudaStream_t)stream;
   rv::LaunchScope scope(rv::CAT_LOSS, st, 12.0 * n * hw * (dtype == RV_F32 ? 4 : 2));
   if (dtype == RV_F32)
@@ -238,6 +321,42 @@ int rv_rmsnorm_silu_bwd(const void* x, const float* gamma_scaled, const void* dy
     RV_CHECK_ARG(false, "rmsnorm_silu_bwd: bad dtype %d", dtype);
   }
 #undef RV_NB
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+int rv_resample2x(const void* x, void* y, int n, int h, int w, int c, int mode, void* stream) {
+  RV_CHECK_ARG(x && y && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "resample2x: bad argument (c %% 8)");
+  RV_CHECK_ARG(mode >= 0 && mode <= 2 && (mode != 2 || (h % 2 == 0 && w % 2 == 0)), "resample2x: bad mode / odd size");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t out_el = mode == 2 ? (int64_t)n * (h / 2) * (w / 2) * c : (int64_t)n * 4 * h * w * c;
+  int64_t blocks = (out_el / 8 + 255) / 256;
+  if (blocks > rv::num_sms() * 32) blocks = rv::num_sms() * 32;
+  if (blocks < 1) blocks = 1;
+  rv::LaunchScope scope(rv::CAT_LAYOUT, st, 2.0 * ((double)n * h * w * c + out_el));
+  rv::resample2x_kernel<<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, mode);
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+int rv_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream) {
+  RV_CHECK_ARG(a && b && y && n > 0 && n % 8 == 0, "add_bf16: element count must be a positive multiple of 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t blocks = (n / 8 + 255) / 256;
+  if (blocks > rv::num_sms() * 32) blocks = rv::num_sms() * 32;
+  rv::LaunchScope scope(rv::CAT_LAYOUT, st, 6.0 * n);
+  rv::add_kernel<<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, n / 8);
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+int rv_softmax_bwd(const void* p, const float* dp, void* ds, void* ds_t, int64_t rows, int64_t cols, int64_t ld_t, int64_t row0,
+                   float scale, void* stream) {
+  RV_CHECK_ARG(p && dp && ds && ds_t && rows > 0 && cols > 0 && ld_t >= row0 + rows, "softmax_bwd: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  rv::LaunchScope scope(rv::CAT_SOFTMAX, st, (double)rows * cols * 10.0);
+  rv::softmax_bwd_kernel<<<(unsigned)rows, 256, 0, st>>>((const __nv_bfloat16*)p, dp, (__nv_bfloat16*)ds, (__nv_bfloat16*)ds_t, cols, ld_t,
+                                                         row0, scale);
   RV_LAUNCH_CHECK();
   return 0;
 }

@@ -1,0 +1,412 @@
+"""The ``rgba_vae`` training step (reference src/training/rgba_vae_stage.py:433-523) on the GPU, Qwen-Image arch, bf16.
+
+    inputs -> clamp -> [-1,1] -> detail-augmented triplet -> encode -> posterior.sample -> decode
+           -> AlphaVAE reconstruction loss + kl_scale * KL -> backward -> clip_grad_norm_ -> AdamW
+
+There is no autograd graph: the forward pass keeps the activations the hand-written backward needs (a "tape" of plain
+tensors per block) and ``backward`` walks the model in reverse, calling librgbavae for every piece:
+
+  * convolutions   data gradient = the forward tcgen05 kernel on flipped / transposed weights; weight gradient =
+                   ``rv_conv2d_wgrad`` (MN-major UMMA operands, split-K over pixels, fp32 accumulation).
+                   stride-2 down-sampler: dY is zero-inserted onto the input grid (``rv_resample2x``) and both gradients
+                   become stride-1 problems; nearest-x2 + conv up-sampler: gradients of the 3x3 conv on the up-sampled
+                   grid followed by a 2x2 sum pool.
+  * RMS norm+SiLU  ``rv_rmsnorm_silu_bwd``
+  * attention      scores are recomputed per block of query rows; dV, dK, dQ are "weight-gradient" GEMMs (the reduction
+                   runs over tokens, which is the pixel axis of the wgrad kernel), dP a plain GEMM, and
+                   ``rv_softmax_bwd`` writes dS and its transpose.
+  * loss / sample  ``rv_recon_loss_bwd`` (with the decoder's [-1,1] clamp mask), ``rv_reparam_bwd`` (+ KL term)
+  * optimizer      ``FlatAdamW`` (fused clip + AdamW over one flat buffer); data parallel: bucketed NCCL all-reduce.
+
+What the reference's step also has and this one does not: LPIPS (third-party VGG, out of scope) and the
+reference-KL term against a frozen copy (``ref_kl_scale`` = 1e-16 in configs/flux_vae.yaml, numerically nil); the
+black / white composites of the triplet are still encoded (``encode_triplet=True``) so the step does the same work.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from . import training as T
+from ._lib import RV_BF16, RV_F32, RvError
+from .autoencoder import RgbaAutoencoder
+from .losses import AlphaVaeLoss
+from .plumbing import build_detail_augmented_triplet
+from .posterior import DiagonalGaussianDistribution
+
+
+class VaeTrainStep:
+    def __init__(self, vae: RgbaAutoencoder, *, lr: float = 1e-5, betas=(0.5, 0.9), eps: float = 1e-8,
+                 weight_decay: float = 0.01, max_grad_norm: Optional[float] = 1.0, kl_scale: Optional[float] = 1e-6,
+                 loss_module: Optional[AlphaVaeLoss] = None, num_buckets: int = 4, encode_triplet: bool = True, group=None):
+        if vae.arch != "qwen":
+            raise NotImplementedError("the training step covers the Qwen-Image arch (configs/flux_vae.yaml trains that VAE)")
+        if vae.dtype != torch.bfloat16:
+            raise TypeError("the training step runs the model in bfloat16 (fp32 master weights live in the optimizer)")
+        self.vae = vae
+        self.loss_module = loss_module if loss_module is not None else AlphaVaeLoss()
+        self.kl_scale = kl_scale
+        self.encode_triplet = encode_triplet
+        # parameters autograd would give a gradient to: everything except the video-only temporal convs
+        named = [(n, p) for n, p in vae.named_parameters() if ".time_conv." not in n]
+        self.names = [n for n, _ in named]
+        self.opt = T.FlatAdamW([p for _, p in named], lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                               max_grad_norm=max_grad_norm)
+        self._gview: Dict[int, torch.Tensor] = {id(p): self.opt.grad_view(i) for i, (_, p) in enumerate(named)}
+        self.reducer = T.GradientAllReducer(self.opt.grad, num_buckets=num_buckets, group=group)
+        self._saved_fuse = None
+
+    # ---- small helpers ---------------------------------------------------------------------
+    def _acc(self, p: torch.nn.Parameter, g: torch.Tensor) -> None:
+        """gradient of one parameter into the flat fp32 buffer (5-D causal kernels: only the last temporal tap is live)."""
+        v = self._gview[id(p)]
+        if v.dim() == 5:
+            v[:, :, -1].add_(g.view(v.shape[0], v.shape[1], v.shape[3], v.shape[4]))
+        else:
+            v.add_(g.view(v.shape))
+
+    def _conv(self, x, conv, **kw):
+        return self.vae._conv(x, conv, **kw)
+
+    def _norm(self, x, norm, silu=True):
+        return self.vae._norm(x, norm, silu)
+
+    def _norm_bwd(self, norm, x, dy, silu=True):
+        dx, dg = T.rmsnorm_silu_backward(x, norm.gamma, dy, silu)
+        self._acc(norm.gamma, dg)
+        return dx
+
+    def _conv_bwd(self, conv, x, dy, *, mode: str = "same", need_dx: bool = True):
+        """x: the conv's NHWC bf16 input (channel-padded for the stems); dy: NHWC bf16 gradient of its output, channel
+        count possibly padded above conv.out_channels with zeros.  Accumulates dW / dbias, returns dX (or None)."""
+        w2d = conv.weight2d()
+        cout, cin, k = conv.out_channels, conv.in_channels, conv.k
+        if mode == "down":
+            dyg = T.resample2x(dy, "zero_insert")
+            dw, db = T.conv_wgrad(x, dyg, k, pad=0)
+        elif mode == "up":
+            dyg = dy
+            dw, db = T.conv_wgrad(T.resample2x(x, "nearest"), dy, k)
+        else:
+            dyg = dy
+            dw, db = T.conv_wgrad(x, dy, k)
+        self._acc(conv.weight, dw[:cout, :cin].contiguous())
+        self._acc(conv.bias, db[:cout])
+        if not need_dx:
+            return None
+        dx = T.conv_dgrad(dyg, w2d, pad_lo=2 if mode == "down" else None)
+        if mode == "up":
+            dx = T.resample2x(dx, "sum_pool")
+        return dx
+
+    # ---- residual block --------------------------------------------------------------------
+    def _res_fwd(self, x, blk, tape: Optional[list]):
+        short = getattr(blk, "conv_shortcut", None)
+        a = self._norm(x, blk.norm1)
+        h = x if short is None else self._conv(x, short)
+        t = self._conv(a, blk.conv1)
+        b = self._norm(t, blk.norm2)
+        y = self._conv(b, blk.conv2, residual=h)
+        if tape is not None:
+            tape.append(("res", blk, (x, a, t, b)))
+        return y
+
+    def _res_bwd(self, blk, saved, dy):
+        x, a, t, b = saved
+        short = getattr(blk, "conv_shortcut", None)
+        db = self._conv_bwd(blk.conv2, b, dy)
+        dt = self._norm_bwd(blk.norm2, t, db)
+        da = self._conv_bwd(blk.conv1, a, dt)
+        dx = self._norm_bwd(blk.norm1, x, da)
+        return T.add_(dx, dy if short is None else self._conv_bwd(short, x, dy))
+
+    # ---- attention -------------------------------------------------------------------------
+    def _gemm(self, *a, **k):
+        return self.vae._gemm(*a, **k)
+
+    def _attn_weights(self, attn):
+        c = attn.proj.in_channels
+        wqkv = attn.to_qkv.weight.detach().reshape(3 * c, c).to(torch.bfloat16).contiguous()
+        bqkv = attn.to_qkv.bias.detach().to(torch.float32).contiguous()
+        wo = attn.proj.weight.detach().reshape(c, c).to(torch.bfloat16).contiguous()
+        bo = attn.proj.bias.detach().to(torch.float32).contiguous()
+        return wqkv, bqkv, wo, bo
+
+    def _attn_fwd(self, x, attn, tape: Optional[list]):
+        n, h, w, c = x.shape
+        t = h * w
+        dev = x.device
+        xn = self._norm(x, attn.norm, silu=False)
+        wqkv, bqkv, wo, bo = self._attn_weights(attn)
+        xn2 = xn.view(n * t, c)
+        q = torch.empty((n * t, c), dtype=torch.bfloat16, device=dev)
+        k = torch.empty_like(q)
+        v = torch.empty_like(q)
+        for i, dst in enumerate((q, k, v)):
+            self._gemm(xn2, wqkv[i * c:(i + 1) * c], rows=n * t, k=c, cols=c, x_ld=c, w_ld=c, y=dst, y_ld=c,
+                       bias=bqkv[i * c:(i + 1) * c].contiguous(), bias_mode=1)
+        o = torch.empty_like(q)
+        scale = ops.attn_scale(c)
+        vt = torch.empty((c, t), dtype=torch.bfloat16, device=dev)
+        q_chunk = self._q_chunk(t)
+        s = torch.empty((q_chunk, t), dtype=torch.float32, device=dev)
+        for i in range(n):
+            sl = slice(i * t, (i + 1) * t)
+            # V^T[c][token] (the PV GEMM wants the reduction axis contiguous)
+            self._gemm(wqkv[2 * c:], xn2[sl], rows=c, k=c, cols=t, x_ld=c, w_ld=c, y=vt, y_ld=t, bias=bqkv[2 * c:].contiguous(),
+                       bias_mode=2)
+            for r0 in range(0, t, q_chunk):
+                rows = min(q_chunk, t - r0)
+                self._gemm(q[i * t + r0:i * t + r0 + rows], k[sl], rows=rows, k=c, cols=t, x_ld=c, w_ld=c, y=s[:rows], y_ld=t,
+                           alpha=scale)
+                p = ops.softmax_rows(s[:rows], torch.bfloat16)
+                self._gemm(p, vt, rows=rows, k=t, cols=c, x_ld=t, w_ld=t, y=o[i * t + r0:i * t + r0 + rows], y_ld=c)
+        out = torch.empty_like(x)
+        self._gemm(o, wo, rows=n * t, k=c, cols=c, x_ld=c, w_ld=c, y=out.view(n * t, c), y_ld=c, bias=bo, bias_mode=1,
+                   residual=x.view(n * t, c))
+        if tape is not None:
+            tape.append(("attn", attn, (x, xn, q, k, v, o)))
+        return out
+
+    @staticmethod
+    def _q_chunk(t: int) -> int:
+        return max(64, min(t, ((1 << 27) // t) // 64 * 64))
+
+    def _attn_bwd(self, attn, saved, dout):
+        x, xn, q, k, v, o = saved
+        n, h, w, c = x.shape
+        t = h * w
+        dev = x.device
+        scale = ops.attn_scale(c)
+        as_img = lambda a, ch: a.view(1, 1, a.shape[0], ch)  # [rows][ch] as a one-row NHWC image
+        dout2 = dout.view(n * t, c)
+        # proj: out = o Wo^T + bo + x
+        dwo, dbo = T.conv_wgrad(as_img(o, c), as_img(dout2, c), 1)
+        self._acc(attn.proj.weight, dwo)
+        self._acc(attn.proj.bias, dbo)
+        d_o = T.conv_dgrad(as_img(dout2, c), attn.proj.weight.detach().reshape(c, c, 1, 1)).view(n * t, c)
+        dqkv = torch.empty((n * t, 3 * c), dtype=torch.bfloat16, device=dev)
+        q_chunk = self._q_chunk(t)
+        s = torch.empty((q_chunk, t), dtype=torch.float32, device=dev)
+        dp = torch.empty((q_chunk, t), dtype=torch.float32, device=dev)
+        ds = torch.empty((q_chunk, t), dtype=torch.bfloat16, device=dev)
+        ds_t = torch.empty((t, t), dtype=torch.bfloat16, device=dev)
+        lib_check = T.check
+        from . import _lib
+        for i in range(n):
+            sl = slice(i * t, (i + 1) * t)
+            dv = torch.zeros((t, c), dtype=torch.float32, device=dev)
+            dk = torch.zeros((t, c), dtype=torch.float32, device=dev)
+            dq = torch.zeros((t, c), dtype=torch.float32, device=dev)
+            for r0 in range(0, t, q_chunk):
+                rows = min(q_chunk, t - r0)
+                rs = slice(i * t + r0, i * t + r0 + rows)
+                self._gemm(q[rs], k[sl], rows=rows, k=c, cols=t, x_ld=c, w_ld=c, y=s[:rows], y_ld=t, alpha=scale)
+                p = ops.softmax_rows(s[:rows], torch.bfloat16)
+                # dP = dO V^T
+                self._gemm(d_o[rs], v[sl], rows=rows, k=c, cols=t, x_ld=c, w_ld=c, y=dp[:rows], y_ld=t)
+                lib_check(_lib.load().rv_softmax_bwd(ops._ptr(p), ops._ptr(dp), ops._ptr(ds), ops._ptr(ds_t), rows, t, t, r0, scale,
+                                                     ops._stream(p)), "rv_softmax_bwd")
+                # dV += P^T dO ; dK += dS^T Q   (reduction over this block's query rows)
+                self._wgrad_into(dv, x=d_o[rs], dy=p, rows=rows, cin=c, cout=t)
+                self._wgrad_into(dk, x=q[rs], dy=ds[:rows], rows=rows, cin=c, cout=t)
+            # dQ = dS K  (reduction over keys: dS^T is the "dy" operand)
+            self._wgrad_into(dq, x=k[sl], dy=ds_t, rows=t, cin=c, cout=t)
+            dqkv[sl, :c] = dq
+            dqkv[sl, c:2 * c] = dk
+            dqkv[sl, 2 * c:] = dv
+        dwqkv, dbqkv = T.conv_wgrad(as_img(xn.view(n * t, c), c), as_img(dqkv, 3 * c), 1)
+        self._acc(attn.to_qkv.weight, dwqkv)
+        self._acc(attn.to_qkv.bias, dbqkv)
+        dxn = T.conv_dgrad(as_img(dqkv, 3 * c), attn.to_qkv.weight.detach().reshape(3 * c, c, 1, 1)).view(x.shape)
+        dx = self._norm_bwd(attn.norm, x, dxn, silu=False)
+        return T.add_(dx, dout)
+
+    @staticmethod
+    def _wgrad_into(dst: torch.Tensor, *, x: torch.Tensor, dy: torch.Tensor, rows: int, cin: int, cout: int) -> None:
+        """dst[cout][cin] (fp32) += dy[rows][cout]^T . x[rows][cin]"""
+        from . import _lib
+        T.check(_lib.load().rv_conv2d_wgrad(ops._ptr(x), ops._ptr(dy), ops._ptr(dst), None, 1, 1, rows, cin, cout, 1, 0,
+                                            ops._stream(x)), "rv_conv2d_wgrad")
+
+    # ---- encoder / decoder -----------------------------------------------------------------
+    def _run_fwd(self, x, items, tape):
+        for kind, m in items:
+            if kind == "res":
+                x = self._res_fwd(x, m, tape)
+            elif kind == "attn":
+                x = self._attn_fwd(x, m, tape)
+            elif kind == "down":
+                y = self._conv(x, m)
+                if tape is not None:
+                    tape.append(("down", m, x))
+                x = y
+            elif kind == "up":
+                y = self._conv(x, m, upsample=True)
+                if tape is not None:
+                    tape.append(("up", m, x))
+                x = y
+            elif kind == "conv":
+                y = self._conv(x, m)
+                if tape is not None:
+                    tape.append(("conv", m, x))
+                x = y
+            elif kind == "norm":
+                y = self._norm(x, m)
+                if tape is not None:
+                    tape.append(("norm", m, x))
+                x = y
+            else:
+                raise AssertionError(kind)
+        return x
+
+    def _run_bwd(self, tape: list, dy):
+        while tape:
+            kind, m, saved = tape.pop()
+            if kind == "res":
+                dy = self._res_bwd(m, saved, dy)
+            elif kind == "attn":
+                dy = self._attn_bwd(m, saved, dy)
+            elif kind in ("down", "up"):
+                dy = self._conv_bwd(m, saved, dy, mode=kind)
+            elif kind == "conv":
+                dy = self._conv_bwd(m, saved, dy)
+            elif kind == "norm":
+                dy = self._norm_bwd(m, saved, dy)
+            elif kind == "stem":  # first conv of a network: input has no gradient (or it is returned as is)
+                conv, need_dx = m
+                dy = self._conv_bwd(conv, saved, dy, need_dx=need_dx)
+            else:
+                raise AssertionError(kind)
+        return dy
+
+    def _encoder_items(self):
+        enc = self.vae.encoder
+        items = []
+        for blk in enc.down_blocks:
+            items.append(("res", blk) if blk._kind == "res" else ("down", blk.resample[1]))
+        mid = enc.mid_block
+        items += [("res", mid.resnets[0]), ("attn", mid.attentions[0]), ("res", mid.resnets[1]), ("norm", enc.norm_out),
+                  ("conv", enc.conv_out)]
+        return items
+
+    def _decoder_items(self):
+        dec = self.vae.decoder
+        mid = dec.mid_block
+        items = [("conv", dec.conv_in), ("res", mid.resnets[0]), ("attn", mid.attentions[0]), ("res", mid.resnets[1])]
+        for blk in dec.up_blocks:
+            items += [("res", r) for r in blk.resnets]
+            if getattr(blk, "upsamplers", None) is not None:
+                items.append(("up", blk.upsamplers[0].resample[1]))
+        items.append(("norm", dec.norm_out))
+        return items
+
+    def encode_moments(self, x_vae: torch.Tensor, tape: Optional[list]) -> torch.Tensor:
+        """(B,4,H,W) in [-1,1] -> fp32 moments (B,32,H/8,W/8), recording the tape."""
+        vae = self.vae
+        vae._check_image(x_vae, 4, "training input", 8)
+        xp = ops.nchw_to_nhwc(x_vae.contiguous(), 16, torch.bfloat16)
+        y = self._conv(xp, vae.encoder.conv_in)
+        if tape is not None:
+            tape.append(("stem", (vae.encoder.conv_in, False), xp))
+        h = self._run_fwd(y, self._encoder_items(), tape)
+        if tape is not None:
+            tape.append(("conv", vae.quant_conv, h))
+        return self._conv(h, vae.quant_conv, y_nchw=True, y_dtype=torch.float32)
+
+    def decode(self, z: torch.Tensor, tape: Optional[list]) -> torch.Tensor:
+        """fp32 latents (B,16,h,w) -> fp32 image (B,4,8h,8w) clamped to [-1,1] (AutoencoderKLQwenImage._decode)."""
+        vae = self.vae
+        zp = ops.nchw_to_nhwc(z.contiguous(), 16, torch.bfloat16)
+        y = self._conv(zp, vae.post_quant_conv)
+        if tape is not None:
+            tape.append(("stem", (vae.post_quant_conv, True), zp))
+        h = self._run_fwd(y, self._decoder_items(), tape)
+        if tape is not None:
+            tape.append(("conv", vae.decoder.conv_out, h))
+        return self._conv(h, vae.decoder.conv_out, y_nchw=True, y_dtype=torch.float32, clamp=(-1.0, 1.0))
+
+    # ---- the step --------------------------------------------------------------------------
+    def forward_backward(self, inputs: torch.Tensor, noise: Optional[torch.Tensor] = None, generator=None) -> Dict[str, torch.Tensor]:
+        """inputs: (B,4,H,W) in [0,1].  Fills the optimizer's flat gradient buffer; returns the step's loss terms."""
+        if not inputs.is_cuda:
+            raise RvError("VaeTrainStep runs on CUDA (sm_100a) only; there is no CPU path")
+        vae = self.vae
+        fuse, vae.fuse_norm = vae.fuse_norm, False  # the tape needs the raw conv outputs
+        try:
+            B = inputs.shape[0]
+            target_vae = torch.clamp(inputs.to(torch.float32), 0.0, 1.0) * 2.0 - 1.0
+            enc_tape: list = []
+            moments = self.encode_moments(target_vae, enc_tape)
+            if self.encode_triplet:  # black / white composites: encoded like the reference does, no gradient path
+                composed = build_detail_augmented_triplet(target_vae)
+                vae.fuse_norm = fuse
+                vae._encode_moments(composed[B:])
+                vae.fuse_norm = False
+            post = DiagonalGaussianDistribution(moments)
+            if noise is None:
+                noise = torch.randn(post.mean.shape, generator=generator, device=inputs.device, dtype=torch.float32)
+            z = post.sample(noise=noise)
+            dec_tape: list = []
+            pred = self.decode(z, dec_tape)
+            lm = self.loss_module
+            recon = lm.reconstruction_loss(pred, target_vae)
+            metrics = {"train/recon": recon}
+            total = recon
+            kl_w = 0.0
+            if self.kl_scale is not None and self.kl_scale > 0.0:
+                kl = lm.kl_loss(post)
+                metrics["train/kl"] = kl
+                total = total + self.kl_scale * kl
+                kl_w = self.kl_scale / B  # posterior.kl() is already the per-sample sum; both reduce rules average it over B
+            metrics["train/loss"] = total
+            # ---- backward ----
+            self.opt.zero_grad()
+            dpred = T.recon_loss_backward(pred, target_vae, lm._eb, lm._eb2, lm.reduce_mean, lm.use_naive_mse, clamp=(-1.0, 1.0))
+            dy = ops.nchw_to_nhwc(dpred, 16, torch.bfloat16)
+            dzp = self._run_bwd(dec_tape, dy)  # NHWC [B,h,w,16]
+            self._mark_ready(decoder_done=True)
+            dz = ops.nhwc_to_nchw(dzp, 16, torch.float32)
+            dmom = T.reparam_backward(moments, noise, dz, kl_weight=kl_w)
+            dm = ops.nchw_to_nhwc(dmom, dmom.shape[1], torch.bfloat16)
+            self._run_bwd(enc_tape, dm)
+            self._mark_ready(decoder_done=False)
+            return metrics
+        finally:
+            vae.fuse_norm = fuse
+
+    def _mark_ready(self, decoder_done: bool) -> None:
+        """Start the all-reduce of every bucket whose parameters all have their gradients (the decoder's parameters come
+        after the encoder's in the flat buffer, so its buckets go first while the encoder backward still runs)."""
+        if self.reducer.world() == 1:
+            return
+        if decoder_done:
+            self._started = set()
+            for b, (lo, hi) in enumerate(self.reducer.buckets):
+                if self._bucket_is_decoder(lo, hi):
+                    self.reducer.ready(b)
+                    self._started.add(b)
+        else:
+            for b in range(len(self.reducer.buckets)):
+                if b not in self._started:
+                    self.reducer.ready(b)
+
+    def _bucket_is_decoder(self, lo: int, hi: int) -> bool:
+        for i, n in enumerate(self.names):
+            if self.opt.offsets[i + 1] > lo and self.opt.offsets[i] < hi and not n.startswith(("decoder.", "post_quant_conv.")):
+                return False
+        return True
+
+    def step(self, inputs: torch.Tensor, noise: Optional[torch.Tensor] = None, generator=None) -> Dict[str, torch.Tensor]:
+        """forward + backward + gradient all-reduce + clip + AdamW; returns the loss terms (device scalars)."""
+        metrics = self.forward_backward(inputs, noise, generator)
+        scale = self.reducer.wait()
+        self.opt.step(grad_scale=scale)
+        self.vae._pack_cache.clear()  # packed weights are stale after the in-place update
+        return metrics
+
+    def named_grads(self) -> Dict[str, torch.Tensor]:
+        return {n: self.opt.grad_view(i) for i, n in enumerate(self.names)}

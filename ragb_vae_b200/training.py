@@ -3,8 +3,9 @@
 What is here: backward of the AlphaVAE reconstruction loss, of the posterior sample (+KL), of RMS-norm + SiLU, the
 data gradient of the stride-1 convolutions (the forward tcgen05 kernels run on flipped/transposed weights), the
 flat-buffer AdamW with fused gradient scaling and ``clip_grad_norm_``, and the bucketed data-parallel gradient
-all-reduce (NCCL over NVLink on the GPUs; the only collective of the whole path).  What is NOT here yet: the weight
-gradient of the convolutions, attention backward and the tape that strings a full backward pass together.
+all-reduce (NCCL over NVLink on the GPUs; the only collective of the whole path), the weight gradient of the
+convolutions and the spatial helpers of the strided / up-sampling layers.  ``trainer.VaeTrainStep`` strings them into
+the full step.
 """
 from __future__ import annotations
 
@@ -24,8 +25,10 @@ from .ops import _dt, _need_cuda, _ptr, _stream
 # backward of the non-conv pieces
 # ------------------------------------------------------------------------------------------
 def recon_loss_backward(pred: torch.Tensor, target: torch.Tensor, eb: Sequence[float], eb2: Sequence[float],
-                        reduce_mean: bool = False, naive_mse: bool = False, grad_output: float = 1.0) -> torch.Tensor:
-    """d reconstruction_loss / d pred (losses.py:67-83 with the reduce rule of :117-123)."""
+                        reduce_mean: bool = False, naive_mse: bool = False, grad_output: float = 1.0,
+                        clamp: Optional[Sequence[float]] = None) -> torch.Tensor:
+    """d reconstruction_loss / d pred (losses.py:67-83 with the reduce rule of :117-123).  ``clamp=(lo, hi)``: pred is
+    the decoder's clamped output; the gradient is zero where it sits on a bound (backward of torch.clamp)."""
     pred, target = ops._pair(pred, target)
     n, _, h, w = pred.shape
     ch = 4 if naive_mse else 3
@@ -33,7 +36,8 @@ def recon_loss_backward(pred: torch.Tensor, target: torch.Tensor, eb: Sequence[f
     out = torch.empty_like(pred)
     ebv = (C.c_float * 3)(*[float(v) for v in eb])
     eb2v = (C.c_float * 3)(*[float(v) for v in eb2])
-    check(_lib.load().rv_recon_loss_bwd(_ptr(pred), _ptr(target), ebv, eb2v, int(naive_mse), scale, _ptr(out), n, h * w,
+    lo, hi = (0.0, 0.0) if clamp is None else (float(clamp[0]), float(clamp[1]))
+    check(_lib.load().rv_recon_loss_bwd(_ptr(pred), _ptr(target), ebv, eb2v, int(naive_mse), scale, lo, hi, _ptr(out), n, h * w,
                                         _dt(pred), _stream(pred)), "rv_recon_loss_bwd")
     return out
 
@@ -67,27 +71,34 @@ def rmsnorm_silu_backward(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor
     return dx, (dg * math.sqrt(c)).reshape(gamma.shape)
 
 
-def conv_dgrad_weights(weight2d: torch.Tensor) -> torch.Tensor:
+def conv_dgrad_weights(weight2d: torch.Tensor, cout_pad: int = 0) -> torch.Tensor:
     """[cout][cin][k][k] -> packed bf16 weights of the convolution that maps dY to dX for a stride-1 'same' conv:
-    W'[cin][cout][k-1-dy][k-1-dx] = W[cout][cin][dy][dx]."""
-    return ops.pack_conv_weights_tc(weight2d.detach().to(torch.float32).flip(2, 3).permute(1, 0, 2, 3).contiguous())
+    W'[cin][cout][k-1-dy][k-1-dx] = W[cout][cin][dy][dx]; ``cout_pad`` zero-pads the (now input) channel axis to dY's."""
+    wt = weight2d.detach().to(torch.float32).flip(2, 3).permute(1, 0, 2, 3)
+    if cout_pad and cout_pad > wt.shape[1]:
+        wt = torch.nn.functional.pad(wt, (0, 0, 0, 0, 0, cout_pad - wt.shape[1]))
+    return ops.pack_conv_weights_tc(wt.contiguous())
 
 
-def conv_dgrad(dy: torch.Tensor, weight2d: torch.Tensor) -> torch.Tensor:
+def conv_dgrad(dy: torch.Tensor, weight2d: torch.Tensor, pad_lo: Optional[int] = None) -> torch.Tensor:
     """dX (NHWC bf16) of a stride-1 3x3 pad-1 (or 1x1) convolution from dY (NHWC bf16): the forward tensor-core
-    kernel on the flipped, transposed weights (no bias)."""
+    kernel on the flipped, transposed weights (no bias).  dY may carry zero-padded channels beyond the conv's cout.
+    ``pad_lo=2`` with a zero-inserted dY is the data gradient of the stride-2 (0,1,0,1)-padded down-sampling conv."""
     _need_cuda(dy, weight2d)
-    n, h, w, cout = dy.shape
+    n, h, w, cy = dy.shape
     cin, k = weight2d.shape[1], weight2d.shape[2]
-    wp = conv_dgrad_weights(weight2d)
+    wp = conv_dgrad_weights(weight2d, cy)
     dx = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device=dy.device)
-    desc = ops.make_desc(n, h, w, cout, cin, k, 1, False, x_dtype=RV_BF16, y_dtype=RV_BF16, bias_mode=0)
+    desc = ops.make_desc(n, h, w, cy, cin, k, 1, False, x_dtype=RV_BF16, y_dtype=RV_BF16, bias_mode=0)
+    if pad_lo is not None:
+        desc.pad_lo = pad_lo
     ops.conv2d_tc(desc, dy.contiguous(), wp, wp.shape[1], None, None, dx)
     return dx
 
 
-def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, want_bias: bool = True):
-    """(dW [cout][cin][k][k], dbias [cout]) in fp32 of a stride-1 'same' convolution from x and dY (NHWC bf16)."""
+def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, want_bias: bool = True, pad: Optional[int] = None):
+    """(dW [cout][cin][k][k], dbias [cout]) in fp32 of a stride-1 'same' convolution from x and dY (NHWC bf16).
+    ``pad=0`` with a zero-inserted dY gives the gradient of the stride-2 (0,1,0,1)-padded conv."""
     _need_cuda(x, dy)
     n, h, w, cin = x.shape
     cout = dy.shape[-1]
@@ -95,8 +106,26 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, want_bias: bool = 
     dw = torch.zeros((cout, taps * cin), dtype=torch.float32, device=x.device)
     db = torch.zeros(cout, dtype=torch.float32, device=x.device) if want_bias else None
     check(_lib.load().rv_conv2d_wgrad(_ptr(x.contiguous()), _ptr(dy.contiguous()), _ptr(dw), _ptr(db), n, h, w, cin, cout, ksize,
-                                      _stream(x)), "rv_conv2d_wgrad")
+                                      ksize // 2 if pad is None else pad, _stream(x)), "rv_conv2d_wgrad")
     return dw.view(cout, ksize, ksize, cin).permute(0, 3, 1, 2).contiguous(), db
+
+
+def resample2x(x: torch.Tensor, mode: str) -> torch.Tensor:
+    """NHWC bf16: 'zero_insert' (x2, zeros between), 'nearest' (x2), 'sum_pool' (2x2 sums)."""
+    _need_cuda(x)
+    m = {"zero_insert": 0, "nearest": 1, "sum_pool": 2}[mode]
+    n, h, w, c = x.shape
+    y = torch.empty((n, h // 2, w // 2, c) if m == 2 else (n, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().rv_resample2x(_ptr(x.contiguous()), _ptr(y), n, h, w, c, m, _stream(x)), "rv_resample2x")
+    return y
+
+
+def add_(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a + b (bf16, same shape) through librgbavae."""
+    _need_cuda(a, b)
+    y = torch.empty_like(a)
+    check(_lib.load().rv_add_bf16(_ptr(a.contiguous()), _ptr(b.contiguous()), _ptr(y), a.numel(), _stream(a)), "rv_add_bf16")
+    return y
 
 
 # ------------------------------------------------------------------------------------------

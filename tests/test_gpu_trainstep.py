@@ -1,0 +1,225 @@
+"""GPU parity of the hand-written backward pass / training step (ragb_vae_b200.trainer) against torch autograd on the
+CPU oracle (oracle.vae_oracle.training_step restates src/training/rgba_vae_stage.py:433-523).
+
+The GPU path keeps activations and activation gradients in bf16 (weight gradients accumulate in fp32), the oracle is
+fp32 throughout, so gradients are compared per tensor by relative L2 error and cosine, with the tolerance written here:
+single blocks 3e-2; the whole 60-conv network 6e-2 per tensor / 2e-2 over the flat gradient (errors of independent
+bf16 roundings add up over depth; measured 3.4e-2 worst tensor, 9.2e-3 flat), cosine > 0.999."""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import vae_oracle as O  # noqa: E402
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu().reshape(-1), b.detach().double().cpu().reshape(-1)
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def cos(a, b):
+    a, b = a.detach().double().cpu().reshape(-1), b.detach().double().cpu().reshape(-1)
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous().cuda().to(torch.bfloat16)
+
+
+def nchw(t):
+    return t.float().permute(0, 3, 1, 2).cpu()
+
+
+@pytest.fixture(scope="module")
+def pair(lib_built):
+    """(oracle with bf16-representable weights, VaeTrainStep over a bf16 GPU model with the same weights)"""
+    import ragb_vae_b200 as R
+    from ragb_vae_b200.trainer import VaeTrainStep
+
+    assert torch.cuda.is_available()
+    oracle = copy.deepcopy(O.build_oracle("qwen", seed=0))
+    with torch.no_grad():
+        for p in oracle.parameters():
+            p.copy_(bf16r(p))
+    vae = R.RgbaAutoencoder("qwen")
+    vae.load_state_dict(oracle.state_dict())
+    vae = vae.to("cuda", torch.bfloat16)
+    step = VaeTrainStep(vae, lr=1e-3, kl_scale=1e-6)
+    return oracle, step
+
+
+def test_resample2x(lib_built):
+    from ragb_vae_b200 import training as T
+
+    x = torch.randn(2, 6, 10, 16, generator=torch.Generator().manual_seed(0)).cuda().to(torch.bfloat16)
+    z = T.resample2x(x, "zero_insert")
+    ref = torch.zeros(2, 12, 20, 16, dtype=torch.bfloat16, device="cuda")
+    ref[:, ::2, ::2] = x
+    assert torch.equal(z, ref)
+    u = T.resample2x(x, "nearest")
+    assert torch.equal(u, x.repeat_interleave(2, 1).repeat_interleave(2, 2))
+    s = T.resample2x(u, "sum_pool")
+    assert rel(s.float(), 4 * x.float()) < 1e-2
+    a = T.add_(x, x)
+    assert torch.equal(a, (2 * x.float()).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("mode", ["down", "up"])
+def test_strided_conv_grads(lib_built, mode):
+    """dX / dW / dbias of the stride-2 (0,1,0,1)-padded conv and of nearest-x2 + conv vs autograd."""
+    from ragb_vae_b200 import training as T
+
+    g = torch.Generator().manual_seed(3)
+    cin, cout = (96, 96) if mode == "down" else (192, 96)
+    n, h, w = 2, 16, 24
+    x = bf16r(torch.randn(n, cin, h, w, generator=g)).requires_grad_(True)
+    wt = bf16r(torch.randn(cout, cin, 3, 3, generator=g) * 0.05).requires_grad_(True)
+    b = torch.zeros(cout, requires_grad=True)
+    if mode == "down":
+        y = F.conv2d(F.pad(x, (0, 1, 0, 1)), wt, b, stride=2)
+    else:
+        y = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest-exact"), wt, b, padding=1)
+    gy = bf16r(torch.randn(y.shape, generator=g))
+    (y * gy).sum().backward()
+    dy = nhwc(gy)
+    xg = nhwc(x.detach())
+    if mode == "down":
+        dyg = T.resample2x(dy, "zero_insert")
+        dw, db = T.conv_wgrad(xg, dyg, 3, pad=0)
+        dx = T.conv_dgrad(dyg, wt.detach().cuda(), pad_lo=2)
+    else:
+        dw, db = T.conv_wgrad(T.resample2x(xg, "nearest"), dy, 3)
+        dx = T.resample2x(T.conv_dgrad(dy, wt.detach().cuda()), "sum_pool")
+    assert rel(dw, wt.grad) < 1e-2
+    assert rel(db, b.grad) < 1e-2
+    assert rel(nchw(dx), x.grad) < 2e-2
+
+
+def _block_case(pair, gpu_blk, oracle_blk, fwd, bwd, cin, n=2, h=8, w=8, tol=3e-2):
+    oracle, step = pair
+    g = torch.Generator().manual_seed(5)
+    x = bf16r(torch.randn(n, cin, h, w, generator=g)).requires_grad_(True)
+    oracle_blk.requires_grad_(True)
+    oracle_blk.zero_grad(set_to_none=True)
+    y = oracle_blk(x)
+    gy = bf16r(torch.randn(y.shape, generator=g))
+    (y * gy).sum().backward()
+    step.opt.zero_grad()
+    tape = []
+    yg = fwd(nhwc(x.detach()), gpu_blk, tape)
+    assert rel(nchw(yg), y) < 2e-2
+    kind, m, saved = tape.pop()
+    dx = bwd(m, saved, nhwc(gy))
+    assert rel(nchw(dx), x.grad) < tol, "dx"
+    grads = step.named_grads()
+    prefix = next(nm for nm, mod in step.vae.named_modules() if mod is gpu_blk) + "."
+    checked = 0
+    for name, p in oracle_blk.named_parameters():
+        if p.grad is None:
+            continue
+        got = grads[prefix + name]
+        want = p.grad
+        if want.dim() == 5:  # causal 3-D kernel: only the last temporal tap sees the frame
+            if got.shape[2] > 1:
+                assert float(got[:, :, :-1].abs().max()) == 0.0
+            got, want = got[:, :, -1], want[:, :, -1]
+        assert rel(got, want) < tol, name
+        checked += 1
+    oracle_blk.requires_grad_(False)
+    assert checked >= 4
+
+
+def test_resblock_backward_with_shortcut(pair):
+    oracle, step = pair
+    _block_case(pair, step.vae.encoder.down_blocks[3], oracle.encoder.down_blocks[3], step._res_fwd, step._res_bwd, 96, h=16, w=16)
+
+
+def test_resblock_backward_identity_shortcut(pair):
+    oracle, step = pair
+    _block_case(pair, step.vae.encoder.down_blocks[0], oracle.encoder.down_blocks[0], step._res_fwd, step._res_bwd, 96, h=16, w=24)
+
+
+@pytest.mark.parametrize("hw,chunk", [((8, 8), None), ((16, 24), None), ((16, 24), 128)])
+def test_attention_backward(pair, hw, chunk):
+    oracle, step = pair
+    if chunk is not None:  # several query-row blocks per image: dV / dK accumulate across blocks
+        step._q_chunk = lambda t: chunk
+    try:
+        _block_case(pair, step.vae.decoder.mid_block.attentions[0], oracle.decoder.mid_block.attentions[0], step._attn_fwd,
+                    step._attn_bwd, 384, h=hw[0], w=hw[1])
+    finally:
+        step.__dict__.pop("_q_chunk", None)
+
+
+def test_full_step_gradients_match_oracle_autograd(pair):
+    """The whole step (triplet, encode, sample, decode, loss, backward) at 2 x 64 x 64: every parameter's gradient."""
+    oracle, step = pair
+    x = O.synthetic_rgba(2, 64, 64, seed=11)
+    noise = torch.randn(2, 16, 8, 8, generator=torch.Generator().manual_seed(12))
+    metrics, want = O.training_step(oracle, x, noise, kl_scale=1e-6)
+    got_metrics = step.forward_backward(x.cuda(), noise.cuda())
+    for k in ("train/recon", "train/kl", "train/loss"):
+        assert abs(float(got_metrics[k]) - float(metrics[k])) <= 2e-2 * abs(float(metrics[k])), k
+    grads = step.named_grads()
+    assert set(want) == set(grads), (set(want) ^ set(grads))
+    worst, flat_g, flat_w = {}, [], []
+    for name, wg in want.items():
+        gg = grads[name]
+        flat_g.append(gg.reshape(-1).cpu())
+        flat_w.append(wg.reshape(-1))
+        worst[name] = (rel(gg, wg), cos(gg, wg))
+    flat_g, flat_w = torch.cat(flat_g), torch.cat(flat_w)
+    import json, os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "trainstep_grad_report.json"), "w") as f:
+            json.dump({"flat_rel": rel(flat_g, flat_w), "flat_cos": cos(flat_g, flat_w),
+                       "per_tensor": {k: v for k, v in sorted(worst.items(), key=lambda kv: -kv[1][0])}}, f, indent=1)
+    except OSError:
+        pass
+    assert rel(flat_g, flat_w) < 2e-2
+    assert cos(flat_g, flat_w) > 0.999
+    big = {k: v for k, v in worst.items() if want[k].norm() > 1e-3 * flat_w.norm()}
+    bad = {k: v for k, v in big.items() if v[0] > 6e-2}
+    assert not bad, bad
+
+
+def test_optimizer_step_moves_weights_like_adamw(pair):
+    """One full step(): clip_grad_norm_(1.0) + AdamW(lr, betas (0.5, 0.9), wd 0.01) on the oracle vs the fused update."""
+    oracle, step = pair
+    x = O.synthetic_rgba(2, 64, 64, seed=21)
+    noise = torch.randn(2, 16, 8, 8, generator=torch.Generator().manual_seed(22))
+    ref = copy.deepcopy(oracle)
+    with torch.no_grad():  # start both from the GPU model's current weights
+        sd = {k: v.detach().float().cpu() for k, v in step.vae.state_dict().items()}
+        ref.load_state_dict(sd)
+    before = {n: p.detach().clone() for n, p in ref.named_parameters()}
+    _, grads = O.training_step(ref, x, noise, kl_scale=1e-6)
+    params = [p for n, p in ref.named_parameters() if n in grads]
+    for n, p in ref.named_parameters():
+        p.requires_grad_(n in grads)
+        p.grad = grads.get(n)
+    torch.nn.utils.clip_grad_norm_(params, 1.0)
+    opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.5, 0.9), weight_decay=0.01)
+    opt.step()
+    step.opt.t = 0
+    step.opt.m.zero_()
+    step.opt.v.zero_()
+    master_before = step.opt.master.clone()
+    step.step(x.cuda(), noise.cuda())
+    delta_gpu = (step.opt.master - master_before).cpu()
+    after = dict(ref.named_parameters())
+    delta_ref = torch.cat([(after[n].detach() - before[n]).reshape(-1) for n in step.names])
+    assert delta_gpu.shape == delta_ref.shape
+    # the first AdamW step is ~ -lr * sign(g): entries whose gradient is ~0 flip freely, so compare in aggregate
+    assert cos(delta_gpu, delta_ref) > 0.97
+    assert abs(float(delta_gpu.abs().mean()) / float(delta_ref.abs().mean()) - 1.0) < 0.03
