@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 10
+#define RV_ABI_VERSION 11
 #define RV_PROF_CATEGORIES 9
 
 int rv_abi_version(void);
@@ -198,16 +198,26 @@ int rv_recon_loss_bwd(const void* pred, const void* target, const float* eb_host
  * (dz / noise may both be NULL for the KL term alone); the logvar gradient is zero outside the clamp range. */
 int rv_reparam_bwd(const void* moments, const void* noise, const void* dz, void* dmoments, int n, int zc,
                    int64_t hw, int dtype, float kl_weight, void* stream);
-/* Backward of rv_rmsnorm_silu: dx, and dgamma_scaled[c] += d loss / d (gamma*sqrt(C)) (fp32, caller zeroes it;
- * d loss / d gamma = sqrt(C) * dgamma_scaled).  gamma_scaled = gamma * sqrt(C).  c in {96, 192, 384}. */
-int rv_rmsnorm_silu_bwd(const void* x, const float* gamma_scaled, const void* dy, void* dx, float* dgamma_scaled,
-                        int64_t pixels, int c, int dtype, int apply_silu, void* stream);
-/* Weight (and bias) gradient of a stride-1 'same' 3x3 or 1x1 convolution on the tensor cores: x NHWC bf16 [n][h][w][cin],
- * dy NHWC bf16 [n][h][w][cout]; dw fp32 [cout][ksize*ksize][cin] and dbias fp32 [cout] (optional) are ACCUMULATED
- * (the caller zeroes them).  cin % 16 == 0, cout % 8 == 0.  pad = ksize/2 for a 'same' conv; pad = 0 with a
- * zero-inserted dy gives the weight gradient of the stride-2 (0,1,0,1)-padded down-sampling conv. */
-int rv_conv2d_wgrad(const void* x, const void* dy, float* dw, float* dbias, int n, int h, int w, int cin, int cout,
-                    int ksize, int pad, void* stream);
+/* Backward of rv_rmsnorm_silu: dx, and dgamma[c] += dgamma_scale * d loss / d (gamma*sqrt(C)) (fp32, ACCUMULATED;
+ * dgamma_scale = sqrt(C) gives d loss / d gamma, so dgamma may point straight into a gradient buffer).
+ * gamma_scaled = gamma * sqrt(C).  c = 3 * 2^k 16-byte chunks (96, 192, 384 in bf16). */
+int rv_rmsnorm_silu_bwd(const void* x, const float* gamma_scaled, const void* dy, void* dx, float* dgamma,
+                        float dgamma_scale, int64_t pixels, int c, int dtype, int apply_silu, void* stream);
+/* Weight (and bias) gradient of a stride-1 3x3 or 1x1 convolution on the tensor cores: x NHWC bf16 [n][h][w][cin],
+ * dy NHWC bf16 [n][h][w][cout].  Element (co, ci, tap) is ACCUMULATED (fp32 atomics) at
+ * dw[co*dw_co_stride + ci*dw_ci_stride + tap*dw_tap_stride], so the gradient can land directly in the parameter's own
+ * layout ([cout][cin][k][k]: strides cin*k*k, k*k, 1; the last temporal slice of a [cout][cin][3][3][3] causal kernel:
+ * strides 27*cin, 27, 1 from dw + 18).  dbias [cout_valid] optional, accumulated.  Only co < cout_valid and
+ * ci < cin_valid are written (channel-padded stems).  cin % 16 == 0, cout % 8 == 0.  pad = ksize/2 for a 'same' conv;
+ * pad = 0 with a zero-inserted dy gives the weight gradient of the stride-2 (0,1,0,1)-padded down-sampling conv. */
+int rv_conv2d_wgrad(const void* x, const void* dy, float* dw, int64_t dw_co_stride, int64_t dw_ci_stride,
+                    int64_t dw_tap_stride, float* dbias, int n, int h, int w, int cin, int cout, int cin_valid,
+                    int cout_valid, int ksize, int pad, void* stream);
+/* Packed bf16 weights of the convolution that maps dY to dX (data gradient of a stride-1 conv): reads the parameter in
+ * place (bf16, element (co, ci, tap) at w[co*w_co_stride + ci*w_ci_stride + tap]) and writes
+ * out[ci][tap'*cout_pad + co] = W[co][ci][taps-1-tap'] (zero for co >= cout): taps flipped, channels transposed. */
+int rv_pack_dgrad_weights(const void* w, int64_t w_co_stride, int64_t w_ci_stride, void* out, int cout, int cin,
+                          int cout_pad, int ksize, void* stream);
 /* Spatial helpers of the backward pass, NHWC bf16, c % 8 == 0.  mode 0: zero-insert x2 (dY of a stride-2 conv onto
  * the input grid); mode 1: nearest x2 upsample; mode 2: 2x2 sum pool (backward of the nearest upsample). */
 int rv_resample2x(const void* x, void* y, int n, int h, int w, int c, int mode, void* stream);

@@ -6,8 +6,12 @@
 // MN-major SWIZZLE_128B layout (64-element MN blocks LBO apart, 8-row K groups 1024 B apart).  The tap shift of X is a
 // TMA coordinate offset; image borders are out-of-bounds zero fill.
 //
-// One CTA = (tap, 128-row Cout tile, Cin tile, pixel split): it streams its image rows through a TMA ring, accumulates
-// in TMEM (fp32) and adds the tile to dW with fp32 atomics (split-K over pixels).  Warps: 0 TMA, 1 MMA, 2-5 epilogue.
+// One CTA = (kernel row ty, 128-row Cout tile, Cin tile, pixel split).  The ksize taps of one kernel row differ only by a
+// one-pixel shift of X, i.e. by one 128-byte row of the X box, so the CTA loads ONE dY box and ONE (KP + ksize - 1)-pixel
+// X box per K block and issues the MMAs of all ksize taps from them (descriptor start address + tx * 128 B) into ksize
+// TMEM accumulators: operand traffic per MMA is a third of the tap-per-CTA form.  It streams its image rows through a
+// TMA ring and adds the tiles to dW with fp32 atomics (split-K over pixels); dW is addressed through three strides so
+// the gradient lands directly in the parameter's own layout.  Warps: 0 TMA, 1 MMA, 2-5 epilogue.
 #include <cstring>
 #include <mutex>
 
@@ -18,17 +22,18 @@ namespace rv {
 constexpr int WG_THREADS = 192;
 constexpr int WG_KP = 64;            // pixels per K block (4 MMAs of K = 16)
 constexpr int WG_MAX_STAGES = 8;
-constexpr uint32_t WG_BOX_BYTES = WG_KP * 128;  // one (64 channels x KP pixels) box
+constexpr uint32_t WG_A_BOX = WG_KP * 128;  // one (64 channels x KP pixels) dY box
+constexpr uint32_t WG_B_BOX = 9 * 1024;     // one (64 channels x (KP + 2) pixels) X box, padded to the swizzle atom
 
 struct WgParams {
   int n_img, h, w;
-  int cin, cout, ksize, pad;
-  int co_tiles, ci_tiles, bn, nboxes_b;  // bn: Cin columns per tile (multiple of 16, <= 256)
+  int cin, cout, cin_valid, cout_valid, ksize, pad;
+  int co_tiles, ci_tiles, bn, nboxes_b;  // bn: Cin columns per tile (multiple of 16, ksize * bn <= 512)
   int splits, rows_per_split, x_blocks;
-  float* dw;      // [cout][taps*cin] fp32, accumulated
-  int dw_ld;
+  float* dw;      // element (co, ci, tap) at dw[co * s_co + ci * s_ci + tap * s_tap], accumulated
+  long long s_co, s_ci, s_tap;
   int stages;
-  uint32_t stage_bytes, tx_bytes;
+  uint32_t stage_bytes, tx_bytes, tmem_cols;
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -49,8 +54,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   const int ci_t = u % p.ci_tiles;
   u /= p.ci_tiles;
   const int co_t = u % p.co_tiles;
-  const int tap = u / p.co_tiles;
-  const int dy = tap / p.ksize - p.pad, dx = tap % p.ksize - p.pad;
+  const int ty = u / p.co_tiles;
+  const int dy = ty - p.pad;
   const int co0 = co_t * 128, ci0 = ci_t * p.bn;
   const int total_rows = p.n_img * p.h;
   const int row_lo = split * p.rows_per_split;
@@ -67,7 +72,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   }
   if (warp == 1) {
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(256u)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -76,7 +81,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
   const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]), done = smem_u32(&bar_done);
-  const uint32_t a_bytes = 2u * WG_BOX_BYTES;
+  const uint32_t a_bytes = 2u * WG_A_BOX;
 
   if (warp == 0) {
     uint32_t stage = 0, phase = 0;
@@ -89,9 +94,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
           const uint32_t dst = smem_base + stage * p.stage_bytes;
           mbar_arrive_expect_tx(full, p.tx_bytes);
           tma_load_4d(dst, &map_dy, full, co0, xb * WG_KP, y, n);
-          tma_load_4d(dst + WG_BOX_BYTES, &map_dy, full, co0 + 64, xb * WG_KP, y, n);
+          tma_load_4d(dst + WG_A_BOX, &map_dy, full, co0 + 64, xb * WG_KP, y, n);
           for (int b = 0; b < p.nboxes_b; ++b)
-            tma_load_4d(dst + a_bytes + b * WG_BOX_BYTES, &map_x, full, ci0 + 64 * b, xb * WG_KP + dx, y + dy, n);
+            tma_load_4d(dst + a_bytes + b * WG_B_BOX, &map_x, full, ci0 + 64 * b, xb * WG_KP - p.pad, y + dy, n);
         }
         __syncwarp();
         if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
@@ -101,12 +106,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     // D fp32, A/B bf16, both MN-major (bits 15, 16), N = bn, M = 128
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.bn >> 3) << 17) |
                            ((128u >> 4) << 24);
-    // MN-major SW128 descriptor: LBO = distance between 64-element MN blocks (one box), SBO = 8 K-rows = 1024 B
-    uint64_t hi = 0;
-    hi |= (uint64_t)(WG_BOX_BYTES >> 4) << 16;
-    hi |= (uint64_t)(1024u >> 4) << 32;
-    hi |= (uint64_t)1 << 46;
-    hi |= (uint64_t)2 << 61;
+    // MN-major SW128 descriptors: LBO = distance between 64-element MN blocks (one box), SBO = 8 K-rows = 1024 B
+    uint64_t hi_a = 0, hi_b = 0;
+    hi_a |= (uint64_t)(WG_A_BOX >> 4) << 16;
+    hi_b |= (uint64_t)(WG_B_BOX >> 4) << 16;
+    hi_a |= (uint64_t)(1024u >> 4) << 32;
+    hi_b |= (uint64_t)(1024u >> 4) << 32;
+    hi_a |= ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    hi_b |= ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
     uint32_t stage = 0, phase = 0;
     for (int kb = 0; kb < num_kb; ++kb) {
       mbar_wait(full0 + 8u * stage, phase);
@@ -114,10 +121,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
       if (elect_one()) {
         const uint32_t a_lo = ((smem_base + stage * p.stage_bytes) & 0x3FFFFu) >> 4;
         const uint32_t b_lo = a_lo + (a_bytes >> 4);
+        for (int tx = 0; tx < p.ksize; ++tx) {
 #pragma unroll
-        for (int ks = 0; ks < WG_KP / 16; ++ks) {
-          // 16 pixels = two 8-row groups = 2048 bytes further down the box
-          umma_bf16(tmem_base, hi | (uint64_t)(a_lo + ks * 128u), hi | (uint64_t)(b_lo + ks * 128u), idesc, (kb | ks) ? 1u : 0u);
+          for (int ks = 0; ks < WG_KP / 16; ++ks) {
+            // 16 pixels = two 8-row groups = 2048 bytes further down the box; tap tx starts tx pixel rows (128 B) in
+            umma_bf16(tmem_base + (uint32_t)(tx * p.bn), hi_a | (uint64_t)(a_lo + ks * 128u),
+                      hi_b | (uint64_t)(b_lo + ks * 128u + tx * 8u), idesc, (kb | ks) ? 1u : 0u);
+          }
         }
         umma_commit(empty0 + 8u * stage);
         if (kb == num_kb - 1) umma_commit(done);
@@ -131,15 +141,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     mbar_wait(done, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    float* out = p.dw + (int64_t)co * p.dw_ld + tap * p.cin + ci0;
-    for (int c0 = 0; c0 < p.bn; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16(taddr + (uint32_t)c0, r);
-      tmem_ld_wait();
-      if (co < p.cout) {
+    for (int tx = 0; tx < p.ksize; ++tx) {
+      float* out = p.dw + (long long)co * p.s_co + (long long)(ty * p.ksize + tx) * p.s_tap;
+      for (int c0 = 0; c0 < p.bn; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)(tx * p.bn + c0), r);
+        tmem_ld_wait();
+        if (co < p.cout_valid) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (ci0 + c0 + j < p.cin) atomicAdd(out + c0 + j, __uint_as_float(r[j]));
+          for (int j = 0; j < 16; ++j)
+            if (ci0 + c0 + j < p.cin_valid) atomicAdd(out + (long long)(ci0 + c0 + j) * p.s_ci, __uint_as_float(r[j]));
+        }
       }
     }
   }
@@ -148,12 +160,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
 }
 
 // per-channel sum over pixels (bias gradient): x [pixels][c] bf16 -> out[c] += sum
-__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int64_t pixels, int c) {
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int64_t pixels, int c,
+                                                    int c_valid) {
   // thread t owns channel (t % c) of pixel rows t / c, t / c + rows_per_iter, ...
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t total_threads = (int64_t)gridDim.x * blockDim.x;
@@ -162,7 +175,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
   const int ch = (int)(t % c);
   float acc = 0.f;
   for (int64_t r = t / c; r < pixels; r += lanes / c) acc += __bfloat162float(x[r * c + ch]);
-  atomicAdd(out + ch, acc);
+  if (ch < c_valid) atomicAdd(out + ch, acc);
 }
 
 int tc_encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
@@ -173,36 +186,42 @@ static bool g_wg_attr[64] = {false};
 
 }  // namespace rv
 
-extern "C" int rv_conv2d_wgrad(const void* x, const void* dy, float* dw, float* dbias, int n, int h, int w, int cin, int cout,
-                               int ksize, int pad, void* stream) {
+extern "C" int rv_conv2d_wgrad(const void* x, const void* dy, float* dw, int64_t dw_co_stride, int64_t dw_ci_stride,
+                               int64_t dw_tap_stride, float* dbias, int n, int h, int w, int cin, int cout, int cin_valid,
+                               int cout_valid, int ksize, int pad, void* stream) {
   using namespace rv;
   if (int rc = tc_ensure_init()) return rc;
   RV_CHECK_ARG(x && dy && dw && n > 0 && h > 0 && w > 0, "conv2d_wgrad: bad argument");
   RV_CHECK_ARG(ksize == 1 || ksize == 3, "conv2d_wgrad: ksize must be 1 or 3");
   RV_CHECK_ARG(cin % 16 == 0 && cout % 8 == 0, "conv2d_wgrad: cin %% 16 and cout %% 8 must be 0 (got %d, %d)", cin, cout);
+  RV_CHECK_ARG(cin_valid > 0 && cin_valid <= cin && cout_valid > 0 && cout_valid <= cout, "conv2d_wgrad: bad valid channel counts");
   RV_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0), "conv2d_wgrad: tensors must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   WgParams p;
   memset(&p, 0, sizeof(p));
   p.n_img = n; p.h = h; p.w = w; p.cin = cin; p.cout = cout; p.ksize = ksize; p.pad = pad;
+  p.cin_valid = cin_valid; p.cout_valid = cout_valid;
   p.co_tiles = (cout + 127) / 128;
   const int c16 = (cin + 15) / 16 * 16;
-  p.ci_tiles = (c16 + 255) / 256;
+  const int bn_max = 128;  // ksize accumulators of bn columns share the 512 TMEM columns
+  p.ci_tiles = (c16 + bn_max - 1) / bn_max;
   p.bn = ((c16 + p.ci_tiles - 1) / p.ci_tiles + 15) / 16 * 16;
   p.nboxes_b = (p.bn + 63) / 64;
   p.x_blocks = (w + WG_KP - 1) / WG_KP;
-  const int taps = ksize * ksize;
-  const int tiles = taps * p.co_tiles * p.ci_tiles;
+  p.tmem_cols = 32;
+  while ((int)p.tmem_cols < ksize * p.bn) p.tmem_cols <<= 1;
+  const int tiles = ksize * p.co_tiles * p.ci_tiles;
   const int total_rows = n * h;
-  int splits = (num_sms() * 2 + tiles - 1) / tiles;
+  int splits = (num_sms() * 2) / tiles;
   if (splits > total_rows) splits = total_rows;
   if (splits < 1) splits = 1;
   p.rows_per_split = (total_rows + splits - 1) / splits;
   p.splits = (total_rows + p.rows_per_split - 1) / p.rows_per_split;
   p.dw = dw;
-  p.dw_ld = taps * cin;
-  p.tx_bytes = (2u + (uint32_t)p.nboxes_b) * WG_BOX_BYTES;
-  p.stage_bytes = p.tx_bytes;
+  p.s_co = dw_co_stride; p.s_ci = dw_ci_stride; p.s_tap = dw_tap_stride;
+  const uint32_t b_rows = (uint32_t)(WG_KP + ksize - 1);
+  p.tx_bytes = 2u * WG_A_BOX + (uint32_t)p.nboxes_b * b_rows * 128u;
+  p.stage_bytes = 2u * WG_A_BOX + (uint32_t)p.nboxes_b * WG_B_BOX;
   p.stages = (int)((200u * 1024u) / p.stage_bytes);
   if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
   CUtensorMap mdy, mx;
@@ -215,7 +234,7 @@ extern "C" int rv_conv2d_wgrad(const void* x, const void* dy, float* dw, float* 
   {
     cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
     cuuint64_t str[3] = {(cuuint64_t)cin * 2u, (cuuint64_t)cin * 2u * w, (cuuint64_t)cin * 2u * w * h};
-    cuuint32_t box[4] = {64, (cuuint32_t)WG_KP, 1, 1};
+    cuuint32_t box[4] = {64, b_rows, 1, 1};
     if (int rc = tc_encode_map(&mx, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   }
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
@@ -229,7 +248,7 @@ extern "C" int rv_conv2d_wgrad(const void* x, const void* dy, float* dw, float* 
     }
   }
   {
-    LaunchScope scope(CAT_CONV_TC, st, 2.0 * (double)n * h * w * cout * cin * taps);
+    LaunchScope scope(CAT_CONV_TC, st, 2.0 * (double)n * h * w * cout * cin * ksize * ksize);
     conv_wgrad_kernel<<<tiles * p.splits, WG_THREADS, smem, st>>>(mdy, mx, p);
     RV_LAUNCH_CHECK();
   }
@@ -240,7 +259,7 @@ extern "C" int rv_conv2d_wgrad(const void* x, const void* dy, float* dw, float* 
     if (blocks > num_sms() * 8) blocks = num_sms() * 8;
     if (blocks < 1) blocks = 1;
     while (blocks * 256 < cout) ++blocks;
-    colsum_kernel<<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, dbias, pixels, cout);
+    colsum_kernel<<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, dbias, pixels, cout, cout_valid);
     RV_LAUNCH_CHECK();
   }
   return 0;

@@ -75,54 +75,103 @@ __global__ void __launch_bounds__(256) reparam_bwd_kernel(const T* __restrict__ 
 }
 
 // Backward of y = act(x * r * g), r = 1/max(||x||_2, 1e-12), g = gamma*sqrt(C), act = SiLU or identity.
-// One warp walks pixels; a lane owns fixed channels (lane + 32*k), so dgamma accumulates in registers and is
-// flushed with one atomicAdd per (warp, channel) at the end.  dgamma_scaled receives d loss / d g (= d gamma / sqrt(C)).
-template <typename T, int CPL>  // CPL = channels per lane = C / 32
+// Same work split as the forward warp kernel: a pixel's channels lie on L lanes (L = C / (3 * 16-byte chunk)), three
+// 16-byte chunks per lane, so both per-pixel reductions are xor-shuffles.  A lane owns fixed channels, so dgamma
+// accumulates in registers across pixels; it is reduced over the warp's pixel groups by shuffles, over the block's warps
+// through shared memory, and leaves the block as ONE atomicAdd per channel, already scaled to d loss / d gamma.
+template <typename T, bool SILU>
 __global__ void __launch_bounds__(256) rmsnorm_silu_bwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma_scaled,
                                                               const T* __restrict__ dy, T* __restrict__ dx,
-                                                              float* __restrict__ dgamma_scaled, int64_t pixels, int silu_on) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
-  constexpr int C = CPL * 32;
-  float g[CPL], dg[CPL];
+                                                              float* __restrict__ dgamma, int64_t pixels, int lanes_per_pixel,
+                                                              float dgamma_scale) {
+  using V = Vec16<T>;
+  constexpr int CPL = 3;
+  extern __shared__ float sdg[];  // [8 warps][C]
+  const int L = lanes_per_pixel;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int sub = lane & (L - 1), grp = lane / L, ppw = 32 / L;
+  const int c = L * CPL * V::N;
+  float g[CPL][V::N], dg[CPL][V::N];
 #pragma unroll
-  for (int k = 0; k < CPL; ++k) {
-    g[k] = gamma_scaled[lane + 32 * k];
-    dg[k] = 0.f;
-  }
-  for (int64_t p = warp_global; p < pixels; p += warps_total) {
-    float xv[CPL], du[CPL];
-    float ss = 0.f;
+  for (int k = 0; k < CPL; ++k)
+#pragma unroll
+    for (int j = 0; j < V::N; ++j) {
+      g[k][j] = gamma_scaled[(k * L + sub) * V::N + j];
+      dg[k][j] = 0.f;
+    }
+  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t p0 = warp_global * ppw; p0 < pixels; p0 += warps_total * ppw) {
+    const int64_t pix = p0 + grp;
+    const bool ok = pix < pixels;
+    V xv[CPL], dv[CPL];
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
-      xv[k] = ldf(x + p * C + lane + 32 * k);
-      ss = fmaf(xv[k], xv[k], ss);
+      if (ok) {
+        xv[k].load(x + pix * c + (int64_t)(k * L + sub) * V::N);
+        dv[k].load(dy + pix * c + (int64_t)(k * L + sub) * V::N);
+      } else {
+        xv[k].zero();
+        dv[k].zero();
+      }
     }
-    ss = warp_sum(ss);
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k)
+#pragma unroll
+      for (int j = 0; j < V::N; ++j) {
+        const float f = xv[k].get(j);
+        ss = fmaf(f, f, ss);
+      }
+    for (int o = 1; o < L; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float nrm = sqrtf(ss);
     const bool clamped = nrm < 1e-12f;
     const float r = 1.0f / fmaxf(nrm, 1e-12f);
+    float du[CPL][V::N];
     float dot = 0.f;
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) {
-      const float u = xv[k] * r * g[k];
-      float d = ldf(dy + p * C + lane + 32 * k);
-      if (silu_on) {
-        const float s = 1.0f / (1.0f + expf(-u));
-        d *= s * (1.0f + u * (1.0f - s));
+    for (int k = 0; k < CPL; ++k)
+#pragma unroll
+      for (int j = 0; j < V::N; ++j) {
+        const float xr = xv[k].get(j) * r;
+        float d = dv[k].get(j);
+        if (SILU) {
+          const float u = xr * g[k][j];
+          const float sg = __fdividef(1.0f, 1.0f + __expf(-u));
+          d *= sg * (1.0f + u * (1.0f - sg));
+        }
+        du[k][j] = d;
+        dg[k][j] = fmaf(xr, d, dg[k][j]);
+        dot = fmaf(xv[k].get(j) * g[k][j], d, dot);
       }
-      du[k] = d;
-      dg[k] = fmaf(xv[k] * r, d, dg[k]);
-      dot = fmaf(xv[k] * g[k], d, dot);
-    }
-    dot = warp_sum(dot);
+    for (int o = 1; o < L; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
     const float corr = clamped ? 0.f : dot * r * r * r;
+    if (ok) {
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) stf(dx + p * C + lane + 32 * k, r * g[k] * du[k] - xv[k] * corr);
+      for (int k = 0; k < CPL; ++k) {
+        V o;
+#pragma unroll
+        for (int j = 0; j < V::N; ++j) o.set(j, r * g[k][j] * du[k][j] - xv[k].get(j) * corr);
+        o.store(dx + pix * c + (int64_t)(k * L + sub) * V::N);
+      }
+    }
   }
+  // warp: sum over the pixel groups (lanes with equal `sub`), then block, then one atomic per channel
 #pragma unroll
-  for (int k = 0; k < CPL; ++k) atomicAdd(dgamma_scaled + lane + 32 * k, dg[k]);
+  for (int k = 0; k < CPL; ++k)
+#pragma unroll
+    for (int j = 0; j < V::N; ++j) {
+      float v = dg[k][j];
+      for (int o = L; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (grp == 0) sdg[wib * c + (k * L + sub) * V::N + j] = v;
+    }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += 256) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += sdg[i * c + ch];
+    atomicAdd(dgamma + ch, acc * dgamma_scale);
+  }
 }
 
 __global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
@@ -242,6 +291,19 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* _
   }
 }
 
+// dgrad weights straight from the parameter: out[ci][tap'][co] = W[co][ci][taps-1-tap'], zero for co >= cout
+__global__ void __launch_bounds__(256) pack_dgrad_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout,
+                                                        int cin, int cout_pad, int taps, int64_t s_co, int64_t s_ci) {
+  const int64_t total = (int64_t)cin * taps * cout_pad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % cout_pad);
+    int64_t r = i / cout_pad;
+    const int tap = (int)(r % taps);
+    const int ci = (int)(r / taps);
+    out[i] = co < cout ? w[co * s_co + ci * s_ci + (taps - 1 - tap)] : __float2bfloat16_rn(0.f);
+  }
+}
+
 static inline dim3 train_grid(int64_t items, int n) {
   unsigned bx = (unsigned)((items + 255) / 256);
   if (bx > 2048) bx = 2048;
@@ -297,30 +359,48 @@ int rv_reparam_bwd(const void* moments, const void* noise, const void* dz, void*
   return 0;
 }
 
-int rv_rmsnorm_silu_bwd(const void* x, const float* gamma_scaled, const void* dy, void* dx, float* dgamma_scaled, int64_t pixels,
-                        int c, int dtype, int apply_silu, void* stream) {
-  RV_CHECK_ARG(x && gamma_scaled && dy && dx && dgamma_scaled && pixels > 0, "rmsnorm_silu_bwd: bad argument");
-  RV_CHECK_ARG(c == 96 || c == 192 || c == 384, "rmsnorm_silu_bwd: channels must be 96, 192 or 384 (got %d)", c);
+int rv_rmsnorm_silu_bwd(const void* x, const float* gamma_scaled, const void* dy, void* dx, float* dgamma, float dgamma_scale,
+                        int64_t pixels, int c, int dtype, int apply_silu, void* stream) {
+  RV_CHECK_ARG(x && gamma_scaled && dy && dx && dgamma && pixels > 0, "rmsnorm_silu_bwd: bad argument");
+  RV_CHECK_ARG(dtype == RV_F32 || dtype == RV_BF16, "rmsnorm_silu_bwd: bad dtype %d", dtype);
+  const int per_chunk = dtype == RV_F32 ? 4 : 8;
+  const int lanes = c / (3 * per_chunk);
+  RV_CHECK_ARG(c % (3 * per_chunk) == 0 && lanes >= 1 && lanes <= 32 && (lanes & (lanes - 1)) == 0,
+               "rmsnorm_silu_bwd: channels must be 3 * 2^k 16-byte chunks (96, 192, 384 ...), got %d", c);
+  RV_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)dx % 16 == 0), "rmsnorm_silu_bwd: unaligned tensor");
   cudaStream_t st = (cudaStream_t)stream;
-  int64_t blocks = (pixels + 63) / 64;
-  const int64_t cap = (int64_t)rv::num_sms() * 16;
+  const int ppw = 32 / lanes;
+  int64_t blocks = (pixels + 8 * ppw * 4 - 1) / (8 * ppw * 4);
+  const int64_t cap = (int64_t)rv::num_sms() * 8;
   if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  const size_t smem = 8 * (size_t)c * sizeof(float);
   rv::LaunchScope scope(rv::CAT_NORM, st, 3.0 * pixels * c * (dtype == RV_F32 ? 4 : 2));
-#define RV_NB(T, CPL)                                                                                                     \
-  rv::rmsnorm_silu_bwd_kernel<T, CPL><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, gamma_scaled, (const T*)dy, (T*)dx, \
-                                                                        dgamma_scaled, pixels, apply_silu)
+#define RV_NB(T, S) \
+  rv::rmsnorm_silu_bwd_kernel<T, S><<<(unsigned)blocks, 256, smem, st>>>((const T*)x, gamma_scaled, (const T*)dy, (T*)dx, dgamma, pixels, lanes, dgamma_scale)
   if (dtype == RV_F32) {
-    if (c == 96) RV_NB(float, 3);
-    else if (c == 192) RV_NB(float, 6);
-    else RV_NB(float, 12);
-  } else if (dtype == RV_BF16) {
-    if (c == 96) RV_NB(__nv_bfloat16, 3);
-    else if (c == 192) RV_NB(__nv_bfloat16, 6);
-    else RV_NB(__nv_bfloat16, 12);
+    if (apply_silu) RV_NB(float, true);
+    else RV_NB(float, false);
   } else {
-    RV_CHECK_ARG(false, "rmsnorm_silu_bwd: bad dtype %d", dtype);
+    if (apply_silu) RV_NB(__nv_bfloat16, true);
+    else RV_NB(__nv_bfloat16, false);
   }
 #undef RV_NB
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+int rv_pack_dgrad_weights(const void* w, int64_t w_co_stride, int64_t w_ci_stride, void* out, int cout, int cin, int cout_pad,
+                          int ksize, void* stream) {
+  RV_CHECK_ARG(w && out && cout > 0 && cin > 0 && cout_pad >= cout && (ksize == 1 || ksize == 3), "pack_dgrad_weights: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int taps = ksize * ksize;
+  const int64_t total = (int64_t)cin * taps * cout_pad;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > rv::num_sms() * 8) blocks = rv::num_sms() * 8;
+  rv::LaunchScope scope(rv::CAT_LAYOUT, st, 4.0 * total);
+  rv::pack_dgrad_kernel<<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)w, (__nv_bfloat16*)out, cout, cin, cout_pad, taps,
+                                                         w_co_stride, w_ci_stride);
   RV_LAUNCH_CHECK();
   return 0;
 }

@@ -60,13 +60,10 @@ class VaeTrainStep:
         self._saved_fuse = None
 
     # ---- small helpers ---------------------------------------------------------------------
-    def _acc(self, p: torch.nn.Parameter, g: torch.Tensor) -> None:
-        """gradient of one parameter into the flat fp32 buffer (5-D causal kernels: only the last temporal tap is live)."""
-        v = self._gview[id(p)]
-        if v.dim() == 5:
-            v[:, :, -1].add_(g.view(v.shape[0], v.shape[1], v.shape[3], v.shape[4]))
-        else:
-            v.add_(g.view(v.shape))
+    def _gw(self, conv) -> torch.Tensor:
+        """fp32 gradient view of a conv weight as [cout][cin][k][k] (5-D causal kernels: only the last temporal tap is live)."""
+        v = self._gview[id(conv.weight)]
+        return v[:, :, -1] if v.dim() == 5 else v
 
     def _conv(self, x, conv, **kw):
         return self.vae._conv(x, conv, **kw)
@@ -75,29 +72,27 @@ class VaeTrainStep:
         return self.vae._norm(x, norm, silu)
 
     def _norm_bwd(self, norm, x, dy, silu=True):
-        dx, dg = T.rmsnorm_silu_backward(x, norm.gamma, dy, silu)
-        self._acc(norm.gamma, dg)
+        dx, _ = T.rmsnorm_silu_backward(x, norm.gamma, dy, silu, dgamma_out=self._gview[id(norm.gamma)].view(-1))
         return dx
 
     def _conv_bwd(self, conv, x, dy, *, mode: str = "same", need_dx: bool = True):
         """x: the conv's NHWC bf16 input (channel-padded for the stems); dy: NHWC bf16 gradient of its output, channel
-        count possibly padded above conv.out_channels with zeros.  Accumulates dW / dbias, returns dX (or None)."""
-        w2d = conv.weight2d()
-        cout, cin, k = conv.out_channels, conv.in_channels, conv.k
+        count possibly padded above conv.out_channels with zeros.  dW / dbias accumulate straight into the flat gradient
+        buffer (in the parameter's own layout); returns dX (or None)."""
+        k = conv.k
+        gw, gb = self._gw(conv), self._gview[id(conv.bias)]
         if mode == "down":
             dyg = T.resample2x(dy, "zero_insert")
-            dw, db = T.conv_wgrad(x, dyg, k, pad=0)
+            T.conv_wgrad(x, dyg, k, pad=0, dw_out=gw, dbias_out=gb)
         elif mode == "up":
             dyg = dy
-            dw, db = T.conv_wgrad(T.resample2x(x, "nearest"), dy, k)
+            T.conv_wgrad(T.resample2x(x, "nearest"), dy, k, dw_out=gw, dbias_out=gb)
         else:
             dyg = dy
-            dw, db = T.conv_wgrad(x, dy, k)
-        self._acc(conv.weight, dw[:cout, :cin].contiguous())
-        self._acc(conv.bias, db[:cout])
+            T.conv_wgrad(x, dy, k, dw_out=gw, dbias_out=gb)
         if not need_dx:
             return None
-        dx = T.conv_dgrad(dyg, w2d, pad_lo=2 if mode == "down" else None)
+        dx = T.conv_dgrad(dyg, conv.weight2d(), pad_lo=2 if mode == "down" else None)
         if mode == "up":
             dx = T.resample2x(dx, "sum_pool")
         return dx
@@ -184,9 +179,8 @@ class VaeTrainStep:
         as_img = lambda a, ch: a.view(1, 1, a.shape[0], ch)  # [rows][ch] as a one-row NHWC image
         dout2 = dout.view(n * t, c)
         # proj: out = o Wo^T + bo + x
-        dwo, dbo = T.conv_wgrad(as_img(o, c), as_img(dout2, c), 1)
-        self._acc(attn.proj.weight, dwo)
-        self._acc(attn.proj.bias, dbo)
+        T.conv_wgrad(as_img(o, c), as_img(dout2, c), 1, dw_out=self._gview[id(attn.proj.weight)],
+                     dbias_out=self._gview[id(attn.proj.bias)])
         d_o = T.conv_dgrad(as_img(dout2, c), attn.proj.weight.detach().reshape(c, c, 1, 1)).view(n * t, c)
         dqkv = torch.empty((n * t, 3 * c), dtype=torch.bfloat16, device=dev)
         q_chunk = self._q_chunk(t)
@@ -194,7 +188,6 @@ class VaeTrainStep:
         dp = torch.empty((q_chunk, t), dtype=torch.float32, device=dev)
         ds = torch.empty((q_chunk, t), dtype=torch.bfloat16, device=dev)
         ds_t = torch.empty((t, t), dtype=torch.bfloat16, device=dev)
-        lib_check = T.check
         from . import _lib
         for i in range(n):
             sl = slice(i * t, (i + 1) * t)
@@ -208,29 +201,21 @@ class VaeTrainStep:
                 p = ops.softmax_rows(s[:rows], torch.bfloat16)
                 # dP = dO V^T
                 self._gemm(d_o[rs], v[sl], rows=rows, k=c, cols=t, x_ld=c, w_ld=c, y=dp[:rows], y_ld=t)
-                lib_check(_lib.load().rv_softmax_bwd(ops._ptr(p), ops._ptr(dp), ops._ptr(ds), ops._ptr(ds_t), rows, t, t, r0, scale,
+                T.check(_lib.load().rv_softmax_bwd(ops._ptr(p), ops._ptr(dp), ops._ptr(ds), ops._ptr(ds_t), rows, t, t, r0, scale,
                                                      ops._stream(p)), "rv_softmax_bwd")
                 # dV += P^T dO ; dK += dS^T Q   (reduction over this block's query rows)
-                self._wgrad_into(dv, x=d_o[rs], dy=p, rows=rows, cin=c, cout=t)
-                self._wgrad_into(dk, x=q[rs], dy=ds[:rows], rows=rows, cin=c, cout=t)
+                T.gemm_tn_accumulate(dv, p, d_o[rs])
+                T.gemm_tn_accumulate(dk, ds[:rows], q[rs])
             # dQ = dS K  (reduction over keys: dS^T is the "dy" operand)
-            self._wgrad_into(dq, x=k[sl], dy=ds_t, rows=t, cin=c, cout=t)
+            T.gemm_tn_accumulate(dq, ds_t, k[sl])
             dqkv[sl, :c] = dq
             dqkv[sl, c:2 * c] = dk
             dqkv[sl, 2 * c:] = dv
-        dwqkv, dbqkv = T.conv_wgrad(as_img(xn.view(n * t, c), c), as_img(dqkv, 3 * c), 1)
-        self._acc(attn.to_qkv.weight, dwqkv)
-        self._acc(attn.to_qkv.bias, dbqkv)
+        T.conv_wgrad(as_img(xn.view(n * t, c), c), as_img(dqkv, 3 * c), 1, dw_out=self._gview[id(attn.to_qkv.weight)],
+                     dbias_out=self._gview[id(attn.to_qkv.bias)])
         dxn = T.conv_dgrad(as_img(dqkv, 3 * c), attn.to_qkv.weight.detach().reshape(3 * c, c, 1, 1)).view(x.shape)
         dx = self._norm_bwd(attn.norm, x, dxn, silu=False)
         return T.add_(dx, dout)
-
-    @staticmethod
-    def _wgrad_into(dst: torch.Tensor, *, x: torch.Tensor, dy: torch.Tensor, rows: int, cin: int, cout: int) -> None:
-        """dst[cout][cin] (fp32) += dy[rows][cout]^T . x[rows][cin]"""
-        from . import _lib
-        T.check(_lib.load().rv_conv2d_wgrad(ops._ptr(x), ops._ptr(dy), ops._ptr(dst), None, 1, 1, rows, cin, cout, 1, 0,
-                                            ops._stream(x)), "rv_conv2d_wgrad")
 
     # ---- encoder / decoder -----------------------------------------------------------------
     def _run_fwd(self, x, items, tape):

@@ -58,26 +58,33 @@ def reparam_backward(moments: torch.Tensor, noise: Optional[torch.Tensor], dz: O
     return out
 
 
-def rmsnorm_silu_backward(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, silu: bool = True):
-    """Backward of ops.rmsnorm_silu: returns (dx, dgamma) with dgamma shaped like ``gamma`` (fp32)."""
+def rmsnorm_silu_backward(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, silu: bool = True,
+                          dgamma_out: Optional[torch.Tensor] = None):
+    """Backward of ops.rmsnorm_silu: returns (dx, dgamma) with dgamma shaped like ``gamma`` (fp32).  ``dgamma_out``: a
+    contiguous fp32 buffer of C elements (e.g. a view of the flat gradient) the gradient is ACCUMULATED into."""
     _need_cuda(x, gamma, dy)
     c = x.shape[-1]
     x, dy = x.contiguous(), dy.to(x.dtype).contiguous()
     g_scaled = (gamma.detach().to(torch.float32).reshape(-1) * math.sqrt(c)).contiguous()
     dx = torch.empty_like(x)
-    dg = torch.zeros(c, dtype=torch.float32, device=x.device)
-    check(_lib.load().rv_rmsnorm_silu_bwd(_ptr(x), _ptr(g_scaled), _ptr(dy), _ptr(dx), _ptr(dg), x.numel() // c, c, _dt(x),
-                                          int(silu), _stream(x)), "rv_rmsnorm_silu_bwd")
-    return dx, (dg * math.sqrt(c)).reshape(gamma.shape)
+    dg = torch.zeros(c, dtype=torch.float32, device=x.device) if dgamma_out is None else dgamma_out
+    check(_lib.load().rv_rmsnorm_silu_bwd(_ptr(x), _ptr(g_scaled), _ptr(dy), _ptr(dx), _ptr(dg), math.sqrt(c), x.numel() // c, c,
+                                          _dt(x), int(silu), _stream(x)), "rv_rmsnorm_silu_bwd")
+    return dx, dg.reshape(gamma.shape)
 
 
 def conv_dgrad_weights(weight2d: torch.Tensor, cout_pad: int = 0) -> torch.Tensor:
-    """[cout][cin][k][k] -> packed bf16 weights of the convolution that maps dY to dX for a stride-1 'same' conv:
-    W'[cin][cout][k-1-dy][k-1-dx] = W[cout][cin][dy][dx]; ``cout_pad`` zero-pads the (now input) channel axis to dY's."""
-    wt = weight2d.detach().to(torch.float32).flip(2, 3).permute(1, 0, 2, 3)
-    if cout_pad and cout_pad > wt.shape[1]:
-        wt = torch.nn.functional.pad(wt, (0, 0, 0, 0, 0, cout_pad - wt.shape[1]))
-    return ops.pack_conv_weights_tc(wt.contiguous())
+    """[cout][cin][k][k] (any outer strides, e.g. the last temporal slice of a causal 3-D kernel) -> packed bf16 weights
+    of the convolution that maps dY to dX for a stride-1 conv: W'[cin][k-1-dy][k-1-dx][cout (zero padded)]."""
+    cout, cin, k = weight2d.shape[0], weight2d.shape[1], weight2d.shape[2]
+    w = weight2d.detach()
+    if w.dtype != torch.bfloat16 or w.stride(-1) != 1 or (k > 1 and w.stride(-2) != k):
+        w = w.to(torch.bfloat16).contiguous()
+    cp = max(cout, cout_pad)
+    out = torch.empty((cin, k * k * cp), dtype=torch.bfloat16, device=w.device)
+    check(_lib.load().rv_pack_dgrad_weights(_ptr(w), w.stride(0), w.stride(1), _ptr(out), cout, cin, cp, k, _stream(w)),
+          "rv_pack_dgrad_weights")
+    return out
 
 
 def conv_dgrad(dy: torch.Tensor, weight2d: torch.Tensor, pad_lo: Optional[int] = None) -> torch.Tensor:
@@ -96,18 +103,35 @@ def conv_dgrad(dy: torch.Tensor, weight2d: torch.Tensor, pad_lo: Optional[int] =
     return dx
 
 
-def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, want_bias: bool = True, pad: Optional[int] = None):
+def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, want_bias: bool = True, pad: Optional[int] = None,
+               dw_out: Optional[torch.Tensor] = None, dbias_out: Optional[torch.Tensor] = None):
     """(dW [cout][cin][k][k], dbias [cout]) in fp32 of a stride-1 'same' convolution from x and dY (NHWC bf16).
-    ``pad=0`` with a zero-inserted dY gives the gradient of the stride-2 (0,1,0,1)-padded conv."""
+    ``pad=0`` with a zero-inserted dY gives the gradient of the stride-2 (0,1,0,1)-padded conv.
+    ``dw_out`` / ``dbias_out``: fp32 views (e.g. of the flat gradient buffer; dw_out [cout'][cin'][k][k] with arbitrary
+    outer strides, cout' <= dY channels, cin' <= x channels) the gradients are ACCUMULATED into."""
     _need_cuda(x, dy)
     n, h, w, cin = x.shape
     cout = dy.shape[-1]
-    taps = ksize * ksize
-    dw = torch.zeros((cout, taps * cin), dtype=torch.float32, device=x.device)
-    db = torch.zeros(cout, dtype=torch.float32, device=x.device) if want_bias else None
-    check(_lib.load().rv_conv2d_wgrad(_ptr(x.contiguous()), _ptr(dy.contiguous()), _ptr(dw), _ptr(db), n, h, w, cin, cout, ksize,
+    if dw_out is None:
+        dw_out = torch.zeros((cout, cin, ksize, ksize), dtype=torch.float32, device=x.device)
+    if dbias_out is None and want_bias:
+        dbias_out = torch.zeros(dw_out.shape[0], dtype=torch.float32, device=x.device)
+    if dw_out.dtype != torch.float32 or dw_out.stride(-1) != 1 or (ksize > 1 and dw_out.stride(-2) != ksize):
+        raise ValueError("dw_out must be fp32 with dense [k][k] inner dimensions")
+    check(_lib.load().rv_conv2d_wgrad(_ptr(x.contiguous()), _ptr(dy.contiguous()), _ptr(dw_out), dw_out.stride(0), dw_out.stride(1), 1,
+                                      _ptr(dbias_out), n, h, w, cin, cout, dw_out.shape[1], dw_out.shape[0], ksize,
                                       ksize // 2 if pad is None else pad, _stream(x)), "rv_conv2d_wgrad")
-    return dw.view(cout, ksize, ksize, cin).permute(0, 3, 1, 2).contiguous(), db
+    return dw_out, dbias_out
+
+
+def gemm_tn_accumulate(dst: torch.Tensor, a: torch.Tensor, b: torch.Tensor) -> None:
+    """dst[m][n] (fp32, contiguous) += a[rows][m]^T . b[rows][n]  (bf16 row-major operands; the reduction runs over the
+    rows, which is the pixel axis of the weight-gradient kernel)."""
+    _need_cuda(dst, a, b)
+    rows, m = a.shape
+    nn_ = b.shape[1]
+    check(_lib.load().rv_conv2d_wgrad(_ptr(b), _ptr(a), _ptr(dst), nn_, 1, 0, None, 1, 1, rows, nn_, m, nn_, m, 1, 0, _stream(a)),
+          "rv_conv2d_wgrad")
 
 
 def resample2x(x: torch.Tensor, mode: str) -> torch.Tensor:
