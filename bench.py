@@ -415,21 +415,31 @@ def c4_arm(a):
     n_host = torch.randn(B, 16, S // 8, S // 8, generator=g).pin_memory()
     x, noise = x_host.to(dev), n_host.to(dev)
     warm = max(a.warmup, 3)
+    run = step.step if a.no_graph else step.step_graphed
     for _ in range(warm):
-        m = step.step(x, noise)
+        m = run(x, noise)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     l0 = ops.launch_count()
-    ops.prof_begin()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
-        m = step.step(x, noise)
+        m = run(x, noise)
     e1.record()
     torch.cuda.synchronize()
-    prof = ops.prof_end()
+    clocks = sampler.stop() if sampler else None
     launches = ops.launch_count() - l0
+    if not a.no_graph:  # replayed launches are not seen by the host-side counter: one capture's count x steps
+        launches = step.launches_per_replay * a.steps
+    # per-category CUDA events need eager launches: one more (eager) step outside the timed region
+    ops.prof_begin()
+    step.step(x, noise)
+    torch.cuda.synchronize()
+    prof = ops.prof_end()
     ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
     # end to end: host batch in, loss out
     if world > 1:
@@ -437,22 +447,38 @@ def c4_arm(a):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        m = step.step(x_host.to(dev, non_blocking=True), n_host.to(dev, non_blocking=True))
+        m = run(x_host.to(dev, non_blocking=True), n_host.to(dev, non_blocking=True))
         loss_host = float(m["train/loss"])
     torch.cuda.synchronize()
     ms_e2e = sharding.max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
+    in_sync = None
+    if world > 1:  # data-parallel replicas must hold identical weights after the same number of steps
+        chk = torch.stack([step.opt.master.double().sum(), step.opt.master.double().abs().sum()])
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        in_sync = all(bool(torch.equal(c, allc[0])) for c in allc)
     if rank == 0:
         mpix = world * B * S * S / 1e6
         kernels = {k: {"ms": round(v["ms"], 3), "launches": v["launches"]} for k, v in prof.items() if v["launches"]}
+        pk = peaks()
+        conv = prof["conv_tc"]
+        ach = conv["work"] / 1e12 / (conv["ms"] / 1e3) if conv["ms"] > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "every tcgen05 launch of one step: forward convs / GEMMs, data-gradient convs (conv_tc*, conv_halo) "
+                                             "and conv_wgrad_kernel",
+                "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
+                "peak_source": f"{pk['source']} bf16_tflops_sustained", "launches_per_step": conv["launches"],
+                "ms_per_step": conv["ms"], "algorithmic_tflop_per_step": conv["work"] / 1e12}
         line = {"metric": "rgba_vae_train_step_mpix_per_s", "value": mpix * a.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
                 "steps": a.steps, "warmup": warm, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"c4: rgba_vae training step, batch {B} x {S}x{S} per GPU, recon (reduce_mean) + 1e-6 KL, "
                                        "no LPIPS, bucketed NCCL gradient all-reduce, clip 1.0, AdamW",
-                           "arch": "qwen", "parallelism": f"data parallel x{world}"},
+                           "arch": "qwen", "parallelism": f"data parallel x{world}",
+                           "launch": "eager launches" if a.no_graph else "CUDA graph replay of the whole step (incl. all-reduce + AdamW)"},
                 "e2e": {"value": mpix * a.steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
                         "h2d_bytes_per_step": (x_host.numel() + n_host.numel()) * 4 * world, "d2h_bytes_per_step": 4 * world},
-                "gpu_launches": int(launches), "kernels": kernels, "loss": loss_host}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels, "loss": loss_host,
+                "replicas_in_sync": in_sync}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 11
+#define RV_ABI_VERSION 12
 #define RV_PROF_CATEGORIES 9
 
 int rv_abi_version(void);
@@ -231,10 +231,14 @@ int rv_softmax_bwd(const void* p, const float* dp, void* ds, void* ds_t, int64_t
 int rv_grad_sqnorm(const float* g, int64_t n, float* out, void* stream);
 /* torch.optim.AdamW step (rgba_vae_stage.py:321-331, 522) over flat fp32 buffers, fused with the gradient scaling
  * of a data-parallel SUM all-reduce (grad_scale = 1/world) and with clip_grad_norm_ (sqnorm = device pointer to the
- * squared norm of the UNscaled gradient, max_norm <= 0 disables).  p_bf16 (optional) receives the bf16 copy. */
+ * squared norm of the UNscaled gradient, max_norm <= 0 disables).  p_bf16 (optional) receives the bf16 copy.
+ * Bias corrections come from the host step count `step` (>= 1), or from `state` (see rv_adamw_advance) when non-NULL. */
 int rv_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
-                  float beta2, float eps, float weight_decay, int step, float grad_scale, const float* sqnorm,
-                  float max_norm, void* stream);
+                  float beta2, float eps, float weight_decay, int step, const float* state, float grad_scale,
+                  const float* sqnorm, float max_norm, void* stream);
+/* Device-resident step counter for CUDA-graph replay of the optimizer: state = [t, 1-beta1^t, 1-beta2^t] (fp32 [3],
+ * zero-initialised); call once per step ahead of rv_adamw_step(..., step = 0, state, ...). */
+int rv_adamw_advance(float* state, float beta1, float beta2, void* stream);
 
 #ifdef __cplusplus
 }

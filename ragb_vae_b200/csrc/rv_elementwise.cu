@@ -373,6 +373,29 @@ __global__ void nchw_to_nhwc_kernel(const TX* __restrict__ x, TY* __restrict__ y
   }
 }
 
+// Same, for pixel rows that are whole 16-byte chunks (the 16-channel padded stems): the per-channel plane reads stay
+// coalesced across the warp, the pixel's row leaves as 16-byte stores instead of c_pad scalar ones.
+template <typename TX, typename TY, int CHUNKS>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_vec_kernel(const TX* __restrict__ x, TY* __restrict__ y, int c, int64_t hw,
+                                                              float scale, float shift) {
+  using V = Vec16<TY>;
+  constexpr int CP = CHUNKS * V::N;
+  const int n = blockIdx.y;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hw; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[CP];
+#pragma unroll
+    for (int ch = 0; ch < CP; ++ch) v[ch] = ch < c ? ldf(x + ((int64_t)n * c + ch) * hw + i) * scale + shift : 0.f;
+    TY* o = y + ((int64_t)n * hw + i) * CP;
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) {
+      V out;
+#pragma unroll
+      for (int j = 0; j < V::N; ++j) out.set(j, v[k * V::N + j]);
+      out.store(o + k * V::N);
+    }
+  }
+}
+
 template <typename TX, typename TY>
 __global__ void nhwc_to_nchw_kernel(const TX* __restrict__ x, TY* __restrict__ y, int c, int64_t hw, int x_cstride) {
   const int n = blockIdx.y;
@@ -539,6 +562,23 @@ int rv_nchw_to_nhwc(const void* x, void* y, int n, int c, int64_t hw, int c_pad,
   dim3 grid(bx, n);
   rv::LaunchScope scope(rv::CAT_LAYOUT, st,
                         (double)n * hw * (c * (x_dtype == RV_F32 ? 4.0 : 2.0) + c_pad * (y_dtype == RV_F32 ? 4.0 : 2.0)));
+  if (y_dtype == RV_BF16 && (c_pad == 16 || c_pad == 32) && ((uintptr_t)y % 16 == 0)) {
+    // 16-byte stores (the channel-padded stems and the 32-channel moments)
+#define RV_VEC(TX, CH) \
+  rv::nchw_to_nhwc_vec_kernel<TX, __nv_bfloat16, CH><<<grid, 256, 0, st>>>((const TX*)x, (__nv_bfloat16*)y, c, hw, scale, shift)
+    if (x_dtype == RV_F32) {
+      if (c_pad == 16) RV_VEC(float, 2);
+      else RV_VEC(float, 4);
+    } else if (x_dtype == RV_BF16) {
+      if (c_pad == 16) RV_VEC(__nv_bfloat16, 2);
+      else RV_VEC(__nv_bfloat16, 4);
+    } else {
+      RV_CHECK_ARG(false, "nchw_to_nhwc: bad dtype");
+    }
+#undef RV_VEC
+    RV_LAUNCH_CHECK();
+    return 0;
+  }
   if (x_dtype == RV_F32 && y_dtype == RV_F32)
     rv::nchw_to_nhwc_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, c, hw, c_pad, scale, shift);
   else if (x_dtype == RV_F32 && y_dtype == RV_BF16)

@@ -188,12 +188,27 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g
   }
 }
 
+// device-resident step counter: state = [t, 1 - beta1^t, 1 - beta2^t]; one launch per optimizer step, ahead of adamw_kernel
+__global__ void adamw_advance_kernel(float* __restrict__ state, float beta1, float beta2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const float t = state[0] + 1.0f;
+    state[0] = t;
+    state[1] = 1.0f - powf(beta1, t);
+    state[2] = 1.0f - powf(beta2, t);
+  }
+}
+
 // torch.optim.AdamW semantics (decoupled weight decay, bias correction), gradients scaled by
 // min(1, max_norm / (sqrt(*sqnorm) + 1e-6)) (clip_grad_norm_) and by grad_scale (1/world for an all-reduce SUM).
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, __nv_bfloat16* __restrict__ p_bf16, int64_t n, float lr,
                                                    float beta1, float beta2, float eps, float wd, float bc1, float bc2,
-                                                   float grad_scale, const float* __restrict__ sqnorm, float max_norm) {
+                                                   float grad_scale, const float* __restrict__ sqnorm, float max_norm,
+                                                   const float* __restrict__ bc_dev) {
+  if (bc_dev != nullptr) {  // step counter kept on the device (CUDA-graph replay): state = [t, 1-b1^t, 1-b2^t]
+    bc1 = bc_dev[1];
+    bc2 = bc_dev[2];
+  }
   float clip = 1.0f;
   if (sqnorm != nullptr && max_norm > 0.f) {
     const float nrm = sqrtf(*sqnorm) * grad_scale;
@@ -452,16 +467,26 @@ int rv_grad_sqnorm(const float* g, int64_t n, float* out, void* stream) {
   return 0;
 }
 
-int rv_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1, float beta2,
-                  float eps, float weight_decay, int step, float grad_scale, const float* sqnorm, float max_norm, void* stream) {
-  RV_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "adamw_step: bad argument");
+int rv_adamw_advance(float* state, float beta1, float beta2, void* stream) {
+  RV_CHECK_ARG(state != nullptr, "adamw_advance: null state");
   cudaStream_t st = (cudaStream_t)stream;
-  const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+  rv::LaunchScope scope(rv::CAT_LAYOUT, st, 12.0);
+  rv::adamw_advance_kernel<<<1, 32, 0, st>>>(state, beta1, beta2);
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+int rv_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, const float* state, float grad_scale, const float* sqnorm,
+                  float max_norm, void* stream) {
+  RV_CHECK_ARG(p && g && m && v && n > 0 && (step >= 1 || state != nullptr), "adamw_step: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float bc1 = 1.0f - powf(beta1, (float)(step > 0 ? step : 1)), bc2 = 1.0f - powf(beta2, (float)(step > 0 ? step : 1));
   int64_t blocks = (n + 256 * 4 - 1) / (256 * 4);
   if (blocks > 4096) blocks = 4096;
   rv::LaunchScope scope(rv::CAT_LAYOUT, st, 28.0 * n);
   rv::adamw_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2,
-                                                     grad_scale, sqnorm, max_norm);
+                                                     grad_scale, sqnorm, max_norm, state);
   RV_LAUNCH_CHECK();
   return 0;
 }

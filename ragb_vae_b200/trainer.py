@@ -57,7 +57,8 @@ class VaeTrainStep:
                                max_grad_norm=max_grad_norm)
         self._gview: Dict[int, torch.Tensor] = {id(p): self.opt.grad_view(i) for i, (_, p) in enumerate(named)}
         self.reducer = T.GradientAllReducer(self.opt.grad, num_buckets=num_buckets, group=group)
-        self._saved_fuse = None
+        self._graphs: Dict[tuple, tuple] = {}
+        self.launches_per_replay = 0
 
     # ---- small helpers ---------------------------------------------------------------------
     def _gw(self, conv) -> torch.Tensor:
@@ -391,6 +392,37 @@ class VaeTrainStep:
         scale = self.reducer.wait()
         self.opt.step(grad_scale=scale)
         self.vae._pack_cache.clear()  # packed weights are stale after the in-place update
+        return metrics
+
+    # ---- CUDA-graph replay ------------------------------------------------------------------
+    def step_graphed(self, inputs: torch.Tensor, noise: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """``step`` captured once per input shape into ONE CUDA graph (forward, backward, the bucketed all-reduce, clip +
+        AdamW: ~1100 launches with no host work in between) and replayed.  ``noise`` must be supplied (the posterior's
+        eps); the returned loss terms are views of the graph's static outputs, valid until the next call."""
+        key = (tuple(inputs.shape), inputs.dtype, tuple(noise.shape), noise.dtype)
+        g = self._graphs.get(key)
+        if g is None:
+            sx, sn = inputs.clone(), noise.clone()
+            stream = torch.cuda.Stream()
+            stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(stream):
+                # warm-up outside the capture (TMA attributes, allocator pools, NCCL communicators) WITHOUT the update,
+                # so that the first replay below is the first optimizer step
+                self.forward_backward(sx, sn)
+                self.reducer.wait()
+            torch.cuda.current_stream().wait_stream(stream)
+            torch.cuda.synchronize()
+            self.vae._pack_cache.clear()  # the weight-packing kernels must be part of the graph (weights change every replay)
+            self._capturing_launches = ops.launch_count()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                metrics = self.step(sx, sn)
+            self.launches_per_replay = ops.launch_count() - self._capturing_launches
+            g = self._graphs[key] = (graph, sx, sn, metrics)
+        graph, sx, sn, metrics = g
+        sx.copy_(inputs, non_blocking=True)
+        sn.copy_(noise, non_blocking=True)
+        graph.replay()
         return metrics
 
     def named_grads(self) -> Dict[str, torch.Tensor]:

@@ -183,7 +183,18 @@ class FlatAdamW:
         self.m = torch.zeros_like(self.master)
         self.v = torch.zeros_like(self.master)
         self.sqnorm = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.t = 0
+        # [t, 1 - beta1^t, 1 - beta2^t] on the device: the step is replayable from a CUDA graph
+        self.state = torch.zeros(3, dtype=torch.float32, device=dev)
+
+    @property
+    def t(self) -> int:
+        return int(self.state[0].item())
+
+    def reset_state(self) -> None:
+        """Back to step 0 with zero moments (the master weights are kept)."""
+        self.state.zero_()
+        self.m.zero_()
+        self.v.zero_()
 
     def grad_view(self, i: int) -> torch.Tensor:
         return self.grad[self.offsets[i]:self.offsets[i + 1]].view(self.params[i].shape)
@@ -193,9 +204,9 @@ class FlatAdamW:
 
     def step(self, grad_scale: float = 1.0) -> None:
         """``grad_scale`` = 1/world_size after a SUM all-reduce."""
-        self.t += 1
         lib = _lib.load()
         st = _stream(self.master)
+        check(lib.rv_adamw_advance(_ptr(self.state), self.betas[0], self.betas[1], st), "rv_adamw_advance")
         sq = None
         mx = 0.0
         if self.max_grad_norm is not None and self.max_grad_norm > 0:
@@ -204,8 +215,8 @@ class FlatAdamW:
             sq, mx = _ptr(self.sqnorm), float(self.max_grad_norm)
         pb = None if self.model_flat is self.master else _ptr(self.model_flat)
         check(lib.rv_adamw_step(_ptr(self.master), _ptr(self.grad), _ptr(self.m), _ptr(self.v), pb, self.master.numel(),
-                                self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.t, grad_scale, sq, mx,
-                                st), "rv_adamw_step")
+                                self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, 0, _ptr(self.state), grad_scale,
+                                sq, mx, st), "rv_adamw_step")
 
 
 class GradientAllReducer:
