@@ -316,10 +316,8 @@ class VaeTrainStep:
         return self._conv(h, vae.decoder.conv_out, y_nchw=True, y_dtype=torch.float32, clamp=(-1.0, 1.0))
 
     # ---- the step --------------------------------------------------------------------------
-    def forward_backward(self, inputs: torch.Tensor, noise: Optional[torch.Tensor] = None, generator=None) -> Dict[str, torch.Tensor]:
-        """inputs: (B,4,H,W) in [0,1].  Fills the optimizer's flat gradient buffer; returns the step's loss terms."""
-        if not inputs.is_cuda:
-            raise RvError("VaeTrainStep runs on CUDA (sm_100a) only; there is no CPU path")
+    def _forward_and_decoder_backward(self, inputs: torch.Tensor, noise: torch.Tensor):
+        """Phase 1: everything up to (and including) the decoder's backward.  Returns (loss terms, context of phase 2)."""
         vae = self.vae
         fuse, vae.fuse_norm = vae.fuse_norm, False  # the tape needs the raw conv outputs
         try:
@@ -333,8 +331,6 @@ class VaeTrainStep:
                 vae._encode_moments(composed[B:])
                 vae.fuse_norm = False
             post = DiagonalGaussianDistribution(moments)
-            if noise is None:
-                noise = torch.randn(post.mean.shape, generator=generator, device=inputs.device, dtype=torch.float32)
             z = post.sample(noise=noise)
             dec_tape: list = []
             pred = self.decode(z, dec_tape)
@@ -354,15 +350,32 @@ class VaeTrainStep:
             dpred = T.recon_loss_backward(pred, target_vae, lm._eb, lm._eb2, lm.reduce_mean, lm.use_naive_mse, clamp=(-1.0, 1.0))
             dy = ops.nchw_to_nhwc(dpred, 16, torch.bfloat16)
             dzp = self._run_bwd(dec_tape, dy)  # NHWC [B,h,w,16]
-            self._mark_ready(decoder_done=True)
-            dz = ops.nhwc_to_nchw(dzp, 16, torch.float32)
-            dmom = T.reparam_backward(moments, noise, dz, kl_weight=kl_w)
-            dm = ops.nchw_to_nhwc(dmom, dmom.shape[1], torch.bfloat16)
-            self._run_bwd(enc_tape, dm)
-            self._mark_ready(decoder_done=False)
-            return metrics
+            return metrics, (enc_tape, moments, noise, dzp, kl_w)
         finally:
             vae.fuse_norm = fuse
+
+    def _encoder_backward(self, ctx) -> None:
+        """Phase 2: posterior sample / KL backward and the encoder's backward."""
+        enc_tape, moments, noise, dzp, kl_w = ctx
+        dz = ops.nhwc_to_nchw(dzp, 16, torch.float32)
+        dmom = T.reparam_backward(moments, noise, dz, kl_weight=kl_w)
+        dm = ops.nchw_to_nhwc(dmom, dmom.shape[1], torch.bfloat16)
+        self._run_bwd(enc_tape, dm)
+
+    def forward_backward(self, inputs: torch.Tensor, noise: Optional[torch.Tensor] = None, generator=None) -> Dict[str, torch.Tensor]:
+        """inputs: (B,4,H,W) in [0,1].  Fills the optimizer's flat gradient buffer (and starts the bucketed all-reduce of
+        the decoder's gradients while the encoder's backward still runs); returns the step's loss terms."""
+        if not inputs.is_cuda:
+            raise RvError("VaeTrainStep runs on CUDA (sm_100a) only; there is no CPU path")
+        if noise is None:
+            b, _, h, w = inputs.shape
+            noise = torch.randn((b, self.vae.config.z_dim, h // 8, w // 8), generator=generator, device=inputs.device,
+                                dtype=torch.float32)
+        metrics, ctx = self._forward_and_decoder_backward(inputs, noise)
+        self._mark_ready(decoder_done=True)
+        self._encoder_backward(ctx)
+        self._mark_ready(decoder_done=False)
+        return metrics
 
     def _mark_ready(self, decoder_done: bool) -> None:
         """Start the all-reduce of every bucket whose parameters all have their gradients (the decoder's parameters come
@@ -396,9 +409,11 @@ class VaeTrainStep:
 
     # ---- CUDA-graph replay ------------------------------------------------------------------
     def step_graphed(self, inputs: torch.Tensor, noise: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """``step`` captured once per input shape into ONE CUDA graph (forward, backward, the bucketed all-reduce, clip +
-        AdamW: ~1100 launches with no host work in between) and replayed.  ``noise`` must be supplied (the posterior's
-        eps); the returned loss terms are views of the graph's static outputs, valid until the next call."""
+        """``step`` as three CUDA graphs captured once per input shape and sharing one memory pool: (1) forward + decoder
+        backward, (2) encoder backward, (3) clip + AdamW -- ~1100 launches with no host work in between.  The bucketed
+        NCCL all-reduces are issued eagerly BETWEEN the replays (decoder buckets after graph 1, so they overlap graph 2 on
+        NCCL's stream).  ``noise`` must be supplied (the posterior's eps); the returned loss terms are views of graph 1's
+        static outputs, valid until the next call."""
         key = (tuple(inputs.shape), inputs.dtype, tuple(noise.shape), noise.dtype)
         g = self._graphs.get(key)
         if g is None:
@@ -412,17 +427,27 @@ class VaeTrainStep:
                 self.reducer.wait()
             torch.cuda.current_stream().wait_stream(stream)
             torch.cuda.synchronize()
-            self.vae._pack_cache.clear()  # the weight-packing kernels must be part of the graph (weights change every replay)
-            self._capturing_launches = ops.launch_count()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                metrics = self.step(sx, sn)
-            self.launches_per_replay = ops.launch_count() - self._capturing_launches
-            g = self._graphs[key] = (graph, sx, sn, metrics)
-        graph, sx, sn, metrics = g
+            self.vae._pack_cache.clear()  # the weight-packing kernels must be part of the graphs (weights change every replay)
+            l0 = ops.launch_count()
+            g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                metrics, ctx = self._forward_and_decoder_backward(sx, sn)
+            with torch.cuda.graph(g2, pool=g1.pool()):
+                self._encoder_backward(ctx)
+            with torch.cuda.graph(g3, pool=g1.pool()):
+                self.opt.step(grad_scale=1.0 / self.reducer.world())
+            self.vae._pack_cache.clear()
+            self.launches_per_replay = ops.launch_count() - l0
+            g = self._graphs[key] = (g1, g2, g3, sx, sn, metrics, ctx)
+        g1, g2, g3, sx, sn, metrics, _ = g
         sx.copy_(inputs, non_blocking=True)
         sn.copy_(noise, non_blocking=True)
-        graph.replay()
+        g1.replay()
+        self._mark_ready(decoder_done=True)
+        g2.replay()
+        self._mark_ready(decoder_done=False)
+        self.reducer.wait()
+        g3.replay()
         return metrics
 
     def named_grads(self) -> Dict[str, torch.Tensor]:
