@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 12
+#define RV_ABI_VERSION 13
 #define RV_PROF_CATEGORIES 9
 
 int rv_abi_version(void);
@@ -227,8 +227,11 @@ int rv_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream);
  * its transpose written into ds_t [cols][ld_t] at column offset row0.  p bf16 [rows][cols], dp fp32 [rows][cols]. */
 int rv_softmax_bwd(const void* p, const float* dp, void* ds, void* ds_t, int64_t rows, int64_t cols, int64_t ld_t,
                    int64_t row0, float scale, void* stream);
-/* *out += sum(g^2) over a flat fp32 gradient buffer (accelerator.clip_grad_norm_, rgba_vae_stage.py:520-521). */
-int rv_grad_sqnorm(const float* g, int64_t n, float* out, void* stream);
+/* *out += sum(g^2) over a flat fp32 gradient buffer (accelerator.clip_grad_norm_, rgba_vae_stage.py:520-521).
+ * Deterministic (fixed partition and summation order, fp64 partials in `scratch`, a device buffer of
+ * rv_grad_sqnorm_scratch_bytes() bytes): data-parallel replicas get bit-identical clip factors. */
+int rv_grad_sqnorm_scratch_bytes(void);
+int rv_grad_sqnorm(const float* g, int64_t n, float* out, void* scratch, void* stream);
 /* torch.optim.AdamW step (rgba_vae_stage.py:321-331, 522) over flat fp32 buffers, fused with the gradient scaling
  * of a data-parallel SUM all-reduce (grad_scale = 1/world) and with clip_grad_norm_ (sqnorm = device pointer to the
  * squared norm of the UNscaled gradient, max_norm <= 0 disables).  p_bf16 (optional) receives the bf16 copy.

@@ -9,7 +9,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "librgbavae.so")
 
 RV_F32, RV_BF16 = 0, 1
-ABI_VERSION = 12
+ABI_VERSION = 13
 PROF_CATEGORIES = 9
 PROF_NAMES = ("conv_tc", "conv_direct", "norm_silu", "softmax", "layout", "reparam", "recon_loss", "composite_psnr",
               "attention")
@@ -79,7 +79,8 @@ SIGNATURES = {
     "rv_resample2x": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "rv_add_bf16": (_I, [_P, _P, _P, _L, _P]),
     "rv_softmax_bwd": (_I, [_P, _P, _P, _P, _L, _L, _L, _L, _F, _P]),
-    "rv_grad_sqnorm": (_I, [_P, _L, _P, _P]),
+    "rv_grad_sqnorm": (_I, [_P, _L, _P, _P, _P]),
+    "rv_grad_sqnorm_scratch_bytes": (_I, []),
     "rv_adamw_step": (_I, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _F, _P, _F, _P]),
     "rv_adamw_advance": (_I, [_P, _F, _F, _P]),
 }

@@ -174,18 +174,35 @@ __global__ void __launch_bounds__(256) rmsnorm_silu_bwd_kernel(const T* __restri
   }
 }
 
-__global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
-  __shared__ float red[8];
-  float acc = 0.f;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc = fmaf(g[i], g[i], acc);
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float v = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
-    v = warp_sum(v);
-    if (threadIdx.x == 0) atomicAdd(out, v);
+// Squared L2 norm in two deterministic stages (fixed partition, fixed summation order): data-parallel replicas must
+// compute bit-identical clip factors from bit-identical all-reduced gradients, or their weights drift apart.
+__global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ partial) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = g[i];
+    acc += (double)v * (double)v;
   }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(256) sqnorm_finish_kernel(const double* __restrict__ partial, int blocks, float* __restrict__ out) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < blocks; i += 256) acc += partial[i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] += (float)red[0];
 }
 
 // device-resident step counter: state = [t, 1 - beta1^t, 1 - beta2^t]; one launch per optimizer step, ahead of adamw_kernel
@@ -456,14 +473,23 @@ int rv_softmax_bwd(const void* p, const float* dp, void* ds, void* ds_t, int64_t
   return 0;
 }
 
-int rv_grad_sqnorm(const float* g, int64_t n, float* out, void* stream) {
-  RV_CHECK_ARG(g && out && n > 0, "grad_sqnorm: bad argument");
+int rv_grad_sqnorm_scratch_bytes(void) { return 2048 * (int)sizeof(double); }
+
+int rv_grad_sqnorm(const float* g, int64_t n, float* out, void* scratch, void* stream) {
+  RV_CHECK_ARG(g && out && scratch && n > 0, "grad_sqnorm: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
   if (blocks > 2048) blocks = 2048;
-  rv::LaunchScope scope(rv::CAT_LAYOUT, st, 4.0 * n);
-  rv::sqnorm_kernel<<<(unsigned)blocks, 256, 0, st>>>(g, n, out);
-  RV_LAUNCH_CHECK();
+  {
+    rv::LaunchScope scope(rv::CAT_LAYOUT, st, 4.0 * n);
+    rv::sqnorm_kernel<<<(unsigned)blocks, 256, 0, st>>>(g, n, (double*)scratch);
+    RV_LAUNCH_CHECK();
+  }
+  {
+    rv::LaunchScope scope(rv::CAT_LAYOUT, st, 8.0 * blocks);
+    rv::sqnorm_finish_kernel<<<1, 256, 0, st>>>((const double*)scratch, (int)blocks, out);
+    RV_LAUNCH_CHECK();
+  }
   return 0;
 }
 

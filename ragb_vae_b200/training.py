@@ -183,6 +183,7 @@ class FlatAdamW:
         self.m = torch.zeros_like(self.master)
         self.v = torch.zeros_like(self.master)
         self.sqnorm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._sq_scratch = torch.zeros(_lib.load().rv_grad_sqnorm_scratch_bytes(), dtype=torch.uint8, device=dev)
         # [t, 1 - beta1^t, 1 - beta2^t] on the device: the step is replayable from a CUDA graph
         self.state = torch.zeros(3, dtype=torch.float32, device=dev)
 
@@ -211,7 +212,7 @@ class FlatAdamW:
         mx = 0.0
         if self.max_grad_norm is not None and self.max_grad_norm > 0:
             self.sqnorm.zero_()
-            check(lib.rv_grad_sqnorm(_ptr(self.grad), self.grad.numel(), _ptr(self.sqnorm), st), "rv_grad_sqnorm")
+            check(lib.rv_grad_sqnorm(_ptr(self.grad), self.grad.numel(), _ptr(self.sqnorm), _ptr(self._sq_scratch), st), "rv_grad_sqnorm")
             sq, mx = _ptr(self.sqnorm), float(self.max_grad_norm)
         pb = None if self.model_flat is self.master else _ptr(self.model_flat)
         check(lib.rv_adamw_step(_ptr(self.master), _ptr(self.grad), _ptr(self.m), _ptr(self.v), pb, self.master.numel(),
