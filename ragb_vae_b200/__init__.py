@@ -14,9 +14,10 @@ from .plumbing import (build_detail_augmented_triplet, pack_latents, rgba_u8_to_
 from .posterior import DiagonalGaussianDistribution  # noqa: E402
 from .rgba_vae import (RgbaVAE, adapt_vae_to_rgba, composite_over_background, composite_over_black,  # noqa: E402
                        composite_over_white)
+from .trainer import VaeTrainStep  # noqa: E402
 from .validation import compute_psnr, evaluate_rgba_vae, validation_metrics  # noqa: E402
 
 __all__ = ["RgbaAutoencoder", "RgbaVAE", "AlphaVaeLoss", "DiagonalGaussianDistribution", "adapt_vae_to_rgba",
            "composite_over_background", "composite_over_white", "composite_over_black", "compute_psnr",
            "validation_metrics", "evaluate_rgba_vae", "build_detail_augmented_triplet", "split_triplet_distribution",
-           "pack_latents", "unpack_latents", "rgba_u8_to_tensor", "tensor_to_rgba_u8"]
+           "pack_latents", "unpack_latents", "rgba_u8_to_tensor", "tensor_to_rgba_u8", "VaeTrainStep"]
