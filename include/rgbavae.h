@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 13
+#define RV_ABI_VERSION 14
 #define RV_PROF_CATEGORIES 9
 
 int rv_abi_version(void);
@@ -69,6 +69,8 @@ typedef struct rv_conv_desc {
   int32_t clamp;             /* 1: clamp to [clamp_lo, clamp_hi] after scale/shift */
   float   clamp_lo, clamp_hi;
   float   alpha;             /* accumulator scale (1/sqrt(d) for QK^T), applied before bias */
+  int32_t taps_1d;           /* 1 (tensor-core path, ksize 3, stride 1): a 3x1 kernel -- vertical taps only, weights
+                              * [cout][3][cin].  With an rv_nchw_to_nhwc_hpack input this is the 3x3 few-channel stem conv. */
 } rv_conv_desc;
 
 /* CUDA-core implicit GEMM, fp32 accumulate, any shape / layout / dtype.  Weights are fp32
@@ -134,6 +136,12 @@ int rv_attention(const void* q, const void* k, int64_t ld_qk, const void* vt, vo
 /* y[n][hw][c_pad] = x[n][c][hw]*scale+shift (extra channels zero). */
 int rv_nchw_to_nhwc(const void* x, void* y, int n, int c, int64_t hw, int c_pad, int x_dtype,
                     int y_dtype, float scale, float shift, void* stream);
+/* Few-channel stem loader (3*c <= 16): NCHW -> NHWC bf16 with 16 channels per pixel holding the pixel's three
+ * HORIZONTAL neighbours, y[n][h][w][dx*c + ch] = x[n][ch][h][w+dx-1]*scale+shift (zero outside the image and past 3c).
+ * A 3x3 conv over x is then a 3x1 conv (taps_1d) over y with K = 16 per tap: 3 MMAs and 3 TMA boxes per tile instead
+ * of 9 each through 16-channel zero padding. */
+int rv_nchw_to_nhwc_hpack(const void* x, void* y, int n, int c, int h, int w, int x_dtype, float scale, float shift,
+                          void* stream);
 int rv_nhwc_to_nchw(const void* x, void* y, int n, int c, int64_t hw, int x_cstride, int x_dtype,
                     int y_dtype, void* stream);
 

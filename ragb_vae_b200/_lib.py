@@ -9,7 +9,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "librgbavae.so")
 
 RV_F32, RV_BF16 = 0, 1
-ABI_VERSION = 13
+ABI_VERSION = 14
 PROF_CATEGORIES = 9
 PROF_NAMES = ("conv_tc", "conv_direct", "norm_silu", "softmax", "layout", "reparam", "recon_loss", "composite_psnr",
               "attention")
@@ -33,6 +33,7 @@ class ConvDesc(C.Structure):
         ("out_scale", C.c_float), ("out_shift", C.c_float),
         ("clamp", C.c_int32), ("clamp_lo", C.c_float), ("clamp_hi", C.c_float),
         ("alpha", C.c_float),
+        ("taps_1d", C.c_int32),
     ]
 
 
@@ -60,6 +61,7 @@ SIGNATURES = {
     "rv_softmax_rows": (_I, [_P, _P, _L, _L, _L, _L, _I, _P]),
     "rv_attention": (_I, [_P, _P, _L, _P, _P, _L, _I, _I, _I, _P]),
     "rv_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _L, _I, _I, _I, _F, _F, _P]),
+    "rv_nchw_to_nhwc_hpack": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _F, _P]),
     "rv_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _L, _I, _I, _I, _P]),
     "rv_im2col3x3": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
     "rv_triplet_augment": (_I, [_P, _P, _I, _L, _I, _P]),

@@ -307,6 +307,7 @@ class RgbaAutoencoder(nn.Module):
         self.gradient_checkpointing = False
         self.fuse_norm_residual = False
         self.fused_attention = True
+        self.hpack_stem = True    # conv_in as 3 vertical taps over a horizontally packed 16-channel image (see _stem)
         self.im2col_stem = False  # measured slower (3.5 ms) than 16-channel padding + 9 narrow K blocks (2.6 ms) at 8x1024^2
         self.fuse_norm = True  # RMS norm + SiLU in the producing conv's epilogue where one tile holds all channels
         self._pack_cache: Dict[tuple, tuple] = {}
@@ -485,6 +486,17 @@ class RgbaAutoencoder(nn.Module):
 
         return self._cached((id(conv), "tc" if tc else "direct", upsample, cin_pad), [conv.weight], build)
 
+    def _hpack_weights(self, conv: Conv):
+        """[cout][c][3][3] -> bf16 [cout][3 * 16]: per vertical tap dy the 16-wide row [dx][c] (zero padded) that matches
+        ``ops.nchw_to_nhwc_hpack``."""
+        def build():
+            w = conv.weight2d().detach().to(torch.float32)            # [cout][c][dy][dx]
+            m = w.permute(0, 2, 3, 1).reshape(w.shape[0], 3, -1)      # [cout][dy][dx*c + ch]
+            m = torch.nn.functional.pad(m, (0, 16 - m.shape[2]))
+            return m.reshape(w.shape[0], 48).to(torch.bfloat16).contiguous()
+
+        return self._cached((id(conv), "hpack"), [conv.weight], build)
+
     def _im2col_weights(self, conv: Conv, kpad: int):
         """[cout][cin][3][3] -> bf16 [cout][kpad] in im2col order ([tap][cin], zero padded)."""
         def build():
@@ -519,7 +531,7 @@ class RgbaAutoencoder(nn.Module):
     def _conv_fused(self, x: torch.Tensor, conv: Conv, *, upsample: bool = False, residual: Optional[torch.Tensor] = None,
                     y_nchw: bool = False, y_dtype: Optional[torch.dtype] = None, out_scale: float = 1.0,
                     out_shift: float = 0.0, clamp=None, next_norm=None, want_raw: bool = True,
-                    im2col: bool = False) -> "_Stream":
+                    im2col: bool = False, hpack: bool = False) -> "_Stream":
         """Convolution whose result feeds ``next_norm = (norm_module, silu)``: where possible that norm is fused
         into the epilogue (second output ``act``); ``want_raw=False`` drops the raw tensor when only the
         normalised one is consumed (conv1 -> norm2 -> conv2 inside a residual block)."""
@@ -533,7 +545,7 @@ class RgbaAutoencoder(nn.Module):
         bias = self._f32(conv.bias, "bias")
         desc = ops.make_desc(n, h, w, cx if tc else cin, cout, k, stride, upsample, x_dtype=code,
                              y_dtype=RV_F32 if y_dt == torch.float32 else RV_BF16, y_nchw=y_nchw, x_cstride=cx,
-                             out_scale=out_scale, out_shift=out_shift, clamp=clamp)
+                             out_scale=out_scale, out_shift=out_shift, clamp=clamp, taps_1d=hpack)
         fuse = next_norm is not None and not y_nchw and y_dt == torch.bfloat16 and self._can_fuse_norm(conv, next_norm[0])
         if fuse and residual is not None and not self.fuse_norm_residual:
             # measured: residual add + raw store + two-pass norm in one epilogue is slower than conv + norm kernel
@@ -542,7 +554,10 @@ class RgbaAutoencoder(nn.Module):
         if want_raw or not fuse:
             y = torch.empty((n, cout, oh, ow) if y_nchw else (n, oh, ow, cout), dtype=y_dt, device=x.device)
         if tc:
-            wp = self._im2col_weights(conv, cx) if im2col else self._conv_weights(conv, True, upsample, cin_pad=cx)
+            if hpack:
+                wp = self._hpack_weights(conv)
+            else:
+                wp = self._im2col_weights(conv, cx) if im2col else self._conv_weights(conv, True, upsample, cin_pad=cx)
             if fuse:
                 norm, silu = next_norm
                 act = torch.empty((n, oh, ow, cout), dtype=y_dt, device=x.device)
@@ -693,6 +708,11 @@ class RgbaAutoencoder(nn.Module):
             # few-channel 3x3 stem (conv_in, Cin = 4): im2col to one 64-wide K block, then a plain GEMM
             xp = ops.im2col3x3(x, 64, act_dt, in_scale, in_shift)
             return self._conv_fused(xp, conv, next_norm=next_norm, im2col=True)
+        if tc and self.hpack_stem and conv.k == 3 and conv.stride == 1 and 3 * c <= 16:
+            # few-channel 3x3 stem (conv_in, Cin = 4): the three horizontal neighbours ride in the pixel's 16 channels,
+            # the conv runs as 3 vertical taps of K = 16 (3 MMAs + 3 TMA boxes per tile instead of 9 + 9)
+            xp = ops.nchw_to_nhwc_hpack(x, in_scale, in_shift)
+            return self._conv_fused(xp, conv, next_norm=next_norm, hpack=True)
         if tc:
             xp = ops.nchw_to_nhwc(x, 16 * ((c + 15) // 16), act_dt, in_scale, in_shift)
             return self._conv_fused(xp, conv, next_norm=next_norm)

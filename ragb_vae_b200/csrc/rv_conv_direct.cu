@@ -158,8 +158,10 @@ int check_conv_desc(const rv_conv_desc* d) {
   // 3x3 stride 1 is always 'same' (pad_lo + pad_hi = 2; pad_lo = 2 is the data gradient of the stride-2 conv)
   RV_CHECK_ARG(d->pad_lo >= 0 && d->pad_lo <= (d->ksize == 3 ? 2 : 0), "conv: bad pad_lo %d", d->pad_lo);
   int pad_hi = (d->ksize == 3 && d->stride == 1) ? 2 - d->pad_lo : (d->ksize == 3 ? 1 - d->pad_lo : 0);
+  RV_CHECK_ARG(!d->taps_1d || (d->ksize == 3 && d->stride == 1 && !d->upsample && d->pad_lo == 1),
+               "conv: taps_1d needs a stride-1 3-tap kernel with pad 1");
   int oh = (heff + d->pad_lo + pad_hi - d->ksize) / d->stride + 1;
-  int ow = (weff + d->pad_lo + pad_hi - d->ksize) / d->stride + 1;
+  int ow = d->taps_1d ? weff : (weff + d->pad_lo + pad_hi - d->ksize) / d->stride + 1;
   RV_CHECK_ARG(oh == d->oh && ow == d->ow, "conv: output size %dx%d inconsistent with input (expected %dx%d)",
                d->oh, d->ow, oh, ow);
   RV_CHECK_ARG((d->x_dtype == RV_F32 || d->x_dtype == RV_BF16) && (d->y_dtype == RV_F32 || d->y_dtype == RV_BF16),
@@ -176,6 +178,7 @@ extern "C" int rv_conv2d_direct(const rv_conv_desc* d, const void* x, const floa
                                 const void* residual, void* y, void* stream) {
   if (int rc = rv::check_conv_desc(d)) return rc;
   RV_CHECK_ARG(x && w && y, "conv_direct: null tensor");
+  RV_CHECK_ARG(!d->taps_1d, "conv_direct: taps_1d is a tensor-core path layout");
   RV_CHECK_ARG(d->bias_mode == 0 || bias, "conv_direct: bias_mode set but bias is null");
   rv::DirectParams p;
   p.d = *d;

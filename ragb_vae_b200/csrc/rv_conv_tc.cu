@@ -621,10 +621,13 @@ static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_
   } else {
     p.th = d->oh;
     p.tw = d->ow;
-    p.ntaps = d->ksize * d->ksize;
+    p.ntaps = d->taps_1d ? d->ksize : d->ksize * d->ksize;
     for (int t = 0; t < p.ntaps; ++t) {
       int dy = t / d->ksize, dx = t % d->ksize;
-      if (d->stride == 2) {
+      if (d->taps_1d) {
+        p.tap_dy[t] = (signed char)(t - d->pad_lo);
+        p.tap_dx[t] = 0;
+      } else if (d->stride == 2) {
         p.tap_dy[t] = (signed char)(dy >> 1);
         p.tap_hp[t] = (signed char)(dy & 1);
         p.tap_dx[t] = (signed char)(dx >> 1);
@@ -683,7 +686,7 @@ static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_
     if (int rc = tc_encode_map(&map_b, w, 2, dims, str, box, sw)) return rc;
   }
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
-  const double flops = 2.0 * (double)d->n * d->oh * d->ow * d->cout * d->cin * d->ksize * d->ksize / (phase >= 0 ? 4.0 : 1.0);
+  const double flops = 2.0 * (double)d->n * d->oh * d->ow * d->cout * d->cin * d->ksize * (d->taps_1d ? 1 : d->ksize) / (phase >= 0 ? 4.0 : 1.0);
   LaunchScope scope(CAT_CONV_TC, st, flops);
   if (pair) {
     const int total_pt = ((p.m_tiles + 1) / 2) * p.n_tiles;

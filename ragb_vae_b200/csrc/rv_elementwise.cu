@@ -396,6 +396,36 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_vec_kernel(const TX* __restr
   }
 }
 
+// Few-channel stem loader: 16 bf16 channels per pixel = the pixel's three horizontal neighbours (dx-major, channel-minor),
+// zero outside the image and past 3c.  One thread per pixel, plane reads coalesced across the warp (the +-1 neighbours
+// hit L1), two 16-byte stores.
+template <typename TX>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_hpack_kernel(const TX* __restrict__ x, __nv_bfloat16* __restrict__ y, int c,
+                                                                int h, int w, float scale, float shift) {
+  using V = Vec16<__nv_bfloat16>;
+  const int n = blockIdx.z, py = blockIdx.y;
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= w) return;
+  const int64_t hw = (int64_t)h * w;
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = 0.f;
+#pragma unroll
+  for (int dx = 0; dx < 3; ++dx) {
+    const int sx = px + dx - 1;
+    if (sx < 0 || sx >= w) continue;
+    for (int ch = 0; ch < c; ++ch) v[dx * c + ch] = ldf(x + ((int64_t)n * c + ch) * hw + (int64_t)py * w + sx) * scale + shift;
+  }
+  __nv_bfloat16* o = y + (((int64_t)n * h + py) * w + px) * 16;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    V out;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out.set(j, v[k * 8 + j]);
+    out.store(o + k * 8);
+  }
+}
+
 template <typename TX, typename TY>
 __global__ void nhwc_to_nchw_kernel(const TX* __restrict__ x, TY* __restrict__ y, int c, int64_t hw, int x_cstride) {
   const int n = blockIdx.y;
@@ -592,6 +622,22 @@ int rv_nchw_to_nhwc(const void* x, void* y, int n, int c, int64_t hw, int c_pad,
         (const __nv_bfloat16*)x, (__nv_bfloat16*)y, c, hw, c_pad, scale, shift);
   else
     RV_CHECK_ARG(false, "nchw_to_nhwc: bad dtype");
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+int rv_nchw_to_nhwc_hpack(const void* x, void* y, int n, int c, int h, int w, int x_dtype, float scale, float shift, void* stream) {
+  RV_CHECK_ARG(x && y && n > 0 && c > 0 && 3 * c <= 16 && h > 0 && w > 0, "nchw_to_nhwc_hpack: bad argument (3*c <= 16)");
+  RV_CHECK_ARG((uintptr_t)y % 16 == 0, "nchw_to_nhwc_hpack: y must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((w + 255) / 256), (unsigned)h, (unsigned)n);
+  rv::LaunchScope scope(rv::CAT_LAYOUT, st, (double)n * h * w * (c * (x_dtype == RV_F32 ? 4.0 : 2.0) + 32.0));
+  if (x_dtype == RV_F32)
+    rv::nchw_to_nhwc_hpack_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (__nv_bfloat16*)y, c, h, w, scale, shift);
+  else if (x_dtype == RV_BF16)
+    rv::nchw_to_nhwc_hpack_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, c, h, w, scale, shift);
+  else
+    RV_CHECK_ARG(false, "nchw_to_nhwc_hpack: bad dtype");
   RV_LAUNCH_CHECK();
   return 0;
 }

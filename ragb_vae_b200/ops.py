@@ -65,7 +65,7 @@ def conv_out_size(h: int, w: int, ksize: int, stride: int, upsample: bool):
 
 def make_desc(n, h, w, cin, cout, ksize=3, stride=1, upsample=False, *, x_dtype, y_dtype, x_nchw=False, y_nchw=False,
               x_cstride=None, y_cstride=None, bias_mode=1, in_scale=1.0, in_shift=0.0, out_scale=1.0, out_shift=0.0,
-              clamp=None, alpha=1.0) -> ConvDesc:
+              clamp=None, alpha=1.0, taps_1d=False) -> ConvDesc:
     oh, ow = conv_out_size(h, w, ksize, stride, upsample)
     d = ConvDesc()
     d.n, d.h, d.w, d.cin, d.cout = n, h, w, cin, cout
@@ -81,6 +81,7 @@ def make_desc(n, h, w, cin, cout, ksize=3, stride=1, upsample=False, *, x_dtype,
     d.clamp = 0 if clamp is None else 1
     d.clamp_lo, d.clamp_hi = (0.0, 0.0) if clamp is None else clamp
     d.alpha = alpha
+    d.taps_1d = int(bool(taps_1d))
     return d
 
 
@@ -192,6 +193,16 @@ def nchw_to_nhwc(x: torch.Tensor, c_pad: int, out_dtype: torch.dtype, scale: flo
     y = torch.empty((n, h, w, c_pad), dtype=out_dtype, device=x.device)
     check(_lib.load().rv_nchw_to_nhwc(_ptr(x), _ptr(y), n, c, h * w, c_pad, _dt(x), _dt(y), scale, shift, _stream(x)),
           "rv_nchw_to_nhwc")
+    return y
+
+
+def nchw_to_nhwc_hpack(x: torch.Tensor, scale: float = 1.0, shift: float = 0.0) -> torch.Tensor:
+    """(N,C,H,W), 3C <= 16 -> (N,H,W,16) bf16: per pixel its three horizontal neighbours ([dx][c], zero padded)."""
+    _need_cuda(x)
+    n, c, h, w = x.shape
+    x = x.contiguous()
+    y = torch.empty((n, h, w, 16), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().rv_nchw_to_nhwc_hpack(_ptr(x), _ptr(y), n, c, h, w, _dt(x), scale, shift, _stream(x)), "rv_nchw_to_nhwc_hpack")
     return y
 
 

@@ -189,3 +189,33 @@ def test_fused_attention(ops, n_img, tokens, scale_up):
     out = ops.attention(qkc[:, :d], qkc[:, d:], vt.cuda(), n_img, tokens)
     assert out.shape == (n_img * tokens, d)
     assert rel(out.float().view(n_img, tokens, d), ref) < 1e-2
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 40, 72), (1, 4, 16, 200), (1, 3, 24, 24)])
+def test_hpack_stem_matches_conv2d(ops, shape):
+    """conv_in through the horizontally packed loader + 3 vertical taps == the plain 3x3 conv (incl. image borders)."""
+    import torch.nn.functional as F
+    import ragb_vae_b200 as R
+
+    g = torch.Generator().manual_seed(7)
+    n, c, h, w = shape
+    x = torch.rand(shape, generator=g)
+    xb = x.to(torch.bfloat16).float()
+    packed = ops.nchw_to_nhwc_hpack(x.cuda().to(torch.bfloat16), 2.0, -1.0)
+    want = torch.zeros(n, h, w, 16)
+    xp = F.pad(xb * 2 - 1, (1, 1))
+    for dx in range(3):
+        want[..., dx * c:(dx + 1) * c] = xp[:, :, :, dx:dx + w].permute(0, 2, 3, 1)
+    want[:, :, 0, :c] = 0
+    want[:, :, -1, 2 * c:3 * c] = 0
+    assert torch.allclose(packed.float().cpu(), want.to(torch.bfloat16).float(), atol=1e-2)
+    m = R.RgbaAutoencoder("qwen", in_channels=c).to("cuda", torch.bfloat16)
+    conv = m.encoder.conv_in
+    ref = F.conv2d((xb * 2 - 1).to(torch.bfloat16).float(), conv.weight2d().float().cpu(), conv.bias.float().cpu(), padding=1)
+    outs = []
+    for flag in (True, False):
+        m.hpack_stem = flag
+        st = m._stem(x.cuda().to(torch.bfloat16), conv, 2.0, -1.0)
+        outs.append(st.raw.float().permute(0, 3, 1, 2).cpu())
+    for o in outs:
+        assert float((o - ref).norm() / ref.norm()) < 1e-2

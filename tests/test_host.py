@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(lib_built):
 
     assert set(_lib.SIGNATURES) == declared, "python binding table and header disagree"
     assert lib.rv_abi_version() == _lib.ABI_VERSION
-    assert ctypes.sizeof(_lib.ConvDesc) == 26 * 4
+    assert ctypes.sizeof(_lib.ConvDesc) == 27 * 4
 
 
 def test_library_is_blackwell_native(lib_built):
