@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
                     help="c2: fixed 1024^2 batches (the headline); c3: mixed-aspect bucket-pure batches sharded across ranks; "
                          "c4: the rgba_vae training step (fwd + bwd + gradient all-reduce + AdamW), data parallel")
-    ap.add_argument("--train-size", type=int, default=512, help="c4: image side")
+    ap.add_argument("--train-size", type=int, default=1024, help="c4: image side (SURVEY 8: 12 x 4 x 1024^2 into the encoder per GPU)")
     ap.add_argument("--train-batch", type=int, default=4, help="c4: per-GPU batch (configs/flux_vae.yaml: 4)")
     ap.add_argument("--batches", type=int, default=64, help="c3: bucket-pure batches in the whole job")
     return ap.parse_args()

@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 14
+#define RV_ABI_VERSION 15
 #define RV_PROF_CATEGORIES 9
 
 int rv_abi_version(void);
@@ -206,6 +206,11 @@ int rv_recon_loss_bwd(const void* pred, const void* target, const float* eb_host
  * (dz / noise may both be NULL for the KL term alone); the logvar gradient is zero outside the clamp range. */
 int rv_reparam_bwd(const void* moments, const void* noise, const void* dz, void* dmoments, int n, int zc,
                    int64_t hw, int dtype, float kl_weight, void* stream);
+/* KL(posterior || frozen reference posterior), the reference-KL term of the train step (rgba_vae_stage.py:489-508;
+ * DiagonalGaussianDistribution.kl(other)): kl_out[n] (fp32) += per-sample sum; dmoments (optional, same layout and
+ * dtype as moments) = weight * d kl / d moments.  moments / ref_moments NCHW [n][2*zc][hw]. */
+int rv_kl_ref(const void* moments, const void* ref_moments, float* kl_out, void* dmoments, int n, int zc, int64_t hw,
+              int dtype, float weight, void* stream);
 /* Backward of rv_rmsnorm_silu: dx, and dgamma[c] += dgamma_scale * d loss / d (gamma*sqrt(C)) (fp32, ACCUMULATED;
  * dgamma_scale = sqrt(C) gives d loss / d gamma, so dgamma may point straight into a gradient buffer).
  * gamma_scaled = gamma * sqrt(C).  c = 3 * 2^k 16-byte chunks (96, 192, 384 in bf16). */

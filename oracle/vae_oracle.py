@@ -544,9 +544,10 @@ def kl_loss(posterior, reference=None, reduce_mean=False):  # losses.py:109-115
 
 
 def training_step(vae: OracleVAE, inputs: torch.Tensor, noise: torch.Tensor, kl_scale: Optional[float] = 1e-6,
-                  reduce_mean: bool = False, use_naive_mse: bool = False):
+                  reduce_mean: bool = False, use_naive_mse: bool = False, ref_vae: Optional[OracleVAE] = None,
+                  ref_kl_scale: Optional[float] = None):
     """One ``rgba_vae`` step up to ``accelerator.backward`` (src/training/rgba_vae_stage.py:433-518) with
-    ``lpips_scale = 0`` and no reference VAE: returns (metrics, {parameter name: gradient}).  ``inputs`` in [0,1];
+    ``lpips_scale = 0`` (the reference-KL term is optional: ``ref_vae`` + ``ref_kl_scale``): returns (metrics, {parameter name: gradient}).  ``inputs`` in [0,1];
     ``noise`` is the posterior sample's eps for the first third of the triplet batch (reproducible ``sample()``)."""
     vae.requires_grad_(True)
     vae.zero_grad(set_to_none=True)
@@ -554,7 +555,7 @@ def training_step(vae: OracleVAE, inputs: torch.Tensor, noise: torch.Tensor, kl_
     target_vae = target * 2.0 - 1.0
     composed = build_detail_augmented_triplet(target_vae)
     posterior_all = vae.encode(composed).latent_dist
-    posterior, _, _ = split_triplet_distribution(posterior_all)
+    posterior, posterior_black, posterior_white = split_triplet_distribution(posterior_all)
     z = posterior.sample(noise=noise)
     pred = vae.decode(z).sample
     recon = reconstruction_loss(pred, target_vae, reduce_mean, use_naive_mse)
@@ -564,6 +565,13 @@ def training_step(vae: OracleVAE, inputs: torch.Tensor, noise: torch.Tensor, kl_
         kl = kl_loss(posterior, None, reduce_mean)
         metrics["train/kl"] = kl.detach()
         total = total + kl_scale * kl
+    if ref_vae is not None and ref_kl_scale and ref_kl_scale > 0.0:  # rgba_vae_stage.py:489-508
+        with torch.no_grad():
+            ref_all = ref_vae.encode(composed).latent_dist
+        _, ref_black, ref_white = split_triplet_distribution(ref_all)
+        ref_kl = 0.5 * (kl_loss(posterior_black, ref_black, reduce_mean) + kl_loss(posterior_white, ref_white, reduce_mean))
+        metrics["train/ref_kl"] = ref_kl.detach()
+        total = total + ref_kl_scale * ref_kl
     metrics["train/loss"] = total.detach()
     total.backward()
     grads = {n: p.grad.detach().clone() for n, p in vae.named_parameters() if p.grad is not None}

@@ -74,6 +74,46 @@ __global__ void __launch_bounds__(256) reparam_bwd_kernel(const T* __restrict__ 
   }
 }
 
+// KL(N(mean, var) || N(rmean, rvar)) against a frozen reference posterior (rgba_vae_stage.py:489-508; diffusers
+// DiagonalGaussianDistribution.kl(other)): per element 0.5 * ((m - rm)^2 / rv + v / rv - 1 - lv + rlv), log-variances clamped
+// to [-30, 20] on both sides.  kl_out[n] += per-sample sum; dmoments (optional) = weight * d kl / d moments:
+// d/dm = (m - rm) / rv, d/dlv = 0.5 * (v / rv - 1) inside the clamp range, else 0.
+template <typename T>
+__global__ void __launch_bounds__(256) kl_ref_kernel(const T* __restrict__ moments, const T* __restrict__ ref, float* __restrict__ kl_out,
+                                                    T* __restrict__ dmoments, int zc, int64_t hw, float weight) {
+  __shared__ float red[8];
+  const int n = blockIdx.y;
+  const int64_t per = (int64_t)zc * hw;
+  const T* mean = moments + (int64_t)n * 2 * per;
+  const T* logv = mean + per;
+  const T* rmean = ref + (int64_t)n * 2 * per;
+  const T* rlogv = rmean + per;
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
+    const float m = ldf(mean + i), lv_raw = ldf(logv + i);
+    const float rm = ldf(rmean + i);
+    const float lv = fminf(fmaxf(lv_raw, -30.f), 20.f);
+    const float rlv = fminf(fmaxf(ldf(rlogv + i), -30.f), 20.f);
+    const float v = expf(lv), irv = expf(-rlv);
+    const float d = m - rm;
+    acc += 0.5f * (d * d * irv + v * irv - 1.0f - lv + rlv);
+    if (dmoments) {
+      T* dmean = dmoments + (int64_t)n * 2 * per;
+      stf(dmean + i, weight * d * irv);
+      const bool inside = lv_raw >= -30.f && lv_raw <= 20.f;
+      stf(dmean + per + i, inside ? weight * 0.5f * (v * irv - 1.0f) : 0.f);
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) atomicAdd(kl_out + n, t);
+  }
+}
+
 // Backward of y = act(x * r * g), r = 1/max(||x||_2, 1e-12), g = gamma*sqrt(C), act = SiLU or identity.
 // Same work split as the forward warp kernel: a pixel's channels lie on L lanes (L = C / (3 * 16-byte chunk)), three
 // 16-byte chunks per lane, so both per-pixel reductions are xor-shuffles.  A lane owns fixed channels, so dgamma
@@ -387,6 +427,23 @@ int rv_reparam_bwd(const void* moments, const void* noise, const void* dz, void*
                                                                                (const __nv_bfloat16*)dz, (__nv_bfloat16*)dmoments, zc, hw,
                                                                                kl_weight);
   else RV_CHECK_ARG(false, "reparam_bwd: bad dtype %d", dtype);
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+int rv_kl_ref(const void* moments, const void* ref_moments, float* kl_out, void* dmoments, int n, int zc, int64_t hw, int dtype,
+              float weight, void* stream) {
+  RV_CHECK_ARG(moments && ref_moments && kl_out && n > 0 && zc > 0 && hw > 0, "kl_ref: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t per = (int64_t)zc * hw;
+  rv::LaunchScope scope(rv::CAT_REPARAM, st, (dmoments ? 6.0 : 4.0) * n * per * (dtype == RV_F32 ? 4 : 2));
+  if (dtype == RV_F32)
+    rv::kl_ref_kernel<float><<<rv::train_grid(per, n), 256, 0, st>>>((const float*)moments, (const float*)ref_moments, kl_out, (float*)dmoments,
+                                                                  zc, hw, weight);
+  else if (dtype == RV_BF16)
+    rv::kl_ref_kernel<__nv_bfloat16><<<rv::train_grid(per, n), 256, 0, st>>>((const __nv_bfloat16*)moments, (const __nv_bfloat16*)ref_moments,
+                                                                          kl_out, (__nv_bfloat16*)dmoments, zc, hw, weight);
+  else RV_CHECK_ARG(false, "kl_ref: bad dtype %d", dtype);
   RV_LAUNCH_CHECK();
   return 0;
 }

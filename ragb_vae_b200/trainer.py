@@ -18,9 +18,10 @@ tensors per block) and ``backward`` walks the model in reverse, calling librgbav
   * loss / sample  ``rv_recon_loss_bwd`` (with the decoder's [-1,1] clamp mask), ``rv_reparam_bwd`` (+ KL term)
   * optimizer      ``FlatAdamW`` (fused clip + AdamW over one flat buffer); data parallel: bucketed NCCL all-reduce.
 
-What the reference's step also has and this one does not: LPIPS (third-party VGG, out of scope) and the
-reference-KL term against a frozen copy (``ref_kl_scale`` = 1e-16 in configs/flux_vae.yaml, numerically nil); the
-black / white composites of the triplet are still encoded (``encode_triplet=True``) so the step does the same work.
+What the reference's step also has and this one does not: LPIPS (third-party VGG, out of scope).  The
+reference-KL term against a frozen copy (``ref_vae`` + ``ref_kl_scale``; 1e-16 in configs/flux_vae.yaml) is optional: with
+it the whole triplet (3B images) runs through the taped encoder and its backward, like the reference's autograd does;
+without it the black / white composites are still encoded (``encode_triplet=True``) but carry no gradient.
 """
 from __future__ import annotations
 
@@ -41,7 +42,8 @@ from .posterior import DiagonalGaussianDistribution
 class VaeTrainStep:
     def __init__(self, vae: RgbaAutoencoder, *, lr: float = 1e-5, betas=(0.5, 0.9), eps: float = 1e-8,
                  weight_decay: float = 0.01, max_grad_norm: Optional[float] = 1.0, kl_scale: Optional[float] = 1e-6,
-                 loss_module: Optional[AlphaVaeLoss] = None, num_buckets: int = 4, encode_triplet: bool = True, group=None):
+                 loss_module: Optional[AlphaVaeLoss] = None, num_buckets: int = 4, encode_triplet: bool = True, group=None,
+                 ref_vae: Optional[RgbaAutoencoder] = None, ref_kl_scale: Optional[float] = None):
         if vae.arch != "qwen":
             raise NotImplementedError("the training step covers the Qwen-Image arch (configs/flux_vae.yaml trains that VAE)")
         if vae.dtype != torch.bfloat16:
@@ -50,6 +52,9 @@ class VaeTrainStep:
         self.loss_module = loss_module if loss_module is not None else AlphaVaeLoss()
         self.kl_scale = kl_scale
         self.encode_triplet = encode_triplet
+        # reference-KL term (rgba_vae_stage.py:385-406, 489-508): a frozen copy's posteriors of the black / white composites
+        self.ref_vae = ref_vae
+        self.ref_kl_scale = ref_kl_scale
         # parameters autograd would give a gradient to: everything except the video-only temporal convs
         named = [(n, p) for n, p in vae.named_parameters() if ".time_conv." not in n]
         self.names = [n for n, _ in named]
@@ -324,12 +329,22 @@ class VaeTrainStep:
             B = inputs.shape[0]
             target_vae = torch.clamp(inputs.to(torch.float32), 0.0, 1.0) * 2.0 - 1.0
             enc_tape: list = []
-            moments = self.encode_moments(target_vae, enc_tape)
-            if self.encode_triplet:  # black / white composites: encoded like the reference does, no gradient path
+            use_ref = self.ref_vae is not None and self.ref_kl_scale is not None and self.ref_kl_scale > 0.0
+            ref_ctx = None
+            if use_ref:
+                # the black / white posteriors carry a gradient now: the whole triplet goes through the taped encoder
                 composed = build_detail_augmented_triplet(target_vae)
-                vae.fuse_norm = fuse
-                vae._encode_moments(composed[B:])
-                vae.fuse_norm = False
+                moments_all = self.encode_moments(composed, enc_tape)
+                moments = moments_all[:B]
+                ref_moments = self.ref_vae._encode_moments(composed)  # frozen copy, inference path, no tape
+                ref_ctx = (moments_all, ref_moments)
+            else:
+                moments = self.encode_moments(target_vae, enc_tape)
+                if self.encode_triplet:  # black / white composites: encoded like the reference does, no gradient path
+                    composed = build_detail_augmented_triplet(target_vae)
+                    vae.fuse_norm = fuse
+                    vae._encode_moments(composed[B:])
+                    vae.fuse_norm = False
             post = DiagonalGaussianDistribution(moments)
             z = post.sample(noise=noise)
             dec_tape: list = []
@@ -344,21 +359,32 @@ class VaeTrainStep:
                 metrics["train/kl"] = kl
                 total = total + self.kl_scale * kl
                 kl_w = self.kl_scale / B  # posterior.kl() is already the per-sample sum; both reduce rules average it over B
+            dm_ref = None
+            if use_ref:
+                # 0.5 * (kl_loss(black, ref_black) + kl_loss(white, ref_white)); kl_loss = per-sample sums averaged over B
+                moments_all, ref_moments = ref_ctx
+                w = self.ref_kl_scale * 0.5 / B
+                kl_bw, dm_ref = T.kl_to_reference(moments_all[B:], ref_moments[B:], grad_weight=w)
+                ref_kl = 0.5 * (kl_bw[:B].mean() + kl_bw[B:].mean())
+                metrics["train/ref_kl"] = ref_kl
+                total = total + self.ref_kl_scale * ref_kl
             metrics["train/loss"] = total
             # ---- backward ----
             self.opt.zero_grad()
             dpred = T.recon_loss_backward(pred, target_vae, lm._eb, lm._eb2, lm.reduce_mean, lm.use_naive_mse, clamp=(-1.0, 1.0))
             dy = ops.nchw_to_nhwc(dpred, 16, torch.bfloat16)
             dzp = self._run_bwd(dec_tape, dy)  # NHWC [B,h,w,16]
-            return metrics, (enc_tape, moments, noise, dzp, kl_w)
+            return metrics, (enc_tape, moments, noise, dzp, kl_w, dm_ref)
         finally:
             vae.fuse_norm = fuse
 
     def _encoder_backward(self, ctx) -> None:
         """Phase 2: posterior sample / KL backward and the encoder's backward."""
-        enc_tape, moments, noise, dzp, kl_w = ctx
+        enc_tape, moments, noise, dzp, kl_w, dm_ref = ctx
         dz = ops.nhwc_to_nchw(dzp, 16, torch.float32)
-        dmom = T.reparam_backward(moments, noise, dz, kl_weight=kl_w)
+        dmom = T.reparam_backward(moments.contiguous(), noise, dz, kl_weight=kl_w)
+        if dm_ref is not None:  # the triplet's black / white thirds get the reference-KL gradient
+            dmom = torch.cat([dmom, dm_ref], dim=0)
         dm = ops.nchw_to_nhwc(dmom, dmom.shape[1], torch.bfloat16)
         self._run_bwd(enc_tape, dm)
 

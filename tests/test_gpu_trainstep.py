@@ -246,3 +246,49 @@ def test_step_graphed_matches_eager(lib_built):
     # split-K fp32 atomics make the gradients order-dependent in the last bits; sign-like AdamW updates amplify that
     # for near-zero gradients only
     assert cos(deltas[0], deltas[1]) > 0.995
+
+
+def test_reference_kl_term_and_full_triplet_backward(lib_built):
+    """With a frozen reference VAE the black / white thirds of the triplet carry the reference-KL gradient: loss terms and
+    every parameter gradient vs the oracle's autograd (ref_kl_scale raised so the term matters)."""
+    import ragb_vae_b200 as R
+    from ragb_vae_b200 import training as T
+    from ragb_vae_b200.trainer import VaeTrainStep
+
+    # the kernel on its own
+    g = torch.Generator().manual_seed(41)
+    mom = (torch.randn(3, 32, 6, 10, generator=g) * 2).requires_grad_(True)
+    ref = torch.randn(3, 32, 6, 10, generator=g) * 2
+    kl = O.DiagonalGaussianDistribution(mom).kl(O.DiagonalGaussianDistribution(ref))
+    (0.7 * kl.sum()).backward()
+    got_kl, got_dm = T.kl_to_reference(mom.detach().cuda(), ref.cuda(), grad_weight=0.7)
+    assert rel(got_kl, kl) < 1e-5
+    assert rel(got_dm, mom.grad) < 1e-5
+
+    def make(seed):
+        o = copy.deepcopy(O.build_oracle("qwen", seed=seed))
+        with torch.no_grad():
+            for p in o.parameters():
+                p.copy_(bf16r(p))
+        v = R.RgbaAutoencoder("qwen")
+        v.load_state_dict(o.state_dict())
+        return o, v.to("cuda", torch.bfloat16)
+
+    oracle, vae = make(0)
+    ref_oracle, ref_vae = make(5)
+    step = VaeTrainStep(vae, kl_scale=1e-6, ref_vae=ref_vae, ref_kl_scale=0.5)
+    x = O.synthetic_rgba(2, 64, 64, seed=43)
+    noise = torch.randn(2, 16, 8, 8, generator=torch.Generator().manual_seed(44))
+    metrics, want = O.training_step(oracle, x, noise, kl_scale=1e-6, ref_vae=ref_oracle, ref_kl_scale=0.5)
+    got = step.forward_backward(x.cuda(), noise.cuda())
+    for k in ("train/recon", "train/kl", "train/ref_kl", "train/loss"):
+        assert abs(float(got[k]) - float(metrics[k])) <= 3e-2 * abs(float(metrics[k])), k
+    grads = step.named_grads()
+    flat_g = torch.cat([grads[n].reshape(-1).cpu() for n in want])
+    flat_w = torch.cat([want[n].reshape(-1) for n in want])
+    assert rel(flat_g, flat_w) < 3e-2
+    assert cos(flat_g, flat_w) > 0.999
+    # the reference-KL term must actually reach the encoder: its gradient differs from the step without the term
+    _, without = O.training_step(oracle, x, noise, kl_scale=1e-6)
+    enc = [n for n in want if n.startswith("encoder.")]
+    assert rel(torch.cat([want[n].reshape(-1) for n in enc]), torch.cat([without[n].reshape(-1) for n in enc])) > 5e-2
