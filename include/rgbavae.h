@@ -237,7 +237,8 @@ int rv_resample2x(const void* x, void* y, int n, int h, int w, int c, int mode, 
 /* y = a + b over n bf16 elements (n % 8 == 0): gradient accumulation where two branches meet. */
 int rv_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream);
 /* Softmax backward for a block of `rows` query rows: dS = P * (dP - rowsum(dP*P)) * scale as bf16 [rows][cols] and as
- * its transpose written into ds_t [cols][ld_t] at column offset row0.  p bf16 [rows][cols], dp fp32 [rows][cols]. */
+ * (optionally, ds_t != NULL) its transpose written into ds_t [cols][ld_t] at column offset row0.  p bf16 [rows][cols],
+ * dp fp32 [rows][cols]. */
 int rv_softmax_bwd(const void* p, const float* dp, void* ds, void* ds_t, int64_t rows, int64_t cols, int64_t ld_t,
                    int64_t row0, float scale, void* stream);
 /* *out += sum(g^2) over a flat fp32 gradient buffer (accelerator.clip_grad_norm_, rgba_vae_stage.py:520-521).

@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* _
     const float v = __bfloat162float(pr[i]) * (dr[i] - tot) * scale;
     const __nv_bfloat16 b = __float2bfloat16_rn(v);
     ds[row * cols + i] = b;
-    dst[i * ldt + row0 + row] = b;
+    if (dst) dst[i * ldt + row0 + row] = b;
   }
 }
 
@@ -521,7 +521,7 @@ int rv_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream) 
 
 int rv_softmax_bwd(const void* p, const float* dp, void* ds, void* ds_t, int64_t rows, int64_t cols, int64_t ld_t, int64_t row0,
                    float scale, void* stream) {
-  RV_CHECK_ARG(p && dp && ds && ds_t && rows > 0 && cols > 0 && ld_t >= row0 + rows, "softmax_bwd: bad argument");
+  RV_CHECK_ARG(p && dp && ds && rows > 0 && cols > 0 && (!ds_t || ld_t >= row0 + rows), "softmax_bwd: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   rv::LaunchScope scope(rv::CAT_SOFTMAX, st, (double)rows * cols * 10.0);
   rv::softmax_bwd_kernel<<<(unsigned)rows, 256, 0, st>>>((const __nv_bfloat16*)p, dp, (__nv_bfloat16*)ds, (__nv_bfloat16*)ds_t, cols, ld_t,

@@ -193,13 +193,17 @@ class VaeTrainStep:
         s = torch.empty((q_chunk, t), dtype=torch.float32, device=dev)
         dp = torch.empty((q_chunk, t), dtype=torch.float32, device=dev)
         ds = torch.empty((q_chunk, t), dtype=torch.bfloat16, device=dev)
-        ds_t = torch.empty((t, t), dtype=torch.bfloat16, device=dev)
+        kt = torch.empty((c, t), dtype=torch.bfloat16, device=dev)
+        wqkv, bqkv, _, _ = self._attn_weights(attn)
+        xn2 = xn.view(n * t, c)
         from . import _lib
         for i in range(n):
             sl = slice(i * t, (i + 1) * t)
             dv = torch.zeros((t, c), dtype=torch.float32, device=dev)
             dk = torch.zeros((t, c), dtype=torch.float32, device=dev)
-            dq = torch.zeros((t, c), dtype=torch.float32, device=dev)
+            # K^T[c][token] (dQ = dS K wants the key index contiguous in its second operand)
+            self._gemm(wqkv[c:2 * c], xn2[sl], rows=c, k=c, cols=t, x_ld=c, w_ld=c, y=kt, y_ld=t, bias=bqkv[c:2 * c].contiguous(),
+                       bias_mode=2)
             for r0 in range(0, t, q_chunk):
                 rows = min(q_chunk, t - r0)
                 rs = slice(i * t + r0, i * t + r0 + rows)
@@ -207,14 +211,13 @@ class VaeTrainStep:
                 p = ops.softmax_rows(s[:rows], torch.bfloat16)
                 # dP = dO V^T
                 self._gemm(d_o[rs], v[sl], rows=rows, k=c, cols=t, x_ld=c, w_ld=c, y=dp[:rows], y_ld=t)
-                T.check(_lib.load().rv_softmax_bwd(ops._ptr(p), ops._ptr(dp), ops._ptr(ds), ops._ptr(ds_t), rows, t, t, r0, scale,
-                                                     ops._stream(p)), "rv_softmax_bwd")
-                # dV += P^T dO ; dK += dS^T Q   (reduction over this block's query rows)
+                T.check(_lib.load().rv_softmax_bwd(ops._ptr(p), ops._ptr(dp), ops._ptr(ds), None, rows, t, t, r0, scale,
+                                                   ops._stream(p)), "rv_softmax_bwd")
+                # dV += P^T dO ; dK += dS^T Q   (reduction over this block's query rows: wgrad-form GEMMs)
                 T.gemm_tn_accumulate(dv, p, d_o[rs])
                 T.gemm_tn_accumulate(dk, ds[:rows], q[rs])
-            # dQ = dS K  (reduction over keys: dS^T is the "dy" operand)
-            T.gemm_tn_accumulate(dq, ds_t, k[sl])
-            dqkv[sl, :c] = dq
+                # dQ = dS K, straight into its third of dqkv
+                self._gemm(ds[:rows], kt, rows=rows, k=t, cols=c, x_ld=t, w_ld=t, y=dqkv[rs, :c], y_ld=3 * c)
             dqkv[sl, c:2 * c] = dk
             dqkv[sl, 2 * c:] = dv
         T.conv_wgrad(as_img(xn.view(n * t, c), c), as_img(dqkv, 3 * c), 1, dw_out=self._gview[id(attn.to_qkv.weight)],
