@@ -164,18 +164,33 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   }
 }
 
-// per-channel sum over pixels (bias gradient): x [pixels][c] bf16 -> out[c] += sum
+// per-channel sum over pixels (bias gradient): x [pixels][c] bf16 -> out[ch] += sum, ch < c_valid.
+// A thread owns one 16-byte chunk (8 channels) of the pixel row and walks pixels; the block's partial sums meet in shared
+// memory, so each block issues one atomicAdd per channel.  c % 8 == 0.
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int64_t pixels, int c,
                                                     int c_valid) {
-  // thread t owns channel (t % c) of pixel rows t / c, t / c + rows_per_iter, ...
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t total_threads = (int64_t)gridDim.x * blockDim.x;
-  const int64_t lanes = total_threads / c * c;  // threads beyond the last full pixel row idle
-  if (t >= lanes) return;
-  const int ch = (int)(t % c);
-  float acc = 0.f;
-  for (int64_t r = t / c; r < pixels; r += lanes / c) acc += __bfloat162float(x[r * c + ch]);
-  if (ch < c_valid) atomicAdd(out + ch, acc);
+  using V = Vec16<__nv_bfloat16>;
+  extern __shared__ float sacc[];  // [c]
+  const int cv = c >> 3;
+  for (int i = threadIdx.x; i < c; i += 256) sacc[i] = 0.f;
+  __syncthreads();
+  const int lanes = 256 / cv * cv;  // threads beyond the last whole pixel row idle
+  if ((int)threadIdx.x < lanes) {
+    const int vec = threadIdx.x % cv, prow = threadIdx.x / cv, rows_per_iter = lanes / cv;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int64_t r = (int64_t)blockIdx.x * rows_per_iter + prow; r < pixels; r += (int64_t)gridDim.x * rows_per_iter) {
+      V v;
+      v.load(x + r * c + vec * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v.get(j);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sacc[vec * 8 + j], acc[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c_valid; i += 256) atomicAdd(out + i, sacc[i]);
 }
 
 int tc_encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
@@ -255,11 +270,14 @@ extern "C" int rv_conv2d_wgrad(const void* x, const void* dy, float* dw, int64_t
   if (dbias) {
     const int64_t pixels = (int64_t)n * h * w;
     LaunchScope scope(CAT_NORM, st, (double)pixels * cout * 2.0);
-    int64_t blocks = (pixels * cout + 256 * 64 - 1) / (256 * 64);
+    RV_CHECK_ARG(cout <= 8192, "conv2d_wgrad: bias gradient supports up to 8192 output channels");
+    const int cv = cout / 8;
+    const int rows_per_iter = cv <= 256 ? 256 / cv : 0;
+    RV_CHECK_ARG(rows_per_iter > 0, "conv2d_wgrad: bias gradient needs cout <= 2048");
+    int64_t blocks = (pixels + (int64_t)rows_per_iter * 16 - 1) / ((int64_t)rows_per_iter * 16);
     if (blocks > num_sms() * 8) blocks = num_sms() * 8;
     if (blocks < 1) blocks = 1;
-    while (blocks * 256 < cout) ++blocks;
-    colsum_kernel<<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, dbias, pixels, cout, cout_valid);
+    colsum_kernel<<<(unsigned)blocks, 256, (size_t)cout * sizeof(float), st>>>((const __nv_bfloat16*)dy, dbias, pixels, cout, cout_valid);
     RV_LAUNCH_CHECK();
   }
   return 0;
