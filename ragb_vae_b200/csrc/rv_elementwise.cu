@@ -386,12 +386,18 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_vec_kernel(const TX* __restr
 #pragma unroll
     for (int ch = 0; ch < CP; ++ch) v[ch] = ch < c ? ldf(x + ((int64_t)n * c + ch) * hw + i) * scale + shift : 0.f;
     TY* o = y + ((int64_t)n * hw + i) * CP;
+    V out[CHUNKS];
 #pragma unroll
-    for (int k = 0; k < CHUNKS; ++k) {
-      V out;
+    for (int k = 0; k < CHUNKS; ++k)
 #pragma unroll
-      for (int j = 0; j < V::N; ++j) out.set(j, v[k * V::N + j]);
-      out.store(o + k * V::N);
+      for (int j = 0; j < V::N; ++j) out[k].set(j, v[k * V::N + j]);
+    if (sizeof(TY) == 2 && CHUNKS % 2 == 0) {  // bf16 rows of 32 / 64 bytes: whole-sector stores
+#pragma unroll
+      for (int k = 0; k < CHUNKS; k += 2)
+        store32(o + k * V::N, *reinterpret_cast<const uint4*>(&out[k].v), *reinterpret_cast<const uint4*>(&out[k + 1].v));
+    } else {
+#pragma unroll
+      for (int k = 0; k < CHUNKS; ++k) out[k].store(o + k * V::N);
     }
   }
 }
@@ -417,12 +423,15 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_hpack_kernel(const TX* __res
     for (int ch = 0; ch < c; ++ch) v[dx * c + ch] = ldf(x + ((int64_t)n * c + ch) * hw + (int64_t)py * w + sx) * scale + shift;
   }
   __nv_bfloat16* o = y + (((int64_t)n * h + py) * w + px) * 16;
+  V out[2];
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    V out;
+  for (int k = 0; k < 2; ++k)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) out.set(j, v[k * 8 + j]);
-    out.store(o + k * 8);
+    for (int j = 0; j < 8; ++j) out[k].set(j, v[k * 8 + j]);
+  if ((reinterpret_cast<uintptr_t>(y) & 31u) == 0) store32(o, out[0].v, out[1].v);
+  else {
+    out[0].store(o);
+    out[1].store(o + 8);
   }
 }
 
@@ -592,7 +601,7 @@ int rv_nchw_to_nhwc(const void* x, void* y, int n, int c, int64_t hw, int c_pad,
   dim3 grid(bx, n);
   rv::LaunchScope scope(rv::CAT_LAYOUT, st,
                         (double)n * hw * (c * (x_dtype == RV_F32 ? 4.0 : 2.0) + c_pad * (y_dtype == RV_F32 ? 4.0 : 2.0)));
-  if (y_dtype == RV_BF16 && (c_pad == 16 || c_pad == 32) && ((uintptr_t)y % 16 == 0)) {
+  if (y_dtype == RV_BF16 && (c_pad == 16 || c_pad == 32) && ((uintptr_t)y % 32 == 0)) {
     // 16-byte stores (the channel-padded stems and the 32-channel moments)
 #define RV_VEC(TX, CH) \
   rv::nchw_to_nhwc_vec_kernel<TX, __nv_bfloat16, CH><<<grid, 256, 0, st>>>((const TX*)x, (__nv_bfloat16*)y, c, hw, scale, shift)

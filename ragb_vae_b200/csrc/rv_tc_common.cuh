@@ -295,8 +295,12 @@ __device__ __forceinline__ void store_bf16_row16(__nv_bfloat16* yp, const float 
     b.y = pack_bf16x2(v[10], v[11]);
     b.z = pack_bf16x2(v[12], v[13]);
     b.w = pack_bf16x2(v[14], v[15]);
-    *reinterpret_cast<uint4*>(yp) = a;
-    *reinterpret_cast<uint4*>(yp + 8) = b;
+    if ((reinterpret_cast<uintptr_t>(yp) & 31u) == 0) {
+      store32(yp, a, b);
+    } else {
+      *reinterpret_cast<uint4*>(yp) = a;
+      *reinterpret_cast<uint4*>(yp + 8) = b;
+    }
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j)
@@ -367,9 +371,19 @@ struct FastStep {
 
   __device__ __forceinline__ void load(const EpiParams& e, uint32_t taddr, int co0, int64_t pix, bool valid) {
     if (RES && valid) {
-      const uint4* rp = reinterpret_cast<const uint4*>(e.residual + pix * e.y_cstride + co0);
+      const __nv_bfloat16* rp16 = e.residual + pix * e.y_cstride + co0;
+      if ((reinterpret_cast<uintptr_t>(rp16) & 31u) == 0) {  // 32-byte loads: one request per sector
 #pragma unroll
-      for (int q = 0; q < W / 8; ++q) res[q] = rp[q];
+        for (int q = 0; q < W / 16; ++q)
+          asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(res[2 * q].x), "=r"(res[2 * q].y), "=r"(res[2 * q].z), "=r"(res[2 * q].w), "=r"(res[2 * q + 1].x),
+                         "=r"(res[2 * q + 1].y), "=r"(res[2 * q + 1].z), "=r"(res[2 * q + 1].w)
+                       : "l"(rp16 + 16 * q));
+      } else {
+        const uint4* rp = reinterpret_cast<const uint4*>(rp16);
+#pragma unroll
+        for (int q = 0; q < W / 8; ++q) res[q] = rp[q];
+      }
     }
     tmem_ldw<W>(taddr, r);
     tmem_ld_wait();
@@ -405,6 +419,19 @@ struct FastStep {
 
 template <int W>
 __device__ __forceinline__ void fast_store(__nv_bfloat16* yp, const float (&v)[W]) {
+  // 32-byte (whole-sector) stores when the row is 32-byte aligned, else 16-byte ones
+  if ((reinterpret_cast<uintptr_t>(yp) & 31u) == 0) {
+#pragma unroll
+    for (int q = 0; q < W / 16; ++q) {
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yp + 16 * q),
+                   "r"(pack_bf16x2(v[16 * q], v[16 * q + 1])), "r"(pack_bf16x2(v[16 * q + 2], v[16 * q + 3])),
+                   "r"(pack_bf16x2(v[16 * q + 4], v[16 * q + 5])), "r"(pack_bf16x2(v[16 * q + 6], v[16 * q + 7])),
+                   "r"(pack_bf16x2(v[16 * q + 8], v[16 * q + 9])), "r"(pack_bf16x2(v[16 * q + 10], v[16 * q + 11])),
+                   "r"(pack_bf16x2(v[16 * q + 12], v[16 * q + 13])), "r"(pack_bf16x2(v[16 * q + 14], v[16 * q + 15]))
+                   : "memory");
+    }
+    return;
+  }
   uint4* dst = reinterpret_cast<uint4*>(yp);
 #pragma unroll
   for (int q = 0; q < W / 8; ++q) {
