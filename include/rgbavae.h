@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 15
+#define RV_ABI_VERSION 16
 #define RV_PROF_CATEGORIES 9
 
 int rv_abi_version(void);
@@ -155,6 +155,11 @@ int rv_im2col3x3(const void* x, void* y, int n, int c, int h, int w, int kpad, i
 /* build_detail_augmented_triplet (src/training/rgba_vae_stage.py:606-625): target NCHW [b][4][hw] in [-1,1] ->
  * out [3b][4][hw] = [target | on black, alpha 1 | on white, alpha 1]. */
 int rv_triplet_augment(const void* target, void* out, int b, int64_t hw, int dtype, void* stream);
+/* RandomBackgroundBlend._blend_tensor (src/training/rgba_vae_stage.py:85-130) for a whole batch: x NCHW [n][4][hw] in
+ * [0,1]; samples with mask[n] != 0 are composited over the opaque colour colors[n][3] (fp32) and get alpha 1, the others
+ * are copied.  colors and mask are device arrays. */
+int rv_background_blend(const void* x, const float* colors, const unsigned char* mask, void* y, int n, int64_t hw,
+                        int dtype, void* stream);
 /* FluxPipeline._pack_latents / _unpack_latents (src/models/flux_kontext_textalpha.py:334-349): (n,c,h,w) <->
  * (n, (h/2)(w/2), 4c) with feature order (c, dy, dx).  unpack = 0: y = (pack(x) - shift) * scale;
  * unpack = 1: y = unpack(x) * scale + shift. */

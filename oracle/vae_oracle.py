@@ -600,6 +600,35 @@ def build_detail_augmented_triplet(target):  # rgba_vae_stage.py:606-625
     return torch.cat([target, black, white], dim=0)
 
 
+def background_blend(tensor, color):  # RandomBackgroundBlend._blend_tensor, rgba_vae_stage.py:118-129 (colour supplied)
+    """tensor: (4,H,W) RGBA in [0,1]; color: (3,) -- composite over the opaque colour, alpha := 1."""
+    tensor = tensor.clone()
+    rgb, alpha = tensor[:3], tensor[3:4]
+    bg = color.to(tensor.dtype).view(3, 1, 1).expand_as(rgb)
+    blended = rgb * alpha + bg * (1.0 - alpha)
+    return torch.cat([blended, torch.ones_like(alpha)], dim=0)
+
+
+def build_training_batch(batch, background_mask=None):  # rgba_vae_stage.py:575-603 (mask supplied instead of torch.rand)
+    tensors = []
+    if "component" in batch and "composite" in batch:
+        tensors.extend([batch["component"], batch["composite"]])
+    elif "composite" in batch:
+        tensors.append(batch["composite"])
+    else:
+        raise ValueError("Batch must contain 'composite' tensor for training.")
+    inputs = torch.cat(tensors, dim=0)
+    if background_mask is not None and "background" in batch:
+        background = batch["background"]
+        if background.dim() == 3:
+            background = background.unsqueeze(0)
+        if background.shape[1] != 4:
+            raise ValueError("Background tensor is expected to have 4 channels (RGBA).")
+        if background_mask.any():
+            inputs = torch.cat([inputs, background[background_mask]], dim=0)
+    return inputs
+
+
 def split_triplet_distribution(posterior):  # rgba_vae_stage.py:690-700
     chunks = torch.chunk(posterior.parameters, 3, dim=0)
     if len(chunks) != 3:

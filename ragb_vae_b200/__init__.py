@@ -9,8 +9,8 @@ _lib.load()  # no library, no package: there is no eager / CPU fallback
 
 from .autoencoder import RgbaAutoencoder  # noqa: E402
 from .losses import AlphaVaeLoss  # noqa: E402
-from .plumbing import (build_detail_augmented_triplet, pack_latents, rgba_u8_to_tensor, split_triplet_distribution,  # noqa: E402
-                       tensor_to_rgba_u8, unpack_latents)
+from .plumbing import (RandomBackgroundBlend, build_detail_augmented_triplet, build_training_batch, pack_latents,  # noqa: E402
+                       rgba_u8_to_tensor, split_triplet_distribution, tensor_to_rgba_u8, unpack_latents)
 from .posterior import DiagonalGaussianDistribution  # noqa: E402
 from .rgba_vae import (RgbaVAE, adapt_vae_to_rgba, composite_over_background, composite_over_black,  # noqa: E402
                        composite_over_white)
@@ -20,4 +20,5 @@ from .validation import compute_psnr, evaluate_rgba_vae, validation_metrics  # n
 __all__ = ["RgbaAutoencoder", "RgbaVAE", "AlphaVaeLoss", "DiagonalGaussianDistribution", "adapt_vae_to_rgba",
            "composite_over_background", "composite_over_white", "composite_over_black", "compute_psnr",
            "validation_metrics", "evaluate_rgba_vae", "build_detail_augmented_triplet", "split_triplet_distribution",
-           "pack_latents", "unpack_latents", "rgba_u8_to_tensor", "tensor_to_rgba_u8", "VaeTrainStep"]
+           "pack_latents", "unpack_latents", "rgba_u8_to_tensor", "tensor_to_rgba_u8", "VaeTrainStep", "RandomBackgroundBlend",
+           "build_training_batch"]

@@ -34,6 +34,44 @@ __global__ void __launch_bounds__(256) triplet_kernel(const T* __restrict__ x, T
   }
 }
 
+// RandomBackgroundBlend._blend_tensor (reference src/training/rgba_vae_stage.py:85-130), batched on the device: samples with
+// mask[n] != 0 become rgb*a + colour[n]*(1-a) with alpha 1, the others are copied.  Each product and the sum are rounded to
+// the tensor dtype like the reference's elementwise ops.
+template <typename T>
+__global__ void __launch_bounds__(256) background_blend_kernel(const T* __restrict__ x, const float* __restrict__ colors,
+                                                              const unsigned char* __restrict__ mask, T* __restrict__ y, int64_t hw) {
+  const int n = blockIdx.y;
+  const T* xp = x + (int64_t)n * 4 * hw;
+  T* yp = y + (int64_t)n * 4 * hw;
+  const bool on = mask[n] != 0;
+  float col[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    T cr;
+    stf(&cr, colors[n * 3 + c]);  // the reference draws the colour in the tensor dtype
+    col[c] = ldf(&cr);
+  }
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hw; i += (int64_t)gridDim.x * blockDim.x) {
+    const float a = ldf(xp + 3 * hw + i);
+    T om;
+    stf(&om, __fsub_rn(1.0f, a));
+    const float one_minus = ldf(&om);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = ldf(xp + c * hw + i);
+      if (on) {
+        T p0, p1;
+        stf(&p0, __fmul_rn(v, a));
+        stf(&p1, __fmul_rn(col[c], one_minus));
+        stf(yp + c * hw + i, __fadd_rn(ldf(&p0), ldf(&p1)));
+      } else {
+        stf(yp + c * hw + i, v);
+      }
+    }
+    stf(yp + 3 * hw + i, on ? 1.0f : a);
+  }
+}
+
 // FluxPipeline._pack_latents: (B,C,h,w) -> (B,(h/2)(w/2),4C), token = (h/2 index, w/2 index), feature = (c, dy, dx);
 // optional affine (z - shift) * scale on the way (src/models/flux_kontext_textalpha.py:330-340).
 template <typename T>
@@ -130,6 +168,22 @@ int rv_triplet_augment(const void* target, void* out, int b, int64_t hw, int dty
   else if (dtype == RV_BF16)
     rv::triplet_kernel<__nv_bfloat16><<<rv::grid_for(hw, b), 256, 0, st>>>((const __nv_bfloat16*)target, (__nv_bfloat16*)out, b, hw);
   else RV_CHECK_ARG(false, "triplet_augment: bad dtype %d", dtype);
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+int rv_background_blend(const void* x, const float* colors, const unsigned char* mask, void* y, int n, int64_t hw, int dtype,
+                        void* stream) {
+  RV_CHECK_ARG(x && colors && mask && y && n > 0 && hw > 0, "background_blend: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t es = dtype == RV_F32 ? 4 : 2;
+  rv::LaunchScope scope(rv::CAT_LAYOUT, st, 8.0 * n * hw * es);
+  if (dtype == RV_F32)
+    rv::background_blend_kernel<float><<<rv::grid_for(hw, n), 256, 0, st>>>((const float*)x, colors, mask, (float*)y, hw);
+  else if (dtype == RV_BF16)
+    rv::background_blend_kernel<__nv_bfloat16><<<rv::grid_for(hw, n), 256, 0, st>>>((const __nv_bfloat16*)x, colors, mask,
+                                                                                 (__nv_bfloat16*)y, hw);
+  else RV_CHECK_ARG(false, "background_blend: bad dtype %d", dtype);
   RV_LAUNCH_CHECK();
   return 0;
 }

@@ -1,11 +1,12 @@
 """The steps either side of the VAE on the GPU: the train step's triplet detail augmentation and
 posterior split (src/training/rgba_vae_stage.py:606-625,690-700), the Flux latent patchify of
 src/models/flux_kontext_textalpha.py:330-349, and the uint8 RGBA <-> tensor conversions of
-inference_rgba_flux.py:15-26.  Same names and errors as the reference functions; one kernel each."""
+inference_rgba_flux.py:15-26, and the batch assembly + RandomBackgroundBlend augmentation of
+rgba_vae_stage.py:85-130,575-603.  Same names and errors as the reference functions; one kernel each."""
 from __future__ import annotations
 
 import ctypes as C
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 
@@ -25,6 +26,62 @@ def build_detail_augmented_triplet(target: torch.Tensor) -> torch.Tensor:
     out = torch.empty((3 * b, 4, h, w), dtype=target.dtype, device=target.device)
     check(_lib.load().rv_triplet_augment(_ptr(target), _ptr(out), b, h * w, _dt(target), _stream(target)), "rv_triplet_augment")
     return out
+
+
+class RandomBackgroundBlend:
+    """rgba_vae_stage.py:85-130 for a whole batch on the device: each sample is, with probability ``prob``, composited
+    over a random opaque colour drawn uniformly from ``color_range`` (alpha becomes 1).  ``__call__`` takes the (B,4,H,W)
+    RGBA batch in [0,1] and returns ``(batch, background_augmented)`` -- the bool mask the reference stores per sample
+    under ``"background_augmented"``.  ``mask`` / ``colors`` can be supplied for reproducibility."""
+
+    def __init__(self, prob: float = 0.1, color_range: Tuple[float, float] = (0.2, 0.9)) -> None:
+        if color_range[0] >= color_range[1]:
+            raise ValueError("color_range lower bound must be < upper bound.")
+        self.prob = prob
+        self.color_range = tuple(float(v) for v in color_range)
+
+    def __call__(self, batch: torch.Tensor, generator=None, mask: Optional[torch.Tensor] = None,
+                 colors: Optional[torch.Tensor] = None):
+        if batch.dim() != 4 or batch.shape[1] != 4:
+            raise ValueError("background blend expects a (B,4,H,W) RGBA batch.")
+        _need_cuda(batch)
+        batch = batch.contiguous()
+        b, _, h, w = batch.shape
+        dev = batch.device
+        if mask is None:
+            mask = torch.rand(b, generator=generator, device=dev) < self.prob
+        if colors is None:
+            lo, hi = self.color_range
+            colors = torch.rand(b, 3, generator=generator, device=dev) * (hi - lo) + lo
+        mask_u8 = mask.to(device=dev, dtype=torch.uint8).contiguous()
+        colors = colors.to(device=dev, dtype=torch.float32).contiguous()
+        out = torch.empty_like(batch)
+        check(_lib.load().rv_background_blend(_ptr(batch), _ptr(colors), _ptr(mask_u8), _ptr(out), b, h * w, _dt(batch),
+                                              _stream(batch)), "rv_background_blend")
+        return out, mask_u8.bool()
+
+
+def build_training_batch(batch: dict, device, *, background_sample_prob: float = 0.0, generator=None) -> torch.Tensor:
+    """rgba_vae_stage.py:575-603: cat(component, composite) (or composite alone) on ``device``, plus the background frames
+    a Bernoulli(background_sample_prob) mask selects.  Same ValueErrors as the reference."""
+    tensors = []
+    if "component" in batch and "composite" in batch:
+        tensors.extend([batch["component"], batch["composite"]])
+    elif "composite" in batch:
+        tensors.append(batch["composite"])
+    else:
+        raise ValueError("Batch must contain 'composite' tensor for training.")
+    inputs = torch.cat([t.to(device, non_blocking=True) for t in tensors], dim=0)
+    if background_sample_prob > 0.0 and "background" in batch:
+        background = batch["background"].to(device, non_blocking=True)
+        if background.dim() == 3:
+            background = background.unsqueeze(0)
+        if background.shape[1] != 4:
+            raise ValueError("Background tensor is expected to have 4 channels (RGBA).")
+        mask = torch.rand(background.shape[0], device=device, generator=generator) < background_sample_prob
+        if mask.any():
+            inputs = torch.cat([inputs, background[mask]], dim=0)
+    return inputs
 
 
 def split_triplet_distribution(posterior: DiagonalGaussianDistribution) -> Tuple[DiagonalGaussianDistribution, ...]:

@@ -70,3 +70,44 @@ def test_uint8_ingest_egress(P):
     assert torch.equal(P.tensor_to_rgba_u8(t).cpu(), img)
     with pytest.raises(ValueError):
         P.rgba_u8_to_tensor(img[..., :3].cuda())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_random_background_blend_matches_reference_blend(P, dtype):
+    """Batched RandomBackgroundBlend vs the per-sample reference formula with the same mask and colours (bit-exact)."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(5, 4, 24, 40, generator=g).to(dtype)
+    mask = torch.tensor([True, False, True, True, False])
+    colors = torch.rand(5, 3, generator=g) * 0.6 + 0.3
+    aug = P.RandomBackgroundBlend(prob=0.5, color_range=(0.3, 0.9))
+    out, flag = aug(x.cuda(), mask=mask, colors=colors)
+    assert flag.cpu().tolist() == mask.tolist()
+    for i in range(5):
+        want = O.background_blend(x[i], colors[i]) if mask[i] else x[i]
+        assert torch.equal(out[i].cpu(), want), i
+    # random path: the fraction of augmented samples follows prob, colours stay inside the range, alpha becomes 1
+    big = torch.rand(256, 4, 4, 4, generator=g)
+    big[:, 3] = 0.0  # fully transparent: the output RGB is exactly the drawn colour
+    out, flag = P.RandomBackgroundBlend(prob=0.25, color_range=(0.3, 0.9))(big.cuda(), generator=torch.Generator("cuda").manual_seed(7))
+    frac = float(flag.float().mean())
+    assert 0.12 < frac < 0.40
+    sel = out[flag]
+    assert float(sel[:, 3].min()) == 1.0 and 0.3 <= float(sel[:, :3].min()) and float(sel[:, :3].max()) <= 0.9
+    assert torch.equal(out[~flag].cpu(), big[~flag.cpu()])
+    with pytest.raises(ValueError):
+        P.RandomBackgroundBlend(color_range=(0.9, 0.2))
+
+
+def test_build_training_batch(P):
+    g = torch.Generator().manual_seed(9)
+    comp, full, bgd = (torch.rand(2, 4, 8, 8, generator=g) for _ in range(3))
+    got = P.build_training_batch({"component": comp, "composite": full}, "cuda")
+    assert torch.equal(got.cpu(), O.build_training_batch({"component": comp, "composite": full}))
+    got = P.build_training_batch({"composite": full, "background": bgd}, "cuda", background_sample_prob=1.0)
+    assert torch.equal(got.cpu(), O.build_training_batch({"composite": full, "background": bgd}, torch.tensor([True, True])))
+    got = P.build_training_batch({"composite": full, "background": bgd[0]}, "cuda", background_sample_prob=0.0)
+    assert got.shape[0] == 2
+    with pytest.raises(ValueError):
+        P.build_training_batch({"component": comp}, "cuda")
+    with pytest.raises(ValueError):
+        P.build_training_batch({"composite": full, "background": bgd[:, :3]}, "cuda", background_sample_prob=1.0)
