@@ -149,22 +149,30 @@ class VaeTrainStep:
         for i, dst in enumerate((q, k, v)):
             self._gemm(xn2, wqkv[i * c:(i + 1) * c], rows=n * t, k=c, cols=c, x_ld=c, w_ld=c, y=dst, y_ld=c,
                        bias=bqkv[i * c:(i + 1) * c].contiguous(), bias_mode=1)
-        o = torch.empty_like(q)
         scale = ops.attn_scale(c)
-        vt = torch.empty((c, t), dtype=torch.bfloat16, device=dev)
-        q_chunk = self._q_chunk(t)
-        s = torch.empty((q_chunk, t), dtype=torch.float32, device=dev)
-        for i in range(n):
-            sl = slice(i * t, (i + 1) * t)
-            # V^T[c][token] (the PV GEMM wants the reduction axis contiguous)
-            self._gemm(wqkv[2 * c:], xn2[sl], rows=c, k=c, cols=t, x_ld=c, w_ld=c, y=vt, y_ld=t, bias=bqkv[2 * c:].contiguous(),
-                       bias_mode=2)
-            for r0 in range(0, t, q_chunk):
-                rows = min(q_chunk, t - r0)
-                self._gemm(q[i * t + r0:i * t + r0 + rows], k[sl], rows=rows, k=c, cols=t, x_ld=c, w_ld=c, y=s[:rows], y_ld=t,
-                           alpha=scale)
-                p = ops.softmax_rows(s[:rows], torch.bfloat16)
-                self._gemm(p, vt, rows=rows, k=t, cols=c, x_ld=t, w_ld=t, y=o[i * t + r0:i * t + r0 + rows], y_ld=c)
+        if self.vae.fused_attention and c == ops.FUSED_ATTENTION_D and t % 128 == 0:
+            # flash kernel: scores / probabilities never reach HBM in the forward (the backward recomputes them per block)
+            vt_all = torch.empty((n, c, t), dtype=torch.bfloat16, device=dev)
+            for i in range(n):
+                self._gemm(wqkv[2 * c:], xn2[i * t:(i + 1) * t], rows=c, k=c, cols=t, x_ld=c, w_ld=c, y=vt_all[i], y_ld=t,
+                           bias=bqkv[2 * c:].contiguous(), bias_mode=2)
+            o = ops.attention(q, k, vt_all, n, t)
+        else:
+            o = torch.empty_like(q)
+            vt = torch.empty((c, t), dtype=torch.bfloat16, device=dev)
+            q_chunk = self._q_chunk(t)
+            s = torch.empty((q_chunk, t), dtype=torch.float32, device=dev)
+            for i in range(n):
+                sl = slice(i * t, (i + 1) * t)
+                # V^T[c][token] (the PV GEMM wants the reduction axis contiguous)
+                self._gemm(wqkv[2 * c:], xn2[sl], rows=c, k=c, cols=t, x_ld=c, w_ld=c, y=vt, y_ld=t, bias=bqkv[2 * c:].contiguous(),
+                           bias_mode=2)
+                for r0 in range(0, t, q_chunk):
+                    rows = min(q_chunk, t - r0)
+                    self._gemm(q[i * t + r0:i * t + r0 + rows], k[sl], rows=rows, k=c, cols=t, x_ld=c, w_ld=c, y=s[:rows], y_ld=t,
+                               alpha=scale)
+                    p = ops.softmax_rows(s[:rows], torch.bfloat16)
+                    self._gemm(p, vt, rows=rows, k=t, cols=c, x_ld=t, w_ld=t, y=o[i * t + r0:i * t + r0 + rows], y_ld=c)
         out = torch.empty_like(x)
         self._gemm(o, wo, rows=n * t, k=c, cols=c, x_ld=c, w_ld=c, y=out.view(n * t, c), y_ld=c, bias=bo, bias_mode=1,
                    residual=x.view(n * t, c))
