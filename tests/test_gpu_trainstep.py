@@ -292,3 +292,33 @@ def test_reference_kl_term_and_full_triplet_backward(lib_built):
     _, without = O.training_step(oracle, x, noise, kl_scale=1e-6)
     enc = [n for n in want if n.startswith("encoder.")]
     assert rel(torch.cat([want[n].reshape(-1) for n in enc]), torch.cat([without[n].reshape(-1) for n in enc])) > 5e-2
+
+
+def test_training_on_a_fixed_batch_reduces_the_loss(lib_built):
+    """End-to-end sanity of backward + clip + AdamW: 60 graph-replayed steps on one fixed batch must drive the
+    reconstruction loss down, the PSNR of the reconstruction up, and keep every weight finite."""
+    import ragb_vae_b200 as R
+    from ragb_vae_b200.trainer import VaeTrainStep
+
+    oracle = O.build_oracle("qwen", seed=0)
+    vae = R.RgbaAutoencoder("qwen")
+    vae.load_state_dict(oracle.state_dict())
+    vae = vae.to("cuda", torch.bfloat16)
+    # the reference's learning rate (configs/flux_vae.yaml: 1e-5); much larger steps saturate the decoder's [-1,1] clamp of this
+    # random-init network, whose gradient is then masked to zero everywhere
+    step = VaeTrainStep(vae, lr=1e-5, kl_scale=1e-6, loss_module=R.AlphaVaeLoss(reduce_mean=True))
+    x = O.synthetic_rgba(4, 64, 64, seed=51, structured=True).cuda()
+    noise = torch.randn(4, 16, 8, 8, generator=torch.Generator().manual_seed(52)).cuda()
+    model = R.RgbaVAE(vae)
+
+    def psnr():
+        recon, _ = model(x.to(torch.bfloat16), noise=noise)
+        return float(R.validation_metrics(recon, x.to(torch.bfloat16), ("white",))["psnr_white"].mean())
+
+    p0 = psnr()
+    losses = [float(step.step_graphed(x, noise)["train/recon"]) for _ in range(60)]
+    p1 = psnr()
+    assert all(l == l for l in losses)
+    assert sum(losses[-10:]) / 10 < 0.6 * losses[0], (losses[:5], losses[-10:])
+    assert p1 > p0 + 0.5, (p0, p1)
+    assert torch.isfinite(step.opt.master).all()
