@@ -43,6 +43,13 @@ y = torch.rand(B, 4, H, W, device="cuda").bfloat16()
 timeit(lambda: ops.composite_psnr(x, y, [(1.0, 1.0, 1.0)]), 2 * x.numel() * 2, "composite+PSNR (white) + alpha MAE")
 timeit(lambda: ops.composite_psnr(x, y, [(1.0, 1.0, 1.0), (0.0, 0.0, 0.0)]), 2 * x.numel() * 2, "composite+PSNR (white+black)")
 timeit(lambda: ops.recon_loss_per_sample(x, y, (-0.0357, -0.0811, -0.1797), (0.3163, 0.3060, 0.3634)), 2 * x.numel() * 2, "AlphaVAE recon loss")
+# the same two reductions at 4x the batch: 128 MiB takes ~40 us, mostly ramp-up / tail / the finishing launch; 512 MiB shows the
+# streaming rate of the kernel itself
+xb = torch.rand(4 * B, 4, H, W, device="cuda").bfloat16()
+yb = torch.rand(4 * B, 4, H, W, device="cuda").bfloat16()
+timeit(lambda: ops.composite_psnr(xb, yb, [(1.0, 1.0, 1.0)]), 2 * xb.numel() * 2, "composite+PSNR (white), B = 32")
+timeit(lambda: ops.recon_loss_per_sample(xb, yb, (-0.0357, -0.0811, -0.1797), (0.3163, 0.3060, 0.3634)), 2 * xb.numel() * 2, "AlphaVAE recon loss, B = 32")
+del xb, yb
 mom = torch.randn(B, 32, H // 8, W // 8, device="cuda").bfloat16()
 eps = torch.randn(B, 16, H // 8, W // 8, device="cuda").bfloat16()
 timeit(lambda: ops.reparam(mom, eps), (mom.numel() + 2 * eps.numel()) * 2, "reparameterize")
