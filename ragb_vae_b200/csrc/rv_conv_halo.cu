@@ -38,7 +38,7 @@ constexpr int HL_RING = 6;
 constexpr int HL_BRING = 3;       // weight-tap ring slots of the single-CTA form
 constexpr int HL_BRING_MAX = 8;   // CTA pairs hold half a tap per slot: the same bytes give a deeper ring
 constexpr int HL_EPI_WARPS = 8;
-constexpr int HL_THREADS = 128 + 32 * HL_EPI_WARPS;  // row-TMA, MMA, weight-TMA, (idle), 8 epilogue warps
+constexpr int HL_THREADS = 128 + 32 * HL_EPI_WARPS;  // row-TMA, MMA (row 0), weight-TMA, MMA (row 1), 8 epilogue warps
 constexpr int HL_PIX = 130;                          // 128 output columns + halo
 constexpr uint32_t HL_R128_BYTES = 17408;            // 130 x 128 B rounded up to 1024
 constexpr uint32_t HL_R64_BYTES = 9216;              // 130 x 64 B rounded up to 1024
@@ -106,14 +106,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a128, const __grid_cons
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < HL_RING; ++s) {
       mbar_init(smem_u32(&bar_rowfull[s]), 1);
-      mbar_init(smem_u32(&bar_rowempty[s]), 1);
+      mbar_init(smem_u32(&bar_rowempty[s]), 2);  // released by both MMA issuers
     }
     for (int s = 0; s < p.bring_slots; ++s) {
       mbar_init(smem_u32(&bar_bfull[s]), 1);
-      mbar_init(smem_u32(&bar_bempty[s]), 1);
+      mbar_init(smem_u32(&bar_bempty[s]), 2);
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(smem_u32(&bar_accfull[a]), 1);
+      mbar_init(smem_u32(&bar_accfull[a]), 2);
       mbar_init(smem_u32(&bar_accempty[a]), PAIR ? 2 * HL_EPI_WARPS : HL_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -211,8 +211,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a128, const __grid_cons
         }
       }
     }
-  } else if (warp == 1 && leader) {
-    // ------------------------------ MMA issuer (PAIR: the leader CTA only) ------------------------------
+  } else if ((warp == 1 || warp == 3) && leader) {
+    // ------------------------------ MMA issuers (PAIR: the leader CTA only) ------------------------------
+    // Two issuing warps, one per output row of the tile (warp 1: row 0 / accumulator d0, warp 3: row 1 / d1): a tcgen05.mma costs
+    // its issuing thread a fixed ~46 cycles on top of the N/2 the tensor pipe needs, so with N = 96 one
+    // issuer leaves the pipe half idle; two independent instruction streams overlap that cost.  Every barrier an issuer releases
+    // (weight slot, accumulator, input rows) therefore counts two arrivals.
+    const int my_r = warp == 3 ? 1 : 0;
     // Everything that can be hoisted is: the four live row-slot addresses per tile, the weight-slot address
     // (advanced incrementally), descriptor high words; the 9 taps are unrolled so (dy, dx) are immediates.
     // (Uniform-datapath integer ops cost ~10 cycles each when dependent: an un-hoisted loop body of ~77 of them
@@ -244,10 +249,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a128, const __grid_cons
           const uint32_t g = g0 + 2u * j + i;
           rslot[i] = g % HL_RING;
           a_lo[i] = ((ring + rslot[i] * p.row_slot_bytes) & 0x3FFFFu) >> 4;
-          if (j == 0 || i >= 2) mbar_wait(rowfull0 + 8u * rslot[i], (g / HL_RING) & 1u);
+          if ((j == 0 || i >= 2) && i >= my_r && i <= my_r + 2) mbar_wait(rowfull0 + 8u * rslot[i], (g / HL_RING) & 1u);
         }
         tc_fence_after();
-        const uint32_t d0 = tmem_base + buf * 2u * bn, d1 = d0 + bn;
+        // the three input rows this issuer's output row reads (static indices: no local-memory array)
+        const uint32_t a3[3] = {my_r ? a_lo[1] : a_lo[0], my_r ? a_lo[2] : a_lo[1], my_r ? a_lo[3] : a_lo[2]};
+        const uint32_t d_tmem = tmem_base + buf * 2u * bn + (my_r ? bn : 0u);
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int dy = tap / 3, dx = tap - 3 * dy;
@@ -255,10 +262,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a128, const __grid_cons
           tc_fence_after();
           if (elect_one()) {
             const uint32_t b_lo = ((bring + bslot * p.b_slot_bytes) & 0x3FFFFu) >> 4;
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-              const uint32_t d_tmem = r ? d1 : d0;
-              const uint32_t ar = a_lo[dy + r];
+            {
+              const uint32_t ar = a3[dy];
 #pragma unroll
               for (int kb = 0; kb < NK128; ++kb) {
                 const uint64_t ad = hi128 | (uint64_t)(ar + kb * (HL_R128_BYTES >> 4) + dx * 8u);
