@@ -647,7 +647,7 @@ class RgbaAutoencoder(nn.Module):
             self._gemm(xn2, pk["wq"], rows=n * t, k=c, cols=c, x_ld=c, w_ld=c, y=q_all, y_ld=c, bias=pk["bq"], bias_mode=1)
             self._gemm(xn2, pk["wk"], rows=n * t, k=c, cols=c, x_ld=c, w_ld=c, y=k_all, y_ld=c, bias=pk["bk"], bias_mode=1)
             ld_qk = c
-        if tc and self.fused_attention and c == ops.FUSED_ATTENTION_D and t % 128 == 0:
+        if tc and self.fused_attention and c in ops.FUSED_ATTENTION_DIMS and t % 128 == 0:
             # flash-style kernel: scores / probabilities never reach HBM
             vt_all = torch.empty((n, c, t), dtype=act_dt, device=dev)
             for i in range(n):

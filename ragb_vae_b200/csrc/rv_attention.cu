@@ -1,4 +1,4 @@
-// Fused single-head attention for the VAE mid block (sm_100a): O = softmax(Q K^T / sqrt(d)) V, d = 384.
+// Fused single-head attention for the VAE mid block (sm_100a): O = softmax(Q K^T / sqrt(d)) V, d = 384 (Qwen) or 512 (Flux).
 //
 // Replaces scaled_dot_product_attention inside diffusers' QwenImageAttentionBlock (mid block of
 // vae.encode / vae.decode; reference call sites src/models/rgba_vae.py:277,279).  The unfused path
@@ -15,6 +15,11 @@
 //               more than 2^8), P = exp2(...) written to shared memory as the bf16 K-major SW128 A
 //               operand of the PV MMA; finally O / l -> bf16 global
 // TMEM: O 384 fp32 columns + S 128 = 512.  Shared memory: Q 96 KB + ring 80 KB + P 32 KB.
+//
+// d = 512 (diffusers Attention of the Flux AutoencoderKL mid block): O alone would fill TMEM, so the key loop runs TWICE per
+// query block, each pass producing 256 of the 512 output columns (S is recomputed: 1.5x the MMA work of an ideal kernel, still
+// no score traffic -- the unfused path moves ~100 GB for one 65 536-token image).  Q (8 chunks, 128 KB) stays resident, the
+// ring shrinks to 3 slots.
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -23,25 +28,25 @@
 
 namespace rv {
 
-constexpr int FA_D = 384;
-constexpr int FA_DCH = FA_D / 64;        // 64-wide chunks of d
 constexpr int FA_BQ = 128, FA_BK = 128;
-constexpr int FA_RING = 5;
+constexpr int FA_RING = 5;               // ring slots at d = 384 (3 at d = 512: Q takes 128 KB)
 constexpr uint32_t FA_SLOT = 16384;      // ring slot: a K chunk [128 keys x 64 d] or a V^T chunk [128 d x 64 keys]
                                          // (CTA pairs: each CTA holds half of the 128 rows, 8 KB)
-constexpr uint32_t FA_Q_BYTES = FA_DCH * 16384;
 constexpr uint32_t FA_P_BYTES = 2 * 16384;
 constexpr int FA_NSPLIT = 4;             // softmax warps per TMEM lane quarter (each owns 128/NSPLIT keys of a block)
 constexpr int FA_SM_WARPS = 4 * FA_NSPLIT;
 constexpr int FA_THREADS = 64 + 32 * FA_SM_WARPS;   // warps: 0 TMA, 1 MMA, 2.. softmax
 constexpr int FA_KCOLS = 128 / FA_NSPLIT;  // S columns per softmax thread
-constexpr int FA_OCOLS = FA_D / FA_NSPLIT; // O columns per softmax thread (rescale / output)
 constexpr float FA_RESCALE_THRESHOLD = 8.0f;
 
 struct FaParams {
   int tokens;          // per image, multiple of 128
   int n_img;
   int ld_out;          // row pitch of O in elements
+  int dch;             // 64-wide chunks of d (6 or 8)
+  int oparts;          // N = 128 parts of O per pass (3: d = 384 in one pass; 2: d = 512 in two passes of 256 columns)
+  int npass;
+  int ring;            // K / V^T ring slots
   float scale_log2;    // 1/sqrt(d) * log2(e)
   __nv_bfloat16* out;  // [n_img*tokens][ld_out]
 };
@@ -84,7 +89,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t q_smem = base, ring = base + FA_Q_BYTES, p_smem = ring + FA_RING * FA_SLOT;
+  const uint32_t q_bytes = (uint32_t)p.dch * 16384u;
+  const uint32_t q_smem = base, ring = base + q_bytes, p_smem = ring + (uint32_t)p.ring * FA_SLOT;
+  const uint32_t nring = (uint32_t)p.ring;
+  const int ocols = p.oparts * 128 / FA_NSPLIT;  // O columns per softmax thread (rescale / output)
   const int nb = p.tokens / FA_BK;
   const int qblocks = p.tokens / FA_BQ;
   const int img = blockIdx.x / qblocks;
@@ -96,7 +104,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
   if (warp == 0 && lane == 0) {
     mbar_init(smem_u32(&bar_q), 1);
-    for (int s = 0; s < FA_RING; ++s) {
+    for (int s = 0; s < p.ring; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
@@ -135,18 +143,19 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
-      if (leader) mbar_arrive_expect_tx(qbar, FA_Q_BYTES * nshare);
-      for (int c = 0; c < FA_DCH; ++c) {
+      if (leader) mbar_arrive_expect_tx(qbar, q_bytes * nshare);
+      for (int c = 0; c < p.dch; ++c) {
         if (PAIR) tma2_load_2d(q_smem + c * 16384u, &map_q, lead_q, c * 64, img * p.tokens + q0);
         else tma_load_2d(q_smem + c * 16384u, &map_q, qbar, c * 64, img * p.tokens + q0);
       }
     }
     __syncwarp();
     uint32_t slot = 0, par = 0;
-    // consumption order: K(0), K(1), V(0), K(2), V(1), ..., K(nb-1), V(nb-2), V(nb-1)
+    // consumption order per pass: K(0), K(1), V(0), K(2), V(1), ..., K(nb-1), V(nb-2), V(nb-1)
+    for (int pass = 0; pass < p.npass; ++pass)
     for (int step = 0; step <= nb; ++step) {
       if (step < nb) {
-        for (int c = 0; c < FA_DCH; ++c) {
+        for (int c = 0; c < p.dch; ++c) {
           mbar_wait(empty0 + 8u * slot, par ^ 1u);
           if (elect_one()) {
             if (leader) mbar_arrive_expect_tx(full0 + 8u * slot, slot_bytes * nshare);
@@ -157,24 +166,25 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
               tma_load_2d(ring + slot * slot_bytes, &map_k, full0 + 8u * slot, c * 64, img * p.tokens + step * FA_BK);
           }
           __syncwarp();
-          if (++slot == FA_RING) { slot = 0; par ^= 1u; }
+          if (++slot == nring) { slot = 0; par ^= 1u; }
         }
       }
       if (step >= 1) {
         const int j = step - 1;
+        const int vrow0 = pass * p.oparts * 128;  // first d-row (output column) of this pass
         for (int kc = 0; kc < 2; ++kc)
-          for (int h = 0; h < 3; ++h) {
+          for (int h = 0; h < p.oparts; ++h) {
             mbar_wait(empty0 + 8u * slot, par ^ 1u);
             if (elect_one()) {
               if (leader) mbar_arrive_expect_tx(full0 + 8u * slot, slot_bytes * nshare);
               if (PAIR)  // this CTA's 64 of the 128 d-rows of the chunk
                 tma2_load_3d(ring + slot * slot_bytes, &map_vt, lead_full0 + 8u * slot, j * FA_BK + kc * 64,
-                             h * 128 + (int)rank * 64, img);
+                             vrow0 + h * 128 + (int)rank * 64, img);
               else
-                tma_load_3d(ring + slot * slot_bytes, &map_vt, full0 + 8u * slot, j * FA_BK + kc * 64, h * 128, img);
+                tma_load_3d(ring + slot * slot_bytes, &map_vt, full0 + 8u * slot, j * FA_BK + kc * 64, vrow0 + h * 128, img);
             }
             __syncwarp();
-            if (++slot == FA_RING) { slot = 0; par ^= 1u; }
+            if (++slot == nring) { slot = 0; par ^= 1u; }
           }
       }
     }
@@ -197,8 +207,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     if (leader) {
     mbar_wait(qbar, 0);
     auto issue_qk = [&](int j) {
-      // S = Q K(j)^T : 6 chunks x 4 k-steps, N = 128
-      for (int c = 0; c < FA_DCH; ++c) {
+      // S = Q K(j)^T : dch chunks x 4 k-steps, N = 128
+      for (int c = 0; c < p.dch; ++c) {
         mbar_wait(full0 + 8u * slot, par);
         tc_fence_after();
         if (elect_one()) {
@@ -209,24 +219,32 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           mma(s_tmem, ad + 4u, bd + 4u, idesc_s, 1u);
           mma(s_tmem, ad + 6u, bd + 6u, idesc_s, 1u);
           commit(empty0 + 8u * slot);
-          if (c == FA_DCH - 1) commit(sfull);
+          if (c == p.dch - 1) commit(sfull);
         }
         __syncwarp();
-        if (++slot == FA_RING) { slot = 0; par ^= 1u; }
+        if (++slot == nring) { slot = 0; par ^= 1u; }
       }
       (void)j;
     };
-    issue_qk(0);
-    for (int j = 0; j < nb; ++j) {
+    // jj counts key blocks over all passes: every barrier flips once per block, so its phase is jj & 1
+    for (int pass = 0, jj = 0; pass < p.npass; ++pass)
+    for (int j = 0; j < nb; ++j, ++jj) {
+      if (j == 0) {
+        if (jj > 0) {  // next pass: the softmax warps have taken the previous pass's last S
+          mbar_wait(sempty, (uint32_t)((jj - 1) & 1));
+          tc_fence_after();
+        }
+        issue_qk(0);
+      }
       if (j + 1 < nb) {
-        mbar_wait(sempty, (uint32_t)(j & 1));   // S(j) is in registers: the S columns may be overwritten
+        mbar_wait(sempty, (uint32_t)(jj & 1));   // S(j) is in registers: the S columns may be overwritten
         tc_fence_after();
         issue_qk(j + 1);
       }
-      mbar_wait(pfull, (uint32_t)(j & 1));      // P(j) is in shared memory (and O has been rescaled if needed)
+      mbar_wait(pfull, (uint32_t)(jj & 1));      // P(j) is in shared memory (and O has been rescaled if needed)
       tc_fence_after();
       for (int kc = 0; kc < 2; ++kc)
-        for (int h = 0; h < 3; ++h) {
+        for (int h = 0; h < p.oparts; ++h) {
           mbar_wait(full0 + 8u * slot, par);
           tc_fence_after();
           if (elect_one()) {
@@ -238,10 +256,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             mma(d_tmem, ad + 4u, bd + 4u, idesc_o, 1u);
             mma(d_tmem, ad + 6u, bd + 6u, idesc_o, 1u);
             commit(empty0 + 8u * slot);
-            if (kc == 1 && h == 2) commit(pvdone);
+            if (kc == 1 && h == p.oparts - 1) commit(pvdone);
           }
           __syncwarp();
-          if (++slot == FA_RING) { slot = 0; par ^= 1u; }
+          if (++slot == nring) { slot = 0; par ^= 1u; }
         }
     }
     }  // leader
@@ -251,98 +269,104 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t s_taddr = lane_addr + 384u + (uint32_t)part * FA_KCOLS;
-    const uint32_t o_taddr = lane_addr + (uint32_t)part * FA_OCOLS;
+    const uint32_t o_taddr = lane_addr + (uint32_t)(part * ocols);
     const int bar_id = 1 + q;
-    float m_used = -INFINITY, l = 0.f;
     // P row: key chunk (64 keys, 16 KB) part/2, 16-byte units (part%2)*4 .. +4 of the row; unit u lives at ((u ^ (row & 7)) * 16)
     const uint32_t p_row = p_smem + (uint32_t)(part >> 1) * 16384u + (uint32_t)row * 128u;
     const uint32_t u0 = (uint32_t)(part & 1) * 4u;
     const uint32_t sw = (uint32_t)(row & 7);
-    for (int j = 0; j < nb; ++j) {
-      mbar_wait(sfull, (uint32_t)(j & 1));
-      tc_fence_after();
-      uint32_t s0[FA_KCOLS];
-      tmem_ld32(s_taddr, s0);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) { if (PAIR) mbar_arrive_cluster(lead_sempty); else mbar_arrive(sempty); }
-      float mx = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < FA_KCOLS; ++i) mx = fmaxf(mx, __uint_as_float(s0[i]));
-      s_xmax[j & 1][part][row] = mx;
-      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * FA_NSPLIT) : "memory");
-#pragma unroll
-      for (int pp = 0; pp < FA_NSPLIT; ++pp) mx = fmaxf(mx, s_xmax[j & 1][pp][row]);
-      mx *= p.scale_log2;
-      float alpha = 1.0f;
-      bool need = false;
-      if (j == 0) {
-        m_used = mx;
-      } else if (mx - m_used > FA_RESCALE_THRESHOLD) {
-        alpha = fast_exp2(m_used - mx);
-        m_used = mx;
-        l *= alpha;
-        need = true;
-      }
-      // probabilities (bf16) and their row sum
-      uint32_t pk[FA_KCOLS / 2];
-      float sum = 0.f;
-#pragma unroll
-      for (int i = 0; i < FA_KCOLS / 2; ++i) {
-        const float a = fast_exp2(fmaf(__uint_as_float(s0[2 * i]), p.scale_log2, -m_used));
-        const float b = fast_exp2(fmaf(__uint_as_float(s0[2 * i + 1]), p.scale_log2, -m_used));
-        pk[i] = pack_bf16x2(a, b);
-        sum += a + b;
-      }
-      l += sum;
-      // the previous PV must be complete before P is overwritten or O is rescaled
-      if (j > 0) {
-        mbar_wait(pvdone, (uint32_t)((j - 1) & 1));
+    for (int pass = 0, jj = 0; pass < p.npass; ++pass) {
+      float m_used = -INFINITY, l = 0.f;
+      for (int j = 0; j < nb; ++j, ++jj) {
+        mbar_wait(sfull, (uint32_t)(jj & 1));
         tc_fence_after();
-        if (__any_sync(0xffffffffu, need)) {
-          for (int c = 0; c < FA_OCOLS / 32; ++c) {
-            uint32_t o[32];
-            tmem_ld32(o_taddr + (uint32_t)c * 32u, o);
-            tmem_ld_wait();
+        uint32_t s0[FA_KCOLS];
+        tmem_ld32(s_taddr, s0);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(lead_sempty); else mbar_arrive(sempty); }
+        float mx = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(o_taddr + (uint32_t)c * 32u, o);
-          }
-          tmem_st_wait();
+        for (int i = 0; i < FA_KCOLS; ++i) mx = fmaxf(mx, __uint_as_float(s0[i]));
+        s_xmax[jj & 1][part][row] = mx;
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * FA_NSPLIT) : "memory");
+#pragma unroll
+        for (int pp = 0; pp < FA_NSPLIT; ++pp) mx = fmaxf(mx, s_xmax[jj & 1][pp][row]);
+        mx *= p.scale_log2;
+        float alpha = 1.0f;
+        bool need = false;
+        if (j == 0) {
+          m_used = mx;
+        } else if (mx - m_used > FA_RESCALE_THRESHOLD) {
+          alpha = fast_exp2(m_used - mx);
+          m_used = mx;
+          l *= alpha;
+          need = true;
         }
-      }
+        // probabilities (bf16) and their row sum
+        uint32_t pk[FA_KCOLS / 2];
+        float sum = 0.f;
 #pragma unroll
-      for (int u = 0; u < FA_KCOLS / 8; ++u) {
-        const uint32_t addr = p_row + (((u0 + (uint32_t)u) ^ sw) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]),
-                     "r"(pk[4 * u + 3])
-                     : "memory");
+        for (int i = 0; i < FA_KCOLS / 2; ++i) {
+          const float a = fast_exp2(fmaf(__uint_as_float(s0[2 * i]), p.scale_log2, -m_used));
+          const float b = fast_exp2(fmaf(__uint_as_float(s0[2 * i + 1]), p.scale_log2, -m_used));
+          pk[i] = pack_bf16x2(a, b);
+          sum += a + b;
+        }
+        l += sum;
+        // the previous PV must be complete before P is overwritten or O is rescaled (block 0 of a later pass: already
+        // waited for in the previous pass's output stage)
+        if (j > 0) {
+          mbar_wait(pvdone, (uint32_t)((jj - 1) & 1));
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, need)) {
+            for (int c = 0; c < ocols / 32; ++c) {
+              uint32_t o[32];
+              tmem_ld32(o_taddr + (uint32_t)c * 32u, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(o_taddr + (uint32_t)c * 32u, o);
+            }
+            tmem_st_wait();
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < FA_KCOLS / 8; ++u) {
+          const uint32_t addr = p_row + (((u0 + (uint32_t)u) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]),
+                       "r"(pk[4 * u + 3])
+                       : "memory");
+        }
+        if (PAIR) asm volatile("fence.proxy.async;" ::: "memory");
+        else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(lead_pfull); else mbar_arrive(pfull); }
       }
-      if (PAIR) asm volatile("fence.proxy.async;" ::: "memory");
-      else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      // ---- output of this pass: O / l into columns [pass * oparts * 128, ...) ----
+      s_xsum[part][row] = l;
+      mbar_wait(pvdone, (uint32_t)((jj - 1) & 1));
+      tc_fence_after();
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * FA_NSPLIT) : "memory");
+      float lt = 0.f;
+#pragma unroll
+      for (int pp = 0; pp < FA_NSPLIT; ++pp) lt += s_xsum[pp][row];
+      const float inv = 1.0f / lt;
+      __nv_bfloat16* orow = p.out + ((int64_t)img * p.tokens + q0 + row) * p.ld_out + pass * p.oparts * 128 + part * ocols;
+      for (int c = 0; c < ocols / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld32(o_taddr + (uint32_t)c * 32u, o);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(o[i]) * inv;
+        fast_store<32>(orow + c * 32, v);
+      }
+      // the next pass rewrites s_xsum and (through the MMA warp, after this thread's next pfull arrive) the O columns
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) { if (PAIR) mbar_arrive_cluster(lead_pfull); else mbar_arrive(pfull); }
-    }
-    // ---- output: O / l ----
-    s_xsum[part][row] = l;
-    mbar_wait(pvdone, (uint32_t)((nb - 1) & 1));
-    tc_fence_after();
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * FA_NSPLIT) : "memory");
-    float lt = 0.f;
-#pragma unroll
-    for (int pp = 0; pp < FA_NSPLIT; ++pp) lt += s_xsum[pp][row];
-    const float inv = 1.0f / lt;
-    __nv_bfloat16* orow = p.out + ((int64_t)img * p.tokens + q0 + row) * p.ld_out + part * FA_OCOLS;
-    for (int c = 0; c < FA_OCOLS / 32; ++c) {
-      uint32_t o[32];
-      tmem_ld32(o_taddr + (uint32_t)c * 32u, o);
-      tmem_ld_wait();
-      float v[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(o[i]) * inv;
-      fast_store<32>(orow + c * 32, v);
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * FA_NSPLIT) : "memory");
     }
   }
 
@@ -371,7 +395,7 @@ extern "C" int rv_attention(const void* q, const void* k, int64_t ld_qk, const v
   using namespace rv;
   if (int rc = tc_ensure_init()) return rc;
   RV_CHECK_ARG(q && k && vt && out && n_img > 0 && tokens > 0, "attention: bad argument");
-  RV_CHECK_ARG(d == FA_D, "attention: the fused kernel is built for d = %d (got %d)", FA_D, d);
+  RV_CHECK_ARG(d == 384 || d == 512, "attention: the fused kernel is built for d = 384 or 512 (got %d)", d);
   RV_CHECK_ARG(tokens % 128 == 0, "attention: tokens (%d) must be a multiple of 128", tokens);
   RV_CHECK_ARG(ld_qk % 8 == 0 && ld_out % 8 == 0 && ld_qk >= d && ld_out >= d, "attention: pitches must be multiples of 8 and >= d");
   RV_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)vt % 16 == 0) && ((uintptr_t)out % 16 == 0),
@@ -397,14 +421,16 @@ extern "C" int rv_attention(const void* q, const void* k, int64_t ld_qk, const v
     cuuint32_t box[3] = {64, 128u / share, 1};
     if (int rc = tc_encode_map(&mv, vt, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   }
-  const size_t smem = FA_Q_BYTES + FA_RING * FA_SLOT + FA_P_BYTES + 1024;
+  const int ring_slots = d == 384 ? FA_RING : 3;
+  const size_t smem = (size_t)(d / 64) * 16384 + (size_t)ring_slots * FA_SLOT + FA_P_BYTES + 1024;
   {
     std::lock_guard<std::mutex> lk(g_fa_mu);
     int dev = 0;
     RV_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !g_fa_attr[dev]) {
-      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int smem_max = 6 * 16384 + FA_RING * (int)FA_SLOT + (int)FA_P_BYTES + 1024;  // d = 384: 214 016 B; d = 512 needs the same
+      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
       g_fa_attr[dev] = true;
     }
   }
@@ -412,6 +438,10 @@ extern "C" int rv_attention(const void* q, const void* k, int64_t ld_qk, const v
   p.tokens = tokens;
   p.n_img = n_img;
   p.ld_out = (int)ld_out;
+  p.dch = d / 64;
+  p.oparts = d == 384 ? 3 : 2;
+  p.npass = d == 384 ? 1 : 2;
+  p.ring = ring_slots;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
   p.out = (__nv_bfloat16*)out;
   const int grid = n_img * (tokens / FA_BQ);

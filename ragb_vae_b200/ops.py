@@ -158,7 +158,8 @@ def groupnorm_silu(x: torch.Tensor, gamma, beta, groups: int = 32, eps: float = 
     return y
 
 
-FUSED_ATTENTION_D = 384
+FUSED_ATTENTION_D = 384            # Qwen-Image mid block
+FUSED_ATTENTION_DIMS = (384, 512)  # + the Flux AutoencoderKL mid block (two output passes inside the kernel)
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, n_img: int, tokens: int) -> torch.Tensor:

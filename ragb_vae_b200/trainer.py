@@ -150,7 +150,7 @@ class VaeTrainStep:
             self._gemm(xn2, wqkv[i * c:(i + 1) * c], rows=n * t, k=c, cols=c, x_ld=c, w_ld=c, y=dst, y_ld=c,
                        bias=bqkv[i * c:(i + 1) * c].contiguous(), bias_mode=1)
         scale = ops.attn_scale(c)
-        if self.vae.fused_attention and c == ops.FUSED_ATTENTION_D and t % 128 == 0:
+        if self.vae.fused_attention and c in ops.FUSED_ATTENTION_DIMS and t % 128 == 0:
             # flash kernel: scores / probabilities never reach HBM in the forward (the backward recomputes them per block)
             vt_all = torch.empty((n, c, t), dtype=torch.bfloat16, device=dev)
             for i in range(n):

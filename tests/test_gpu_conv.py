@@ -172,10 +172,10 @@ def test_tc_conv_fused_rmsnorm_epilogue(ops, cout, want_raw, silu, w):
                            torch.ones(384, device="cuda"), True)
 
 
+@pytest.mark.parametrize("d", [384, 512])  # Qwen-Image mid block; Flux mid block (two output passes inside the kernel)
 @pytest.mark.parametrize("n_img,tokens", [(1, 128), (2, 512), (1, 2048)])
 @pytest.mark.parametrize("scale_up", [1.0, 6.0])  # larger scores exercise the lazy-rescale path
-def test_fused_attention(ops, n_img, tokens, scale_up):
-    d = 384
+def test_fused_attention(ops, n_img, tokens, scale_up, d):
     g = torch.Generator().manual_seed(tokens + n_img)
     qk = (torch.randn(n_img * tokens, 2 * d, generator=g) * scale_up).bfloat16()
     # make the row maxima grow along the key axis so that several rescales happen
