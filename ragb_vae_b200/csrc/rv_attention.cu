@@ -43,10 +43,6 @@ struct FaParams {
   int tokens;          // per image, multiple of 128
   int n_img;
   int ld_out;          // row pitch of O in elements
-  int dch;             // 64-wide chunks of d (6 or 8)
-  int oparts;          // N = 128 parts of O per pass (3: d = 384 in one pass; 2: d = 512 in two passes of 256 columns)
-  int npass;
-  int ring;            // K / V^T ring slots
   float scale_log2;    // 1/sqrt(d) * log2(e)
   __nv_bfloat16* out;  // [n_img*tokens][ld_out]
 };
@@ -77,7 +73,9 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 
 // PAIR: two CTAs (256 queries) issue M = 256 MMAs and split every K / V^T chunk between their shared memories
 // (cta_group::2), which halves the B-operand reads that bound the single-CTA form.
-template <bool PAIR>
+// DCH: 64-wide chunks of d; OPARTS: N = 128 parts of O per pass; NPASS: key-loop passes; RING: K / V^T ring slots
+// (6, 3, 1, 5 for d = 384; 8, 2, 2, 3 for d = 512) -- compile-time so that the d = 384 loops stay fully unrolled
+template <bool PAIR, int DCH, int OPARTS, int NPASS, int RING>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                   const __grid_constant__ CUtensorMap map_vt, const __grid_constant__ FaParams p) {
@@ -89,10 +87,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t q_bytes = (uint32_t)p.dch * 16384u;
-  const uint32_t q_smem = base, ring = base + q_bytes, p_smem = ring + (uint32_t)p.ring * FA_SLOT;
-  const uint32_t nring = (uint32_t)p.ring;
-  const int ocols = p.oparts * 128 / FA_NSPLIT;  // O columns per softmax thread (rescale / output)
+  constexpr uint32_t q_bytes = (uint32_t)DCH * 16384u;
+  const uint32_t q_smem = base, ring = base + q_bytes, p_smem = ring + (uint32_t)RING * FA_SLOT;
+  constexpr uint32_t nring = (uint32_t)RING;
+  constexpr int ocols = OPARTS * 128 / FA_NSPLIT;  // O columns per softmax thread (rescale / output)
   const int nb = p.tokens / FA_BK;
   const int qblocks = p.tokens / FA_BQ;
   const int img = blockIdx.x / qblocks;
@@ -104,7 +102,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
   if (warp == 0 && lane == 0) {
     mbar_init(smem_u32(&bar_q), 1);
-    for (int s = 0; s < p.ring; ++s) {
+    for (int s = 0; s < RING; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
@@ -144,7 +142,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
       if (leader) mbar_arrive_expect_tx(qbar, q_bytes * nshare);
-      for (int c = 0; c < p.dch; ++c) {
+      for (int c = 0; c < DCH; ++c) {
         if (PAIR) tma2_load_2d(q_smem + c * 16384u, &map_q, lead_q, c * 64, img * p.tokens + q0);
         else tma_load_2d(q_smem + c * 16384u, &map_q, qbar, c * 64, img * p.tokens + q0);
       }
@@ -152,10 +150,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     __syncwarp();
     uint32_t slot = 0, par = 0;
     // consumption order per pass: K(0), K(1), V(0), K(2), V(1), ..., K(nb-1), V(nb-2), V(nb-1)
-    for (int pass = 0; pass < p.npass; ++pass)
+    for (int pass = 0; pass < NPASS; ++pass)
     for (int step = 0; step <= nb; ++step) {
       if (step < nb) {
-        for (int c = 0; c < p.dch; ++c) {
+        for (int c = 0; c < DCH; ++c) {
           mbar_wait(empty0 + 8u * slot, par ^ 1u);
           if (elect_one()) {
             if (leader) mbar_arrive_expect_tx(full0 + 8u * slot, slot_bytes * nshare);
@@ -171,9 +169,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
       if (step >= 1) {
         const int j = step - 1;
-        const int vrow0 = pass * p.oparts * 128;  // first d-row (output column) of this pass
+        const int vrow0 = pass * OPARTS * 128;  // first d-row (output column) of this pass
         for (int kc = 0; kc < 2; ++kc)
-          for (int h = 0; h < p.oparts; ++h) {
+          for (int h = 0; h < OPARTS; ++h) {
             mbar_wait(empty0 + 8u * slot, par ^ 1u);
             if (elect_one()) {
               if (leader) mbar_arrive_expect_tx(full0 + 8u * slot, slot_bytes * nshare);
@@ -208,7 +206,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     mbar_wait(qbar, 0);
     auto issue_qk = [&](int j) {
       // S = Q K(j)^T : dch chunks x 4 k-steps, N = 128
-      for (int c = 0; c < p.dch; ++c) {
+      for (int c = 0; c < DCH; ++c) {
         mbar_wait(full0 + 8u * slot, par);
         tc_fence_after();
         if (elect_one()) {
@@ -219,7 +217,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           mma(s_tmem, ad + 4u, bd + 4u, idesc_s, 1u);
           mma(s_tmem, ad + 6u, bd + 6u, idesc_s, 1u);
           commit(empty0 + 8u * slot);
-          if (c == p.dch - 1) commit(sfull);
+          if (c == DCH - 1) commit(sfull);
         }
         __syncwarp();
         if (++slot == nring) { slot = 0; par ^= 1u; }
@@ -227,7 +225,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       (void)j;
     };
     // jj counts key blocks over all passes: every barrier flips once per block, so its phase is jj & 1
-    for (int pass = 0, jj = 0; pass < p.npass; ++pass)
+    for (int pass = 0, jj = 0; pass < NPASS; ++pass)
     for (int j = 0; j < nb; ++j, ++jj) {
       if (j == 0) {
         if (jj > 0) {  // next pass: the softmax warps have taken the previous pass's last S
@@ -244,7 +242,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       mbar_wait(pfull, (uint32_t)(jj & 1));      // P(j) is in shared memory (and O has been rescaled if needed)
       tc_fence_after();
       for (int kc = 0; kc < 2; ++kc)
-        for (int h = 0; h < p.oparts; ++h) {
+        for (int h = 0; h < OPARTS; ++h) {
           mbar_wait(full0 + 8u * slot, par);
           tc_fence_after();
           if (elect_one()) {
@@ -256,7 +254,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             mma(d_tmem, ad + 4u, bd + 4u, idesc_o, 1u);
             mma(d_tmem, ad + 6u, bd + 6u, idesc_o, 1u);
             commit(empty0 + 8u * slot);
-            if (kc == 1 && h == p.oparts - 1) commit(pvdone);
+            if (kc == 1 && h == OPARTS - 1) commit(pvdone);
           }
           __syncwarp();
           if (++slot == nring) { slot = 0; par ^= 1u; }
@@ -275,7 +273,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const uint32_t p_row = p_smem + (uint32_t)(part >> 1) * 16384u + (uint32_t)row * 128u;
     const uint32_t u0 = (uint32_t)(part & 1) * 4u;
     const uint32_t sw = (uint32_t)(row & 7);
-    for (int pass = 0, jj = 0; pass < p.npass; ++pass) {
+    for (int pass = 0, jj = 0; pass < NPASS; ++pass) {
       float m_used = -INFINITY, l = 0.f;
       for (int j = 0; j < nb; ++j, ++jj) {
         mbar_wait(sfull, (uint32_t)(jj & 1));
@@ -354,7 +352,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #pragma unroll
       for (int pp = 0; pp < FA_NSPLIT; ++pp) lt += s_xsum[pp][row];
       const float inv = 1.0f / lt;
-      __nv_bfloat16* orow = p.out + ((int64_t)img * p.tokens + q0 + row) * p.ld_out + pass * p.oparts * 128 + part * ocols;
+      __nv_bfloat16* orow = p.out + ((int64_t)img * p.tokens + q0 + row) * p.ld_out + pass * OPARTS * 128 + part * ocols;
       for (int c = 0; c < ocols / 32; ++c) {
         uint32_t o[32];
         tmem_ld32(o_taddr + (uint32_t)c * 32u, o);
@@ -364,9 +362,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(o[i]) * inv;
         fast_store<32>(orow + c * 32, v);
       }
-      // the next pass rewrites s_xsum and (through the MMA warp, after this thread's next pfull arrive) the O columns
-      tc_fence_before();
-      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * FA_NSPLIT) : "memory");
+      if (pass + 1 < NPASS) {  // the next pass rewrites s_xsum and (through the MMA warp, after this thread's next pfull arrive) O
+        tc_fence_before();
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * FA_NSPLIT) : "memory");
+      }
     }
   }
 
@@ -429,8 +428,10 @@ extern "C" int rv_attention(const void* q, const void* k, int64_t ld_qk, const v
     RV_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !g_fa_attr[dev]) {
       const int smem_max = 6 * 16384 + FA_RING * (int)FA_SLOT + (int)FA_P_BYTES + 1024;  // d = 384: 214 016 B; d = 512 needs the same
-      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<false, 6, 3, 1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<true, 6, 3, 1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<false, 8, 2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<true, 8, 2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
       g_fa_attr[dev] = true;
     }
   }
@@ -438,10 +439,6 @@ extern "C" int rv_attention(const void* q, const void* k, int64_t ld_qk, const v
   p.tokens = tokens;
   p.n_img = n_img;
   p.ld_out = (int)ld_out;
-  p.dch = d / 64;
-  p.oparts = d == 384 ? 3 : 2;
-  p.npass = d == 384 ? 1 : 2;
-  p.ring = ring_slots;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
   p.out = (__nv_bfloat16*)out;
   const int grid = n_img * (tokens / FA_BQ);
@@ -459,9 +456,11 @@ extern "C" int rv_attention(const void* q, const void* k, int64_t ld_qk, const v
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RV_CUDA(cudaLaunchKernelEx(&cfg, flash_attn_kernel<true>, mq, mk, mv, p));
+    if (d == 384) RV_CUDA(cudaLaunchKernelEx(&cfg, flash_attn_kernel<true, 6, 3, 1, 5>, mq, mk, mv, p));
+    else RV_CUDA(cudaLaunchKernelEx(&cfg, flash_attn_kernel<true, 8, 2, 2, 3>, mq, mk, mv, p));
   } else {
-    flash_attn_kernel<false><<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, p);
+    if (d == 384) flash_attn_kernel<false, 6, 3, 1, 5><<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, p);
+    else flash_attn_kernel<false, 8, 2, 2, 3><<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, p);
   }
   RV_LAUNCH_CHECK();
   return 0;
