@@ -9,7 +9,10 @@
 //   warp 0      TMA producer: Q once (6 x [128 x 64] SW128 chunks), then per key block the K chunks
 //               (6 x 16 KB) and V^T chunks (6 x [128 d x 64 keys] = 16 KB) through one 5-slot ring,
 //               in exactly the order the MMA warp consumes them
-//   warp 1      tcgen05.mma issuer: S = Q K^T into TMEM columns [384, 512), O += P V into [0, 384)
+//   warp 1      tcgen05.mma issuer for S = Q K^T into TMEM columns [384, 512)
+//   warp 18     tcgen05.mma issuer for O += P V into [0, 384): two issuing threads, because a tcgen05.mma costs its issuer a
+//               fixed ~46 cycles on top of the N/2 the tensor pipe needs -- with one issuer the 48 N = 128
+//               MMAs of a key block serialise that cost; S(j+1) and O(j) are independent accumulators, so the two streams overlap
 //   warps 2-17  softmax (thread = query row; the four warps of a lane quarter split the 128 keys):
 //               S -> registers, running max with lazy rescale (O is only rescaled when the max grows by
 //               more than 2^8), P = exp2(...) written to shared memory as the bf16 K-major SW128 A
@@ -35,7 +38,8 @@ constexpr uint32_t FA_SLOT = 16384;      // ring slot: a K chunk [128 keys x 64 
 constexpr uint32_t FA_P_BYTES = 2 * 16384;
 constexpr int FA_NSPLIT = 4;             // softmax warps per TMEM lane quarter (each owns 128/NSPLIT keys of a block)
 constexpr int FA_SM_WARPS = 4 * FA_NSPLIT;
-constexpr int FA_THREADS = 64 + 32 * FA_SM_WARPS;   // warps: 0 TMA, 1 MMA, 2.. softmax
+constexpr int FA_THREADS = 96 + 32 * FA_SM_WARPS;   // warps: 0 TMA, 1 MMA (S = Q K^T), 2..17 softmax, 18 MMA (O += P V)
+constexpr int FA_PV_WARP = 2 + FA_SM_WARPS;
 constexpr int FA_KCOLS = 128 / FA_NSPLIT;  // S columns per softmax thread
 constexpr float FA_RESCALE_THRESHOLD = 8.0f;
 
@@ -80,7 +84,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                   const __grid_constant__ CUtensorMap map_vt, const __grid_constant__ FaParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_q, bar_full[FA_RING], bar_empty[FA_RING], bar_sfull, bar_sempty, bar_pfull, bar_pvdone;
+  // One operand ring, two consumers (the S and the O issuer): a slot's "full" signal goes to the barrier of the KIND of chunk it
+  // holds, so each consumer's parity wait can only ever see its own loads (with one shared barrier per slot a consumer that is
+  // a whole phase behind would alias phases k and k+2).
+  __shared__ __align__(8) uint64_t bar_q, bar_fullk[FA_RING], bar_fullv[FA_RING], bar_empty[FA_RING], bar_sfull, bar_sempty, bar_pfull,
+      bar_pvdone;
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_xmax[2][FA_NSPLIT][128];  // [block parity][column part][row]
   __shared__ float s_xsum[FA_NSPLIT][128];
@@ -103,7 +111,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   if (warp == 0 && lane == 0) {
     mbar_init(smem_u32(&bar_q), 1);
     for (int s = 0; s < RING; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_fullk[s]), 1);
+      mbar_init(smem_u32(&bar_fullv[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     mbar_init(smem_u32(&bar_sfull), 1);
@@ -129,11 +138,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   if (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
-  const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
+  const uint32_t fullk0 = smem_u32(&bar_fullk[0]), fullv0 = smem_u32(&bar_fullv[0]), empty0 = smem_u32(&bar_empty[0]);
   const uint32_t sfull = smem_u32(&bar_sfull), sempty = smem_u32(&bar_sempty), pfull = smem_u32(&bar_pfull),
                  pvdone = smem_u32(&bar_pvdone), qbar = smem_u32(&bar_q);
   // barriers the MMA issuer (leader CTA) waits on, as cluster addresses, for signals that come from both CTAs
-  const uint32_t lead_full0 = PAIR ? mapa_rank(full0, 0) : full0;
+  const uint32_t lead_fullk0 = PAIR ? mapa_rank(fullk0, 0) : fullk0;
+  const uint32_t lead_fullv0 = PAIR ? mapa_rank(fullv0, 0) : fullv0;
   const uint32_t lead_q = PAIR ? mapa_rank(qbar, 0) : qbar;
   const uint32_t lead_sempty = PAIR ? mapa_rank(sempty, 0) : sempty;
   const uint32_t lead_pfull = PAIR ? mapa_rank(pfull, 0) : pfull;
@@ -156,12 +166,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int c = 0; c < DCH; ++c) {
           mbar_wait(empty0 + 8u * slot, par ^ 1u);
           if (elect_one()) {
-            if (leader) mbar_arrive_expect_tx(full0 + 8u * slot, slot_bytes * nshare);
+            if (leader) mbar_arrive_expect_tx(fullk0 + 8u * slot, slot_bytes * nshare);
             if (PAIR)   // this CTA's 64 of the block's 128 keys
-              tma2_load_2d(ring + slot * slot_bytes, &map_k, lead_full0 + 8u * slot, c * 64,
+              tma2_load_2d(ring + slot * slot_bytes, &map_k, lead_fullk0 + 8u * slot, c * 64,
                            img * p.tokens + step * FA_BK + (int)rank * 64);
             else
-              tma_load_2d(ring + slot * slot_bytes, &map_k, full0 + 8u * slot, c * 64, img * p.tokens + step * FA_BK);
+              tma_load_2d(ring + slot * slot_bytes, &map_k, fullk0 + 8u * slot, c * 64, img * p.tokens + step * FA_BK);
           }
           __syncwarp();
           if (++slot == nring) { slot = 0; par ^= 1u; }
@@ -174,27 +184,29 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           for (int h = 0; h < OPARTS; ++h) {
             mbar_wait(empty0 + 8u * slot, par ^ 1u);
             if (elect_one()) {
-              if (leader) mbar_arrive_expect_tx(full0 + 8u * slot, slot_bytes * nshare);
+              if (leader) mbar_arrive_expect_tx(fullv0 + 8u * slot, slot_bytes * nshare);
               if (PAIR)  // this CTA's 64 of the 128 d-rows of the chunk
-                tma2_load_3d(ring + slot * slot_bytes, &map_vt, lead_full0 + 8u * slot, j * FA_BK + kc * 64,
+                tma2_load_3d(ring + slot * slot_bytes, &map_vt, lead_fullv0 + 8u * slot, j * FA_BK + kc * 64,
                              vrow0 + h * 128 + (int)rank * 64, img);
               else
-                tma_load_3d(ring + slot * slot_bytes, &map_vt, full0 + 8u * slot, j * FA_BK + kc * 64, vrow0 + h * 128, img);
+                tma_load_3d(ring + slot * slot_bytes, &map_vt, fullv0 + 8u * slot, j * FA_BK + kc * 64, vrow0 + h * 128, img);
             }
             __syncwarp();
             if (++slot == nring) { slot = 0; par ^= 1u; }
           }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------ MMA issuer ------------------------------
-    const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
-    const uint32_t idesc_o = idesc_s;  // PV in three N = 128 thirds of d
+  } else if (warp == 1 || warp == FA_PV_WARP) {
+    // ------------------------------ MMA issuers ------------------------------
+    // Both walk the producer's push sequence (per pass: K(0) | K(1) V(0) | K(2) V(1) | ... | V(nb-1)); each consumes its own
+    // kind of ring slot and only counts past the other's.
+    const bool is_qk = warp == 1;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
     const uint64_t hi = make_smem_desc(0u, 1024u, 2u);
     const uint32_t q_lo = (q_smem & 0x3FFFFu) >> 4, p_lo = (p_smem & 0x3FFFFu) >> 4, ring_lo = (ring & 0x3FFFFu) >> 4;
     const uint32_t s_tmem = tmem_base + 384u;
-    uint32_t slot = 0, par = 0;
-    auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accf) {
+    uint32_t slot = 0, use_par = 0;  // bit s of use_par: parity of this issuer's next use of slot s
+    auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accf) {
       if (PAIR) umma2_bf16(d, a, b, idesc, accf);
       else umma_bf16(d, a, b, idesc, accf);
     };
@@ -202,66 +214,76 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       if (PAIR) umma2_commit_both(bar);
       else umma_commit(bar);
     };
-    if (leader) {
-    mbar_wait(qbar, 0);
-    auto issue_qk = [&](int j) {
-      // S = Q K(j)^T : dch chunks x 4 k-steps, N = 128
-      for (int c = 0; c < DCH; ++c) {
-        mbar_wait(full0 + 8u * slot, par);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t ad = hi | (uint64_t)(q_lo + c * 1024u);
-          const uint64_t bd = hi | (uint64_t)(ring_lo + slot * (slot_bytes >> 4));
-          mma(s_tmem, ad, bd, idesc_s, c == 0 ? 0u : 1u);
-          mma(s_tmem, ad + 2u, bd + 2u, idesc_s, 1u);
-          mma(s_tmem, ad + 4u, bd + 4u, idesc_s, 1u);
-          mma(s_tmem, ad + 6u, bd + 6u, idesc_s, 1u);
-          commit(empty0 + 8u * slot);
-          if (c == DCH - 1) commit(sfull);
-        }
-        __syncwarp();
-        if (++slot == nring) { slot = 0; par ^= 1u; }
-      }
-      (void)j;
+    auto skip = [&](int n) {
+      for (int i = 0; i < n; ++i)
+        if (++slot == nring) slot = 0;
     };
-    // jj counts key blocks over all passes: every barrier flips once per block, so its phase is jj & 1
-    for (int pass = 0, jj = 0; pass < NPASS; ++pass)
-    for (int j = 0; j < nb; ++j, ++jj) {
-      if (j == 0) {
-        if (jj > 0) {  // next pass: the softmax warps have taken the previous pass's last S
-          mbar_wait(sempty, (uint32_t)((jj - 1) & 1));
-          tc_fence_after();
-        }
-        issue_qk(0);
-      }
-      if (j + 1 < nb) {
-        mbar_wait(sempty, (uint32_t)(jj & 1));   // S(j) is in registers: the S columns may be overwritten
-        tc_fence_after();
-        issue_qk(j + 1);
-      }
-      mbar_wait(pfull, (uint32_t)(jj & 1));      // P(j) is in shared memory (and O has been rescaled if needed)
-      tc_fence_after();
-      for (int kc = 0; kc < 2; ++kc)
-        for (int h = 0; h < OPARTS; ++h) {
-          mbar_wait(full0 + 8u * slot, par);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t ad = hi | (uint64_t)(p_lo + kc * 1024u);
-            const uint64_t bd = hi | (uint64_t)(ring_lo + slot * (slot_bytes >> 4));
-            const uint32_t d_tmem = tmem_base + (uint32_t)h * 128u;
-            mma(d_tmem, ad, bd, idesc_o, (j == 0 && kc == 0) ? 0u : 1u);
-            mma(d_tmem, ad + 2u, bd + 2u, idesc_o, 1u);
-            mma(d_tmem, ad + 4u, bd + 4u, idesc_o, 1u);
-            mma(d_tmem, ad + 6u, bd + 6u, idesc_o, 1u);
-            commit(empty0 + 8u * slot);
-            if (kc == 1 && h == OPARTS - 1) commit(pvdone);
+    if (leader) {
+      if (is_qk) mbar_wait(qbar, 0);
+      int g = 0;  // key blocks issued so far over all passes: every per-block barrier flips once per block
+      for (int pass = 0; pass < NPASS; ++pass)
+        for (int step = 0; step <= nb; ++step) {
+          if (step < nb) {
+            if (is_qk) {
+              if (g > 0) {  // S(previous block) is in the softmax warps' registers: the S columns may be overwritten
+                mbar_wait(sempty, (uint32_t)((g - 1) & 1));
+                tc_fence_after();
+              }
+              // S = Q K(step)^T : DCH chunks x 4 k-steps, N = 128
+              for (int c = 0; c < DCH; ++c) {
+                mbar_wait(fullk0 + 8u * slot, (use_par >> slot) & 1u);
+                use_par ^= 1u << slot;
+                tc_fence_after();
+                if (elect_one()) {
+                  const uint64_t ad = hi | (uint64_t)(q_lo + c * 1024u);
+                  const uint64_t bd = hi | (uint64_t)(ring_lo + slot * (slot_bytes >> 4));
+                  mma(s_tmem, ad, bd, c == 0 ? 0u : 1u);
+                  mma(s_tmem, ad + 2u, bd + 2u, 1u);
+                  mma(s_tmem, ad + 4u, bd + 4u, 1u);
+                  mma(s_tmem, ad + 6u, bd + 6u, 1u);
+                  commit(empty0 + 8u * slot);
+                  if (c == DCH - 1) commit(sfull);
+                }
+                __syncwarp();
+                if (++slot == nring) slot = 0;
+              }
+              ++g;
+            } else {
+              skip(DCH);
+            }
           }
-          __syncwarp();
-          if (++slot == nring) { slot = 0; par ^= 1u; }
+          if (step >= 1) {
+            if (!is_qk) {
+              const int j = step - 1;
+              mbar_wait(pfull, (uint32_t)(g & 1));  // P(j) is in shared memory (and O has been rescaled if needed)
+              tc_fence_after();
+              for (int kc = 0; kc < 2; ++kc)
+                for (int h = 0; h < OPARTS; ++h) {
+                  mbar_wait(fullv0 + 8u * slot, (use_par >> slot) & 1u);
+                  use_par ^= 1u << slot;
+                  tc_fence_after();
+                  if (elect_one()) {
+                    const uint64_t ad = hi | (uint64_t)(p_lo + kc * 1024u);
+                    const uint64_t bd = hi | (uint64_t)(ring_lo + slot * (slot_bytes >> 4));
+                    const uint32_t d_tmem = tmem_base + (uint32_t)h * 128u;
+                    mma(d_tmem, ad, bd, (j == 0 && kc == 0) ? 0u : 1u);
+                    mma(d_tmem, ad + 2u, bd + 2u, 1u);
+                    mma(d_tmem, ad + 4u, bd + 4u, 1u);
+                    mma(d_tmem, ad + 6u, bd + 6u, 1u);
+                    commit(empty0 + 8u * slot);
+                    if (kc == 1 && h == OPARTS - 1) commit(pvdone);
+                  }
+                  __syncwarp();
+                  if (++slot == nring) slot = 0;
+                }
+              ++g;
+            } else {
+              skip(2 * OPARTS);
+            }
+          }
         }
-    }
     }  // leader
-  } else if (warp >= 2) {
+  } else if (warp >= 2 && warp < FA_PV_WARP) {
     // ------------------------------ softmax / correction / output ------------------------------
     const int q = warp & 3, part = (warp - 2) >> 2;
     const int row = q * 32 + lane;
