@@ -307,7 +307,7 @@ def gpu_arm(a):
 
     cpu_b = None
     if world == 1 and not a.no_cpu_baseline:
-        cpu_b, _ = run_cpu_baseline(a.arch, S, 2, 1)
+        cpu_b, _ = run_cpu_baseline(a.arch, S, 4, 1)  # ~10-15 s of host work on a bounded sample
 
     cfg = workload_config(a)
     cfg["launch"] = "CUDA graph replay (one capture per shape)" if use_graph else "eager launches"
