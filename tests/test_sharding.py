@@ -80,3 +80,45 @@ def test_world_size_2_gloo_gradient_allreduce(tmp_path, lib_built):
     port = 31500 + (os.getpid() % 2000)
     mp.spawn(_allreduce_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ar0").exists() and (tmp_path / "ar1").exists()
+
+
+def test_trainer_bucket_schedule_covers_every_bucket_once(lib_built):
+    """Host logic of VaeTrainStep's two-phase all-reduce schedule (no GPU): after the decoder's backward only buckets made
+    of decoder / post_quant_conv parameters start; after the encoder's backward the rest; every bucket exactly once."""
+    from types import SimpleNamespace
+
+    from ragb_vae_b200.trainer import VaeTrainStep
+    from ragb_vae_b200.training import GradientAllReducer
+
+    names = ["encoder.a", "encoder.b", "decoder.a", "decoder.b", "decoder.c", "quant_conv.w", "post_quant_conv.w"]
+    sizes = [300, 200, 250, 250, 300, 50, 50]
+    offsets = [0]
+    for n in sizes:
+        offsets.append(offsets[-1] + n)
+    step = object.__new__(VaeTrainStep)
+    step.names = names
+    step.opt = SimpleNamespace(offsets=offsets)
+    started = []
+
+    class FakeReducer(GradientAllReducer):
+        def world(self):
+            return 2
+
+        def ready(self, bucket):
+            started.append(bucket)
+
+    step.reducer = FakeReducer(torch.zeros(offsets[-1]), num_buckets=7)
+    step._mark_ready(decoder_done=True)
+    first = list(started)
+    for b in first:  # only decoder-side parameters inside these buckets
+        lo, hi = step.reducer.buckets[b]
+        inside = [n for i, n in enumerate(names) if offsets[i + 1] > lo and offsets[i] < hi]
+        assert inside and all(n.startswith(("decoder.", "post_quant_conv.")) for n in inside), (b, inside)
+    assert first, "some decoder-only bucket must be ready after the decoder's backward"
+    step._mark_ready(decoder_done=False)
+    assert sorted(started) == list(range(len(step.reducer.buckets)))
+    # a bucket that mixes encoder-side and decoder-side parameters waits for the second phase
+    mixed = [b for b, (lo, hi) in enumerate(step.reducer.buckets)
+             if any(offsets[i + 1] > lo and offsets[i] < hi and not n.startswith(("decoder.", "post_quant_conv."))
+                    for i, n in enumerate(names))]
+    assert all(b not in first for b in mixed)
