@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 16
+#define RV_ABI_VERSION 17
 #define RV_PROF_CATEGORIES 9
 
 int rv_abi_version(void);
@@ -218,9 +218,10 @@ int rv_kl_ref(const void* moments, const void* ref_moments, float* kl_out, void*
               int dtype, float weight, void* stream);
 /* Backward of rv_rmsnorm_silu: dx, and dgamma[c] += dgamma_scale * d loss / d (gamma*sqrt(C)) (fp32, ACCUMULATED;
  * dgamma_scale = sqrt(C) gives d loss / d gamma, so dgamma may point straight into a gradient buffer).
- * gamma_scaled = gamma * sqrt(C).  c = 3 * 2^k 16-byte chunks (96, 192, 384 in bf16). */
-int rv_rmsnorm_silu_bwd(const void* x, const float* gamma_scaled, const void* dy, void* dx, float* dgamma,
-                        float dgamma_scale, int64_t pixels, int c, int dtype, int apply_silu, void* stream);
+ * gamma_scaled = gamma * sqrt(C).  c = 3 * 2^k 16-byte chunks (96, 192, 384 in bf16).  add (optional, same layout as dx) is
+ * added to dx: the gradient of the skip branch that meets the normalised one at this point. */
+int rv_rmsnorm_silu_bwd(const void* x, const float* gamma_scaled, const void* dy, const void* add, void* dx,
+                        float* dgamma, float dgamma_scale, int64_t pixels, int c, int dtype, int apply_silu, void* stream);
 /* Weight (and bias) gradient of a stride-1 3x3 or 1x1 convolution on the tensor cores: x NHWC bf16 [n][h][w][cin],
  * dy NHWC bf16 [n][h][w][cout].  Element (co, ci, tap) is ACCUMULATED (fp32 atomics) at
  * dw[co*dw_co_stride + ci*dw_ci_stride + tap*dw_tap_stride], so the gradient can land directly in the parameter's own

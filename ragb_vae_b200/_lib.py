@@ -9,7 +9,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "librgbavae.so")
 
 RV_F32, RV_BF16 = 0, 1
-ABI_VERSION = 16
+ABI_VERSION = 17
 PROF_CATEGORIES = 9
 PROF_NAMES = ("conv_tc", "conv_direct", "norm_silu", "softmax", "layout", "reparam", "recon_loss", "composite_psnr",
               "attention")
@@ -76,7 +76,7 @@ SIGNATURES = {
     "rv_reduce_blocks": (_I, [_L]),
     "rv_recon_loss_bwd": (_I, [_P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float), _I, _F, _F, _F, _P, _I, _L, _I, _P]),
     "rv_reparam_bwd": (_I, [_P, _P, _P, _P, _I, _I, _L, _I, _F, _P]),
-    "rv_rmsnorm_silu_bwd": (_I, [_P, _P, _P, _P, _P, _F, _L, _I, _I, _I, _P]),
+    "rv_rmsnorm_silu_bwd": (_I, [_P, _P, _P, _P, _P, _P, _F, _L, _I, _I, _I, _P]),
     "rv_conv2d_wgrad": (_I, [_P, _P, _P, _L, _L, _L, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rv_pack_dgrad_weights": (_I, [_P, _L, _L, _P, _I, _I, _I, _I, _P]),
     "rv_resample2x": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),

@@ -121,9 +121,9 @@ __global__ void __launch_bounds__(256) kl_ref_kernel(const T* __restrict__ momen
 // through shared memory, and leaves the block as ONE atomicAdd per channel, already scaled to d loss / d gamma.
 template <typename T, bool SILU>
 __global__ void __launch_bounds__(256) rmsnorm_silu_bwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma_scaled,
-                                                              const T* __restrict__ dy, T* __restrict__ dx,
-                                                              float* __restrict__ dgamma, int64_t pixels, int lanes_per_pixel,
-                                                              float dgamma_scale) {
+                                                              const T* __restrict__ dy, const T* __restrict__ add,
+                                                              T* __restrict__ dx, float* __restrict__ dgamma, int64_t pixels,
+                                                              int lanes_per_pixel, float dgamma_scale) {
   using V = Vec16<T>;
   constexpr int CPL = 3;
   extern __shared__ float sdg[];  // [8 warps][C]
@@ -144,15 +144,18 @@ __global__ void __launch_bounds__(256) rmsnorm_silu_bwd_kernel(const T* __restri
   for (int64_t p0 = warp_global * ppw; p0 < pixels; p0 += warps_total * ppw) {
     const int64_t pix = p0 + grp;
     const bool ok = pix < pixels;
-    V xv[CPL], dv[CPL];
+    V xv[CPL], dv[CPL], av[CPL];  // av: gradient of the skip branch that meets this one (optional), added to dx
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
       if (ok) {
         xv[k].load(x + pix * c + (int64_t)(k * L + sub) * V::N);
         dv[k].load(dy + pix * c + (int64_t)(k * L + sub) * V::N);
+        if (add) av[k].load(add + pix * c + (int64_t)(k * L + sub) * V::N);
+        else av[k].zero();
       } else {
         xv[k].zero();
         dv[k].zero();
+        av[k].zero();
       }
     }
     float ss = 0.f;
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(256) rmsnorm_silu_bwd_kernel(const T* __restri
       for (int k = 0; k < CPL; ++k) {
         V o;
 #pragma unroll
-        for (int j = 0; j < V::N; ++j) o.set(j, r * g[k][j] * du[k][j] - xv[k].get(j) * corr);
+        for (int j = 0; j < V::N; ++j) o.set(j, r * g[k][j] * du[k][j] - xv[k].get(j) * corr + av[k].get(j));
         o.store(dx + pix * c + (int64_t)(k * L + sub) * V::N);
       }
     }
@@ -448,15 +451,16 @@ int rv_kl_ref(const void* moments, const void* ref_moments, float* kl_out, void*
   return 0;
 }
 
-int rv_rmsnorm_silu_bwd(const void* x, const float* gamma_scaled, const void* dy, void* dx, float* dgamma, float dgamma_scale,
-                        int64_t pixels, int c, int dtype, int apply_silu, void* stream) {
+int rv_rmsnorm_silu_bwd(const void* x, const float* gamma_scaled, const void* dy, const void* add, void* dx, float* dgamma,
+                        float dgamma_scale, int64_t pixels, int c, int dtype, int apply_silu, void* stream) {
   RV_CHECK_ARG(x && gamma_scaled && dy && dx && dgamma && pixels > 0, "rmsnorm_silu_bwd: bad argument");
   RV_CHECK_ARG(dtype == RV_F32 || dtype == RV_BF16, "rmsnorm_silu_bwd: bad dtype %d", dtype);
   const int per_chunk = dtype == RV_F32 ? 4 : 8;
   const int lanes = c / (3 * per_chunk);
   RV_CHECK_ARG(c % (3 * per_chunk) == 0 && lanes >= 1 && lanes <= 32 && (lanes & (lanes - 1)) == 0,
                "rmsnorm_silu_bwd: channels must be 3 * 2^k 16-byte chunks (96, 192, 384 ...), got %d", c);
-  RV_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)dx % 16 == 0), "rmsnorm_silu_bwd: unaligned tensor");
+  RV_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)dx % 16 == 0) && ((uintptr_t)add % 16 == 0),
+               "rmsnorm_silu_bwd: unaligned tensor");
   cudaStream_t st = (cudaStream_t)stream;
   const int ppw = 32 / lanes;
   int64_t blocks = (pixels + 8 * ppw * 4 - 1) / (8 * ppw * 4);
@@ -466,7 +470,7 @@ int rv_rmsnorm_silu_bwd(const void* x, const float* gamma_scaled, const void* dy
   const size_t smem = 8 * (size_t)c * sizeof(float);
   rv::LaunchScope scope(rv::CAT_NORM, st, 3.0 * pixels * c * (dtype == RV_F32 ? 4 : 2));
 #define RV_NB(T, S) \
-  rv::rmsnorm_silu_bwd_kernel<T, S><<<(unsigned)blocks, 256, smem, st>>>((const T*)x, gamma_scaled, (const T*)dy, (T*)dx, dgamma, pixels, lanes, dgamma_scale)
+  rv::rmsnorm_silu_bwd_kernel<T, S><<<(unsigned)blocks, 256, smem, st>>>((const T*)x, gamma_scaled, (const T*)dy, (const T*)add, (T*)dx, dgamma, pixels, lanes, dgamma_scale)
   if (dtype == RV_F32) {
     if (apply_silu) RV_NB(float, true);
     else RV_NB(float, false);

@@ -77,8 +77,9 @@ class VaeTrainStep:
     def _norm(self, x, norm, silu=True):
         return self.vae._norm(x, norm, silu)
 
-    def _norm_bwd(self, norm, x, dy, silu=True):
-        dx, _ = T.rmsnorm_silu_backward(x, norm.gamma, dy, silu, dgamma_out=self._gview[id(norm.gamma)].view(-1))
+    def _norm_bwd(self, norm, x, dy, silu=True, add=None):
+        """``add``: gradient of the skip branch meeting this one at x (fused into the norm backward's store)."""
+        dx, _ = T.rmsnorm_silu_backward(x, norm.gamma, dy, silu, dgamma_out=self._gview[id(norm.gamma)].view(-1), add=add)
         return dx
 
     def _conv_bwd(self, conv, x, dy, *, mode: str = "same", need_dx: bool = True):
@@ -121,8 +122,8 @@ class VaeTrainStep:
         db = self._conv_bwd(blk.conv2, b, dy)
         dt = self._norm_bwd(blk.norm2, t, db)
         da = self._conv_bwd(blk.conv1, a, dt)
-        dx = self._norm_bwd(blk.norm1, x, da)
-        return T.add_(dx, dy if short is None else self._conv_bwd(short, x, dy))
+        skip = dy if short is None else self._conv_bwd(short, x, dy)
+        return self._norm_bwd(blk.norm1, x, da, add=skip)
 
     # ---- attention -------------------------------------------------------------------------
     def _gemm(self, *a, **k):
@@ -231,8 +232,7 @@ class VaeTrainStep:
         T.conv_wgrad(as_img(xn.view(n * t, c), c), as_img(dqkv, 3 * c), 1, dw_out=self._gview[id(attn.to_qkv.weight)],
                      dbias_out=self._gview[id(attn.to_qkv.bias)])
         dxn = T.conv_dgrad(as_img(dqkv, 3 * c), attn.to_qkv.weight.detach().reshape(3 * c, c, 1, 1)).view(x.shape)
-        dx = self._norm_bwd(attn.norm, x, dxn, silu=False)
-        return T.add_(dx, dout)
+        return self._norm_bwd(attn.norm, x, dxn, silu=False, add=dout)
 
     # ---- encoder / decoder -----------------------------------------------------------------
     def _run_fwd(self, x, items, tape):

@@ -73,16 +73,19 @@ def kl_to_reference(moments: torch.Tensor, ref_moments: torch.Tensor, grad_weigh
 
 
 def rmsnorm_silu_backward(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, silu: bool = True,
-                          dgamma_out: Optional[torch.Tensor] = None):
+                          dgamma_out: Optional[torch.Tensor] = None, add: Optional[torch.Tensor] = None):
     """Backward of ops.rmsnorm_silu: returns (dx, dgamma) with dgamma shaped like ``gamma`` (fp32).  ``dgamma_out``: a
-    contiguous fp32 buffer of C elements (e.g. a view of the flat gradient) the gradient is ACCUMULATED into."""
+    contiguous fp32 buffer of C elements (e.g. a view of the flat gradient) the gradient is ACCUMULATED into.  ``add``: the
+    gradient of the skip branch that meets the normalised one here; it is added to dx in the same pass."""
     _need_cuda(x, gamma, dy)
     c = x.shape[-1]
     x, dy = x.contiguous(), dy.to(x.dtype).contiguous()
     g_scaled = (gamma.detach().to(torch.float32).reshape(-1) * math.sqrt(c)).contiguous()
     dx = torch.empty_like(x)
     dg = torch.zeros(c, dtype=torch.float32, device=x.device) if dgamma_out is None else dgamma_out
-    check(_lib.load().rv_rmsnorm_silu_bwd(_ptr(x), _ptr(g_scaled), _ptr(dy), _ptr(dx), _ptr(dg), math.sqrt(c), x.numel() // c, c,
+    if add is not None:
+        add = add.to(x.dtype).contiguous()
+    check(_lib.load().rv_rmsnorm_silu_bwd(_ptr(x), _ptr(g_scaled), _ptr(dy), _ptr(add), _ptr(dx), _ptr(dg), math.sqrt(c), x.numel() // c, c,
                                           _dt(x), int(silu), _stream(x)), "rv_rmsnorm_silu_bwd")
     return dx, dg.reshape(gamma.shape)
 
