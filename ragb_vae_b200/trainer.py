@@ -109,8 +109,11 @@ class VaeTrainStep:
         short = getattr(blk, "conv_shortcut", None)
         a = self._norm(x, blk.norm1)
         h = x if short is None else self._conv(x, short)
-        t = self._conv(a, blk.conv1)
-        b = self._norm(t, blk.norm2)
+        # conv1 writes its raw output (the norm backward needs it) AND act(norm2(.)) from the same epilogue where one tile holds
+        # the pixel's whole channel vector (Cout <= 256); else the norm kernel runs
+        st = self.vae._conv_fused(a, blk.conv1, next_norm=(blk.norm2, True), want_raw=True)
+        t = st.raw
+        b = st.act if st.act is not None else self._norm(t, blk.norm2)
         y = self._conv(b, blk.conv2, residual=h)
         if tape is not None:
             tape.append(("res", blk, (x, a, t, b)))
@@ -335,59 +338,54 @@ class VaeTrainStep:
     def _forward_and_decoder_backward(self, inputs: torch.Tensor, noise: torch.Tensor):
         """Phase 1: everything up to (and including) the decoder's backward.  Returns (loss terms, context of phase 2)."""
         vae = self.vae
-        fuse, vae.fuse_norm = vae.fuse_norm, False  # the tape needs the raw conv outputs
-        try:
-            B = inputs.shape[0]
-            target_vae = torch.clamp(inputs.to(torch.float32), 0.0, 1.0) * 2.0 - 1.0
-            enc_tape: list = []
-            use_ref = self.ref_vae is not None and self.ref_kl_scale is not None and self.ref_kl_scale > 0.0
-            ref_ctx = None
-            if use_ref:
-                # the black / white posteriors carry a gradient now: the whole triplet goes through the taped encoder
+        # (the taped convs go through _conv / _conv_fused(want_raw=True), which never drop the raw output)
+        B = inputs.shape[0]
+        target_vae = torch.clamp(inputs.to(torch.float32), 0.0, 1.0) * 2.0 - 1.0
+        enc_tape: list = []
+        use_ref = self.ref_vae is not None and self.ref_kl_scale is not None and self.ref_kl_scale > 0.0
+        ref_ctx = None
+        if use_ref:
+            # the black / white posteriors carry a gradient now: the whole triplet goes through the taped encoder
+            composed = build_detail_augmented_triplet(target_vae)
+            moments_all = self.encode_moments(composed, enc_tape)
+            moments = moments_all[:B]
+            ref_moments = self.ref_vae._encode_moments(composed)  # frozen copy, inference path, no tape
+            ref_ctx = (moments_all, ref_moments)
+        else:
+            moments = self.encode_moments(target_vae, enc_tape)
+            if self.encode_triplet:  # black / white composites: encoded like the reference does, no gradient path
                 composed = build_detail_augmented_triplet(target_vae)
-                moments_all = self.encode_moments(composed, enc_tape)
-                moments = moments_all[:B]
-                ref_moments = self.ref_vae._encode_moments(composed)  # frozen copy, inference path, no tape
-                ref_ctx = (moments_all, ref_moments)
-            else:
-                moments = self.encode_moments(target_vae, enc_tape)
-                if self.encode_triplet:  # black / white composites: encoded like the reference does, no gradient path
-                    composed = build_detail_augmented_triplet(target_vae)
-                    vae.fuse_norm = fuse
-                    vae._encode_moments(composed[B:])
-                    vae.fuse_norm = False
-            post = DiagonalGaussianDistribution(moments)
-            z = post.sample(noise=noise)
-            dec_tape: list = []
-            pred = self.decode(z, dec_tape)
-            lm = self.loss_module
-            recon = lm.reconstruction_loss(pred, target_vae)
-            metrics = {"train/recon": recon}
-            total = recon
-            kl_w = 0.0
-            if self.kl_scale is not None and self.kl_scale > 0.0:
-                kl = lm.kl_loss(post)
-                metrics["train/kl"] = kl
-                total = total + self.kl_scale * kl
-                kl_w = self.kl_scale / B  # posterior.kl() is already the per-sample sum; both reduce rules average it over B
-            dm_ref = None
-            if use_ref:
-                # 0.5 * (kl_loss(black, ref_black) + kl_loss(white, ref_white)); kl_loss = per-sample sums averaged over B
-                moments_all, ref_moments = ref_ctx
-                w = self.ref_kl_scale * 0.5 / B
-                kl_bw, dm_ref = T.kl_to_reference(moments_all[B:], ref_moments[B:], grad_weight=w)
-                ref_kl = 0.5 * (kl_bw[:B].mean() + kl_bw[B:].mean())
-                metrics["train/ref_kl"] = ref_kl
-                total = total + self.ref_kl_scale * ref_kl
-            metrics["train/loss"] = total
-            # ---- backward ----
-            self.opt.zero_grad()
-            dpred = T.recon_loss_backward(pred, target_vae, lm._eb, lm._eb2, lm.reduce_mean, lm.use_naive_mse, clamp=(-1.0, 1.0))
-            dy = ops.nchw_to_nhwc(dpred, 16, torch.bfloat16)
-            dzp = self._run_bwd(dec_tape, dy)  # NHWC [B,h,w,16]
-            return metrics, (enc_tape, moments, noise, dzp, kl_w, dm_ref)
-        finally:
-            vae.fuse_norm = fuse
+                vae._encode_moments(composed[B:])
+        post = DiagonalGaussianDistribution(moments)
+        z = post.sample(noise=noise)
+        dec_tape: list = []
+        pred = self.decode(z, dec_tape)
+        lm = self.loss_module
+        recon = lm.reconstruction_loss(pred, target_vae)
+        metrics = {"train/recon": recon}
+        total = recon
+        kl_w = 0.0
+        if self.kl_scale is not None and self.kl_scale > 0.0:
+            kl = lm.kl_loss(post)
+            metrics["train/kl"] = kl
+            total = total + self.kl_scale * kl
+            kl_w = self.kl_scale / B  # posterior.kl() is already the per-sample sum; both reduce rules average it over B
+        dm_ref = None
+        if use_ref:
+            # 0.5 * (kl_loss(black, ref_black) + kl_loss(white, ref_white)); kl_loss = per-sample sums averaged over B
+            moments_all, ref_moments = ref_ctx
+            w = self.ref_kl_scale * 0.5 / B
+            kl_bw, dm_ref = T.kl_to_reference(moments_all[B:], ref_moments[B:], grad_weight=w)
+            ref_kl = 0.5 * (kl_bw[:B].mean() + kl_bw[B:].mean())
+            metrics["train/ref_kl"] = ref_kl
+            total = total + self.ref_kl_scale * ref_kl
+        metrics["train/loss"] = total
+        # ---- backward ----
+        self.opt.zero_grad()
+        dpred = T.recon_loss_backward(pred, target_vae, lm._eb, lm._eb2, lm.reduce_mean, lm.use_naive_mse, clamp=(-1.0, 1.0))
+        dy = ops.nchw_to_nhwc(dpred, 16, torch.bfloat16)
+        dzp = self._run_bwd(dec_tape, dy)  # NHWC [B,h,w,16]
+        return metrics, (enc_tape, moments, noise, dzp, kl_w, dm_ref)
 
     def _encoder_backward(self, ctx) -> None:
         """Phase 2: posterior sample / KL backward and the encoder's backward."""
