@@ -33,6 +33,8 @@ Reference call sites restated here:
   src/models/rgba_vae.py:274-281 RgbaVAE.forward
   src/models/losses.py:67-83,109-123  reconstruction_loss / kl_loss / _reduce
   src/training/rgba_vae_stage.py:606-625,690-700,712-715  triplet / split / psnr
+  src/training/rgba_vae_stage.py:433-518  the train step up to backward (training_step; torch autograd gives the gradients)
+  src/training/rgba_vae_stage.py:85-130,575-603  RandomBackgroundBlend._blend_tensor / build_training_batch
 """
 from __future__ import annotations
 
