@@ -5,7 +5,6 @@ inference_rgba_flux.py:15-26, and the batch assembly + RandomBackgroundBlend aug
 rgba_vae_stage.py:85-130,575-603.  Same names and errors as the reference functions; one kernel each."""
 from __future__ import annotations
 
-import ctypes as C
 from typing import Optional, Tuple
 
 import torch

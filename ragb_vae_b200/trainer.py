@@ -25,14 +25,13 @@ without it the black / white composites are still encoded (``encode_triplet=True
 """
 from __future__ import annotations
 
-import math
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import torch
 
 from . import ops
 from . import training as T
-from ._lib import RV_BF16, RV_F32, RvError
+from ._lib import RvError
 from .autoencoder import RgbaAutoencoder
 from .losses import AlphaVaeLoss
 from .plumbing import build_detail_augmented_triplet
