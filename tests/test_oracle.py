@@ -121,3 +121,51 @@ def test_adapt_matches_reference_rule():
         assert torch.equal(m.decoder.conv_out.weight[:3], w_out) and torch.all(m.decoder.conv_out.weight[3] == 0)
         assert float(m.decoder.conv_out.bias[3]) == pytest.approx(0.7)
         assert m.config.in_channels == 4 and m.config.out_channels == 4
+
+
+def test_training_step_oracle_invariants():
+    """oracle.training_step (rgba_vae_stage.py:433-518): what autograd must give on one frame -- no gradient for the
+    video-only temporal convs, exact zeros in the unused temporal taps of the causal 3-D kernels, finite everything, and
+    a reference-KL term that only appears with a reference VAE and a positive scale."""
+    import copy
+
+    import torch
+
+    from oracle import vae_oracle as O
+
+    vae = copy.deepcopy(O.build_oracle("qwen", seed=0))
+    x = O.synthetic_rgba(1, 32, 32, seed=3)
+    noise = torch.randn(1, 16, 4, 4, generator=torch.Generator().manual_seed(4))
+    metrics, grads = O.training_step(vae, x, noise, kl_scale=1e-6)
+    assert set(metrics) == {"train/recon", "train/kl", "train/loss"}
+    assert all(torch.isfinite(v).all() for v in grads.values())
+    names = dict(vae.named_parameters())
+    assert not any(".time_conv." in n for n in grads) and any(".time_conv." in n for n in names)
+    w = grads["encoder.down_blocks.0.conv1.weight"]
+    assert w.dim() == 5 and float(w[:, :, :-1].abs().max()) == 0.0 and float(w[:, :, -1].abs().max()) > 0.0
+    assert abs(float(metrics["train/loss"]) - float(metrics["train/recon"]) - 1e-6 * float(metrics["train/kl"])) < 1e-6 * abs(
+        float(metrics["train/loss"])) + 1e-9
+    ref = copy.deepcopy(O.build_oracle("qwen", seed=5))
+    m2, g2 = O.training_step(vae, x, noise, kl_scale=1e-6, ref_vae=ref, ref_kl_scale=0.5)
+    assert "train/ref_kl" in m2 and float(m2["train/ref_kl"]) > 0.0
+    assert float((g2["encoder.conv_in.weight"] - grads["encoder.conv_in.weight"]).abs().max()) > 0.0
+    m3, _ = O.training_step(vae, x, noise, kl_scale=1e-6, ref_vae=ref, ref_kl_scale=0.0)
+    assert "train/ref_kl" not in m3
+
+
+def test_background_blend_and_batch_assembly_oracle():
+    import torch
+
+    from oracle import vae_oracle as O
+
+    t = torch.rand(4, 6, 5, generator=torch.Generator().manual_seed(1))
+    c = torch.tensor([0.3, 0.5, 0.9])
+    out = O.background_blend(t, c)
+    assert out.shape == (4, 6, 5) and float(out[3].min()) == 1.0
+    a = t[3:4]
+    assert torch.allclose(out[:3], t[:3] * a + c.view(3, 1, 1) * (1 - a))
+    b = {"component": torch.zeros(2, 4, 3, 3), "composite": torch.ones(2, 4, 3, 3), "background": torch.full((2, 4, 3, 3), 0.5)}
+    assert O.build_training_batch(b).shape[0] == 4
+    assert O.build_training_batch(b, torch.tensor([True, False])).shape[0] == 5
+    with pytest.raises(ValueError):
+        O.build_training_batch({"component": b["component"]})
