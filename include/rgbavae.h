@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 17
+#define RV_ABI_VERSION 18
 #define RV_PROF_CATEGORIES 9
 
 int rv_abi_version(void);
@@ -185,18 +185,27 @@ int rv_reparam(const void* moments, const void* noise, void* z, float* kl_out, i
                int64_t hw, int dtype, float z_shift, float z_scale, void* stream);
 
 /* ---- losses and validation metrics -------------------------------------------------------*/
+/* The three reductions below read both images once and finish in the same launch (the last block of a sample sums
+ * the per-block fp64 partials in a fixed order: deterministic, and a sample's bits do not depend on its batch).
+ * `partial` is caller-provided scratch of n * rv_reduce_blocks(hw) * K doubles (K per function below).  Calls on
+ * one stream are ordered; calls on different streams are independent. */
 /* AlphaVaeLoss.reconstruction_loss (src/models/losses.py:67-83): pred/target NCHW [n][4][hw] in
- * [-1,1].  per_sample[n] receives the per-sample SUM of the loss map (naive: over 4 channels).
- * partial is a scratch buffer of n*rv_reduce_blocks(hw) doubles. */
+ * [-1,1].  per_sample[n] receives the per-sample SUM of the loss map (naive: over 4 channels).  K = 1. */
 int rv_recon_loss(const void* pred, const void* target, const float* eb_host, const float* eb2_host,
                   int naive_mse, float* per_sample, double* partial, int n, int64_t hw, int dtype,
                   void* stream);
 /* composite_over_background + compute_psnr + alpha MAE (src/models/rgba_vae.py:75-84,
  * src/training/rgba_vae_stage.py:712-715,742-753) in one pass over recon/target NCHW [n][4][hw]
  * in [0,1].  bgs_host: nbg (<= 4) RGB triples (HOST pointer).  out: [n][nbg+1] fp32: PSNR per
- * background, then alpha MAE.  partial: n*rv_reduce_blocks(hw)*(nbg+1) doubles. */
+ * background, then alpha MAE.  K = 5. */
 int rv_composite_psnr(const void* recon, const void* target, const float* bgs_host, int nbg,
                       float* out, double* partial, int n, int64_t hw, int dtype, void* stream);
+/* Every term RgbaVAE.loss weighs (src/models/rgba_vae.py:283-316) in one pass over recon/target NCHW [n][4][hw] in
+ * [0,1].  out [n][6] fp32 per-sample SUMS: [0] the AlphaVAE map (:324-336) on the pair rescaled to [-1,1],
+ * [1] (recon_rgb - target_rgb)^2 (the use_naive_mse branch, :291-293), [2] / [3] squared error of the composites over
+ * white / black (:298-306), [4] (alpha_r - alpha_t)^2 (:308-309), [5] |alpha_r - alpha_t| (:311-312).  K = 6. */
+int rv_rgba_loss_terms(const void* recon, const void* target, const float* eb_host, const float* eb2_host, float* out,
+                       double* partial, int n, int64_t hw, int dtype, void* stream);
 /* number of partial blocks per sample the two reductions above use for `hw` pixels */
 int rv_reduce_blocks(int64_t hw);
 

@@ -9,7 +9,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "librgbavae.so")
 
 RV_F32, RV_BF16 = 0, 1
-ABI_VERSION = 17
+ABI_VERSION = 18
 PROF_CATEGORIES = 9
 PROF_NAMES = ("conv_tc", "conv_direct", "norm_silu", "softmax", "layout", "reparam", "recon_loss", "composite_psnr",
               "attention")
@@ -73,6 +73,7 @@ SIGNATURES = {
     "rv_reparam": (_I, [_P, _P, _P, _P, _I, _I, _L, _I, _F, _F, _P]),
     "rv_recon_loss": (_I, [_P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float), _I, _P, _P, _I, _L, _I, _P]),
     "rv_composite_psnr": (_I, [_P, _P, C.POINTER(C.c_float), _I, _P, _P, _I, _L, _I, _P]),
+    "rv_rgba_loss_terms": (_I, [_P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P, _I, _L, _I, _P]),
     "rv_reduce_blocks": (_I, [_L]),
     "rv_recon_loss_bwd": (_I, [_P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float), _I, _F, _F, _F, _P, _I, _L, _I, _P]),
     "rv_reparam_bwd": (_I, [_P, _P, _P, _P, _I, _I, _L, _I, _F, _P]),

@@ -273,6 +273,30 @@ QWEN_CONFIG = dict(
     block_out_channels=[96, 192, 384, 384], sample_size=256, scaling_factor=1.0, shift_factor=0.0)
 
 
+def _load_checkpoint_tensors(root: str) -> Dict[str, torch.Tensor]:
+    """The weight files diffusers' ``from_pretrained`` accepts, in its order of preference: one safetensors file, a
+    sharded safetensors checkpoint (``*.safetensors.index.json`` -> ``weight_map``), or a pickled state dict
+    (``diffusion_pytorch_model.bin`` / ``pytorch_model.bin``, loaded with ``weights_only=True``)."""
+    from safetensors.torch import load_file
+
+    single = os.path.join(root, WEIGHTS_NAME)
+    if os.path.isfile(single):
+        return load_file(single)
+    index = single + ".index.json"
+    if os.path.isfile(index):
+        with open(index) as f:
+            shards = sorted(set(json.load(f)["weight_map"].values()))
+        sd: Dict[str, torch.Tensor] = {}
+        for shard in shards:
+            sd.update(load_file(os.path.join(root, shard)))
+        return sd
+    for name in ("diffusion_pytorch_model.bin", "pytorch_model.bin"):
+        cand = os.path.join(root, name)
+        if os.path.isfile(cand):
+            return dict(torch.load(cand, map_location="cpu", weights_only=True))
+    raise FileNotFoundError(f"no {WEIGHTS_NAME}, sharded index or .bin state dict under {root}")
+
+
 def _arch_of(config: dict) -> str:
     cls = str(config.get("_class_name", ""))
     if "Qwen" in cls or "base_dim" in config:
@@ -311,6 +335,7 @@ class RgbaAutoencoder(nn.Module):
         self.im2col_stem = False  # measured slower (3.5 ms) than 16-channel padding + 9 narrow K blocks (2.6 ms) at 8x1024^2
         self.fuse_norm = True  # RMS norm + SiLU in the producing conv's epilogue where one tile holds all channels
         self._pack_cache: Dict[tuple, tuple] = {}
+        self.weights_generation = 0
         self.requires_grad_(False)
         self.eval()
 
@@ -368,37 +393,43 @@ class RgbaAutoencoder(nn.Module):
         self.use_slicing = False
 
     def enable_gradient_checkpointing(self):
+        """Honoured by ``trainer.VaeTrainStep``: residual and attention blocks keep only their input and recompute their
+        intermediates in the backward (diffusers checkpoints per block; rgba_vae_stage.py:305-307 turns it on)."""
         self.gradient_checkpointing = True
 
     def disable_gradient_checkpointing(self):
         self.gradient_checkpointing = False
 
-    def _encode_maybe_tiled(self, x: torch.Tensor) -> torch.Tensor:
+    def _encode_maybe_tiled(self, x: torch.Tensor, in_scale: float = 1.0, in_shift: float = 0.0) -> torch.Tensor:
         ts, ss, tl, sl = self._tiling()
+        enc = lambda t: self._encode_moments(t, in_scale=in_scale, in_shift=in_shift)
         if self.use_tiling and isinstance(x, torch.Tensor) and x.dim() == 4 and (x.shape[-1] > ts or x.shape[-2] > ts):
             if self.arch == "flux":   # blend_extent = int(latent_tile * 0.25), row_limit = latent_tile - blend_extent
                 blend = int(tl * 0.25)
                 limit = tl - blend
             else:                      # blend = latent_tile - latent_stride, crop to the latent stride
                 blend, limit = tl - sl, sl
-            m = self._tiled(x, self._encode_moments, ts, ss, blend, limit)
+            m = self._tiled(x, enc, ts, ss, blend, limit)
             return m[:, :, :x.shape[2] // 8, :x.shape[3] // 8].contiguous()
-        return self._encode_moments(x)
+        return enc(x)
 
-    def _decode_maybe_tiled(self, z: torch.Tensor) -> torch.Tensor:
+    def _decode_maybe_tiled(self, z: torch.Tensor, out_scale: float = 1.0, out_shift: float = 0.0, clamp=None) -> torch.Tensor:
+        """``clamp((decode(z) * out_scale + out_shift))``.  Tiled: the affine map commutes with the linear seam blend, so
+        it stays fused in every tile's conv_out epilogue; the clamp does not and runs once after blending."""
         ts, ss, tl, sl = self._tiling()
         if self.use_tiling and isinstance(z, torch.Tensor) and z.dim() == 4 and (z.shape[-1] > tl or z.shape[-2] > tl):
             if self.arch == "flux":
                 blend = int(ts * 0.25)
                 limit = ts - blend
-                fn = self._decode_image
+                fn = lambda t: self._decode_image(t, out_scale=out_scale, out_shift=out_shift)
             else:
                 blend, limit = ts - ss, ss
                 # AutoencoderKLQwenImage.tiled_decode returns the blended tiles without the clamp of _decode
-                fn = lambda t: self._decode_image(t, model_clamp=False)
+                fn = lambda t: self._decode_image(t, out_scale=out_scale, out_shift=out_shift, model_clamp=False)
             y = self._tiled(z, fn, tl, sl, blend, limit)
-            return y[:, :, :z.shape[2] * 8, :z.shape[3] * 8].contiguous()
-        return self._decode_image(z)
+            y = y[:, :, :z.shape[2] * 8, :z.shape[3] * 8].contiguous()
+            return y if clamp is None else y.clamp_(clamp[0], clamp[1])
+        return self._decode_image(z, out_scale=out_scale, out_shift=out_shift, clamp=clamp)
 
     def encode(self, x: torch.Tensor, return_dict: bool = True):
         moments = self._run_sliced(self._encode_maybe_tiled, x)
@@ -436,8 +467,6 @@ class RgbaAutoencoder(nn.Module):
     def from_pretrained(cls, path: str, subfolder: Optional[str] = None, torch_dtype: Optional[torch.dtype] = None,
                         ignore_mismatched_sizes: bool = False, low_cpu_mem_usage: bool = False, arch: Optional[str] = None,
                         **_):
-        from safetensors.torch import load_file
-
         root = os.path.join(path, subfolder) if subfolder else path
         with open(os.path.join(root, CONFIG_NAME)) as f:
             cfg = json.load(f)
@@ -446,7 +475,7 @@ class RgbaAutoencoder(nn.Module):
         out_ch = int(cfg.get("out_channels", in_ch))
         keep = {k: v for k, v in cfg.items() if k not in ("in_channels", "out_channels")}
         model = cls(arch, in_ch, out_ch, **keep)
-        sd = load_file(os.path.join(root, WEIGHTS_NAME))
+        sd = _load_checkpoint_tensors(root)
         own = model.state_dict()
         mismatched = [k for k, v in sd.items() if k in own and tuple(own[k].shape) != tuple(v.shape)]
         if mismatched and not ignore_mismatched_sizes:
@@ -464,6 +493,13 @@ class RgbaAutoencoder(nn.Module):
         return model
 
     # ---- weight packing cache ------------------------------------------------------------
+    def mark_weights_changed(self) -> None:
+        """Call after parameters were rewritten behind torch's back (raw-pointer optimizer updates: neither ``data_ptr``
+        nor ``_version`` moves).  Drops every packed copy and bumps ``weights_generation`` (captured inference graphs of
+        ``RgbaVAE.forward_graphed`` are keyed on it)."""
+        self._pack_cache.clear()
+        self.weights_generation += 1
+
     def _cached(self, key: tuple, params, build):
         ver = tuple((p.data_ptr(), p._version, tuple(p.shape), p.dtype) for p in params)
         hit = self._pack_cache.get(key)

@@ -291,6 +291,38 @@ def composite_psnr(recon: torch.Tensor, target: torch.Tensor, backgrounds: Seque
     return out
 
 
+def rgba_loss_terms(recon: torch.Tensor, target: torch.Tensor, eb: Sequence[float], eb2: Sequence[float]) -> torch.Tensor:
+    """[B, 6] fp32 per-sample sums of every term ``RgbaVAE.loss`` weighs (rgba_vae.py:283-316): AlphaVAE map on the
+    rescaled pair, rgb squared error, white / black composite squared error, alpha squared error, alpha absolute error."""
+    recon, target = _pair(recon, target)
+    n, _, h, w = recon.shape
+    lib = _lib.load()
+    blocks = lib.rv_reduce_blocks(h * w)
+    partial = torch.empty((n * blocks * 6,), dtype=torch.float64, device=recon.device)
+    out = torch.empty((n, 6), dtype=torch.float32, device=recon.device)
+    ebv = (C.c_float * 3)(*[float(v) for v in eb])
+    eb2v = (C.c_float * 3)(*[float(v) for v in eb2])
+    check(lib.rv_rgba_loss_terms(_ptr(recon), _ptr(target), ebv, eb2v, _ptr(out), _ptr(partial), n, h * w, _dt(recon),
+                                 _stream(recon)), "rv_rgba_loss_terms")
+    return out
+
+
+def kl_to_reference(moments: torch.Tensor, ref_moments: torch.Tensor, grad_weight: Optional[float] = None):
+    """Per-sample KL(posterior || reference posterior) [n] (fp32) and, with ``grad_weight``, grad_weight * d KL / d moments
+    (rgba_vae_stage.py:489-508; DiagonalGaussianDistribution.kl(other))."""
+    _need_cuda(moments, ref_moments)
+    moments = moments.contiguous()
+    ref_moments = ref_moments.to(moments.dtype).contiguous()
+    if moments.shape != ref_moments.shape:
+        raise ValueError(f"posteriors differ in shape: {tuple(moments.shape)} vs {tuple(ref_moments.shape)}")
+    n, c2, h, w = moments.shape
+    kl = torch.zeros(n, dtype=torch.float32, device=moments.device)
+    dm = torch.empty_like(moments) if grad_weight is not None else None
+    check(_lib.load().rv_kl_ref(_ptr(moments), _ptr(ref_moments), _ptr(kl), _ptr(dm), n, c2 // 2, h * w, _dt(moments),
+                                0.0 if grad_weight is None else float(grad_weight), _stream(moments)), "rv_kl_ref")
+    return kl, dm
+
+
 def blend_tiles(a: torch.Tensor, b: torch.Tensor, extent: int, vertical: bool) -> torch.Tensor:
     """diffusers blend_v / blend_h on contiguous NCHW tiles; b is modified in place and returned."""
     _need_cuda(a, b)

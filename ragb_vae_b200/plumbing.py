@@ -60,9 +60,11 @@ class RandomBackgroundBlend:
         return out, mask_u8.bool()
 
 
-def build_training_batch(batch: dict, device, *, background_sample_prob: float = 0.0, generator=None) -> torch.Tensor:
+def build_training_batch(batch: dict, device, *, background_sample_prob: float = 0.0, generator=None,
+                         background_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """rgba_vae_stage.py:575-603: cat(component, composite) (or composite alone) on ``device``, plus the background frames
-    a Bernoulli(background_sample_prob) mask selects.  Same ValueErrors as the reference."""
+    a Bernoulli(background_sample_prob) mask selects (``background_mask`` supplies the draw, for reproducibility).  Same
+    ValueErrors as the reference."""
     tensors = []
     if "component" in batch and "composite" in batch:
         tensors.extend([batch["component"], batch["composite"]])
@@ -71,13 +73,16 @@ def build_training_batch(batch: dict, device, *, background_sample_prob: float =
     else:
         raise ValueError("Batch must contain 'composite' tensor for training.")
     inputs = torch.cat([t.to(device, non_blocking=True) for t in tensors], dim=0)
-    if background_sample_prob > 0.0 and "background" in batch:
+    if (background_sample_prob > 0.0 or background_mask is not None) and "background" in batch:
         background = batch["background"].to(device, non_blocking=True)
         if background.dim() == 3:
             background = background.unsqueeze(0)
         if background.shape[1] != 4:
             raise ValueError("Background tensor is expected to have 4 channels (RGBA).")
-        mask = torch.rand(background.shape[0], device=device, generator=generator) < background_sample_prob
+        if background_mask is not None:
+            mask = background_mask.to(device=background.device, dtype=torch.bool)
+        else:
+            mask = torch.rand(background.shape[0], device=device, generator=generator) < background_sample_prob
         if mask.any():
             inputs = torch.cat([inputs, background[mask]], dim=0)
     return inputs

@@ -62,10 +62,10 @@ class DiagonalGaussianDistribution:
         if other is None:
             _, kl = ops.reparam(self.parameters, None, want_kl=True)
             return kl
-        # KL to another posterior (reference-KL term, rgba_vae_stage.py:489-508): rare, device torch ops
-        m, lv, om, olv = self.mean.float(), self.logvar.float(), other.mean.float(), other.logvar.float()
-        ov = torch.exp(olv)
-        return 0.5 * torch.sum((m - om).pow(2) / ov + torch.exp(lv) / ov - 1.0 - lv + olv, dim=[1, 2, 3])
+        # KL to another posterior (reference-KL term, rgba_vae_stage.py:489-508): one fused pass (rv_kl_ref)
+        if other.deterministic:
+            raise ValueError("kl(other): the reference posterior is deterministic (zero variance)")
+        return ops.kl_to_reference(self.parameters, other.parameters)[0]
 
     def mode(self) -> torch.Tensor:
         return self.mean

@@ -112,59 +112,100 @@ def adapt_vae_to_rgba(vae, alpha_bias_init: float = 0.0) -> None:
     vae.config.out_channels = 4
 
 
+def _locate_weight_file(directory: str) -> Optional[str]:
+    """rgba_vae.py:135-140 (plus diffusers' own name for a pickled checkpoint)."""
+    for filename in (WEIGHTS_NAME, "pytorch_model.bin", "diffusion_pytorch_model.bin"):
+        candidate = os.path.join(directory, filename)
+        if os.path.isfile(candidate):
+            return candidate
+    return None
+
+
 def _maybe_restore_rgba_convs(vae, model_name_or_path: str, subfolder: Optional[str]) -> bool:
     """rgba_vae.py:143-191 -- a checkpoint saved after widening still says ``in_channels: 3`` in its
-    config while its tensors are 4-channel; re-read those tensors straight from the safetensors file.
-    Returns True if anything was restored; raises RuntimeError on NaN/Inf like the reference."""
-    from safetensors import safe_open
-
-    root = os.path.join(model_name_or_path, subfolder) if subfolder else model_name_or_path
-    path = os.path.join(root, WEIGHTS_NAME)
-    if not os.path.isfile(path):
+    config while its tensors are 4-channel; re-read ``encoder.conv_in`` / ``decoder.conv_out`` (weight and bias)
+    straight from the weight file (``.safetensors``, or a pickled ``.bin`` state dict loaded with
+    ``weights_only=True``).  Silently does nothing when the file or the tensors are missing or are not 4-channel,
+    like the reference; returns True if the tensors were restored; raises RuntimeError on NaN/Inf."""
+    root = str(model_name_or_path)
+    if not os.path.exists(root):
         return False
-    restored = False
-    targets = {"encoder.conv_in.weight": (vae.encoder.conv_in, "weight"),
-               "decoder.conv_out.weight": (vae.decoder.conv_out, "weight"),
-               "decoder.conv_out.bias": (vae.decoder.conv_out, "bias")}
-    with safe_open(path, framework="pt") as f:
-        keys = set(f.keys())
-        for key, (mod, attr) in targets.items():
-            if key not in keys:
-                continue
-            t = f.get_tensor(key)
-            cur = getattr(mod, attr)
-            if tuple(t.shape) != tuple(cur.shape):
-                continue
-            if torch.isnan(t).any() or torch.isinf(t).any():
-                raise RuntimeError(f"{key} contains NaN/Inf after loading RGBA checkpoint.")
-            with torch.no_grad():
+    if subfolder:
+        root = os.path.join(root, subfolder)
+    if not os.path.isdir(root):
+        return False
+    path = _locate_weight_file(root)
+    if path is None:
+        return False
+    wanted = ("encoder.conv_in.weight", "encoder.conv_in.bias", "decoder.conv_out.weight", "decoder.conv_out.bias")
+    try:
+        if path.endswith(".safetensors"):
+            from safetensors import safe_open
+
+            with safe_open(path, framework="pt") as f:
+                keys = set(f.keys())
+                sd = {k: f.get_tensor(k) for k in wanted if k in keys}
+        else:
+            full = torch.load(path, map_location="cpu", weights_only=True)
+            sd = {k: full[k] for k in wanted if k in full}
+    except Exception:
+        return False
+    w_in, w_out = sd.get("encoder.conv_in.weight"), sd.get("decoder.conv_out.weight")
+    if w_in is None or w_out is None or w_in.shape[1] != 4 or w_out.shape[0] != 4:
+        return False
+    conv_in, conv_out = vae.encoder.conv_in, vae.decoder.conv_out
+    with torch.no_grad():
+        for mod, attr, key in ((conv_in, "weight", "encoder.conv_in.weight"), (conv_in, "bias", "encoder.conv_in.bias"),
+                               (conv_out, "weight", "decoder.conv_out.weight"), (conv_out, "bias", "decoder.conv_out.bias")):
+            cur, t = getattr(mod, attr, None), sd.get(key)
+            if cur is not None and t is not None:
                 cur.copy_(t.to(device=cur.device, dtype=cur.dtype))
-            restored = True
-    return restored
+    for name, tensor in (("encoder.conv_in.weight", conv_in.weight), ("decoder.conv_out.weight", conv_out.weight)):
+        if torch.isnan(tensor).any() or torch.isinf(tensor).any():
+            raise RuntimeError(f"{name} contains NaN/Inf after loading RGBA checkpoint.")
+    return True
 
 
 class RgbaVAE(nn.Module):
     """src/models/rgba_vae.py:194-342.  ``forward(x)`` takes (B,3|4,H,W) in [0,1] and returns
     ``(recon in [0,1], posterior)``; ``noise=`` makes the posterior sample reproducible."""
 
-    def __init__(self, vae: RgbaAutoencoder, loss_reduce_mean: bool = False, use_naive_mse: bool = False,
-                 custom_eb: Optional[Sequence[float]] = None, custom_eb2: Optional[Sequence[float]] = None, beta: float = 0.25,
-                 **legacy_weights):
+    def __init__(self, vae: RgbaAutoencoder, beta: float = 0.25, alpha_loss_weight: float = 1.0, alpha_l1_weight: float = 0.0,
+                 rgb_loss_weight: float = 1.0, white_bg_weight: float = 0.0, black_bg_weight: float = 0.0,
+                 loss_reduce_mean: bool = False, use_naive_mse: bool = False, custom_eb: Optional[Sequence[float]] = None,
+                 custom_eb2: Optional[Sequence[float]] = None) -> None:
+        """Same arguments, order and defaults as rgba_vae.py:195-208."""
         super().__init__()
         from .losses import AlphaVaeLoss
 
         self.vae = vae
         self.beta = beta
-        self.legacy_weights = legacy_weights  # alpha_loss_weight etc. of the reference's pre-AlphaVAE loss
+        self.alpha_loss_weight = alpha_loss_weight
+        self.alpha_l1_weight = alpha_l1_weight
+        self.rgb_loss_weight = rgb_loss_weight
+        self.white_bg_weight = white_bg_weight
+        self.black_bg_weight = black_bg_weight
+        self.loss_reduce_mean = loss_reduce_mean
+        self.use_naive_mse = use_naive_mse
         self._graphs = {}
+        self._graphs_generation = 0
+        # validates custom_eb / custom_eb2 like rgba_vae.py:224-225 and carries the Eb constants
         self.loss_module = AlphaVaeLoss(reduce_mean=loss_reduce_mean, use_naive_mse=use_naive_mse, custom_eb=custom_eb,
                                         custom_eb2=custom_eb2)
+        self.register_buffer("alphavae_eb", self.loss_module.eb.clone(), persistent=False)
+        self.register_buffer("alphavae_eb2", self.loss_module.eb2.clone(), persistent=False)
 
     @classmethod
     def from_pretrained_rgb(cls, model_name_or_path: str, subfolder: Optional[str] = "vae",
                             torch_dtype: Optional[torch.dtype] = torch.float32, alpha_bias_init: float = 0.0,
-                            device: Optional[torch.device] = None, **kwargs) -> "RgbaVAE":
-        if subfolder and not os.path.isfile(os.path.join(model_name_or_path, subfolder, CONFIG_NAME)):
+                            beta: float = 0.25, alpha_loss_weight: float = 1.0, alpha_l1_weight: float = 0.0,
+                            rgb_loss_weight: float = 1.0, white_bg_weight: float = 0.0, black_bg_weight: float = 0.0,
+                            device: Optional[torch.device] = None, loss_reduce_mean: bool = False, use_naive_mse: bool = False,
+                            custom_eb: Optional[Sequence[float]] = None, custom_eb2: Optional[Sequence[float]] = None) -> "RgbaVAE":
+        """rgba_vae.py:231-272.  One convenience beyond the reference: a checkpoint directory without the ``vae/``
+        sub-folder (what ``save_pretrained`` writes) is accepted with the default ``subfolder``."""
+        if subfolder and not os.path.isfile(os.path.join(model_name_or_path, subfolder, CONFIG_NAME)) \
+                and os.path.isfile(os.path.join(model_name_or_path, CONFIG_NAME)):
             subfolder = None
         vae = RgbaAutoencoder.from_pretrained(model_name_or_path, subfolder=subfolder, torch_dtype=torch_dtype,
                                               ignore_mismatched_sizes=True, low_cpu_mem_usage=False)
@@ -172,18 +213,23 @@ class RgbaVAE(nn.Module):
         _maybe_restore_rgba_convs(vae, model_name_or_path, subfolder)
         if device is not None:
             vae = vae.to(device)
-        return cls(vae=vae, **kwargs)
+        return cls(vae=vae, beta=beta, alpha_loss_weight=alpha_loss_weight, alpha_l1_weight=alpha_l1_weight,
+                   rgb_loss_weight=rgb_loss_weight, white_bg_weight=white_bg_weight, black_bg_weight=black_bg_weight,
+                   loss_reduce_mean=loss_reduce_mean, use_naive_mse=use_naive_mse, custom_eb=custom_eb, custom_eb2=custom_eb2)
 
     def forward(self, x: torch.Tensor, noise: Optional[torch.Tensor] = None, generator=None):
-        x_rgba = _ensure_alpha(x)
-        # _to_vae_range is the conv_in loader's affine; _from_vae_range + clamp(0,1) the conv_out epilogue's
-        moments = self.vae._run_sliced(lambda t: self.vae._encode_moments(t, in_scale=2.0, in_shift=-1.0), x_rgba)
+        """rgba_vae.py:274-281.  Goes through the same tiled / sliced encode and decode as ``vae.encode`` /
+        ``vae.decode`` (the reference stage enables both, rgba_vae_stage.py:296-304), so ``model(x)`` and
+        ``model.vae.encode(x)`` always agree; ``_to_vae_range`` is the conv_in loader's affine and
+        ``_from_vae_range`` + ``clamp(0, 1)`` the conv_out epilogue's (after the seam blend when tiled)."""
         from .posterior import DiagonalGaussianDistribution
 
+        x_rgba = _ensure_alpha(x)
+        vae = self.vae
+        moments = vae._run_sliced(lambda t: vae._encode_maybe_tiled(t, in_scale=2.0, in_shift=-1.0), x_rgba)
         posterior = DiagonalGaussianDistribution(moments)
         z = posterior.sample(generator=generator, noise=noise)
-        recon = self.vae._run_sliced(
-            lambda t: self.vae._decode_image(t, out_scale=0.5, out_shift=0.5, clamp=(0.0, 1.0)), z)
+        recon = vae._run_sliced(lambda t: vae._decode_maybe_tiled(t, out_scale=0.5, out_shift=0.5, clamp=(0.0, 1.0)), z)
         return recon, posterior
 
     @torch.no_grad()
@@ -199,6 +245,9 @@ class RgbaVAE(nn.Module):
         (the packed-weight cache is baked into the graph); ``reset_graphs()`` drops the captures."""
         x = _ensure_alpha(x)
         key = (tuple(x.shape), x.dtype, tuple(noise.shape), noise.dtype, tuple(tuple(b) for b in backgrounds))
+        if self._graphs and self._graphs_generation != self.vae.weights_generation:
+            self._graphs.clear()  # captured with packed copies of weights that have been updated since
+        self._graphs_generation = self.vae.weights_generation
         g = self._graphs.get(key)
         if g is None:
             sx, sn = x.clone(), noise.clone()
@@ -224,7 +273,27 @@ class RgbaVAE(nn.Module):
         self._graphs.clear()
 
     def loss(self, recon: torch.Tensor, target: torch.Tensor, posterior) -> torch.Tensor:
-        """AlphaVAE reconstruction term + beta * KL (rgba_vae.py:283-316 with the default weights of
-        configs/flux_vae.yaml; inputs in [0,1])."""
-        rec = self.loss_module.reconstruction_loss(_to_vae_range(_ensure_alpha(recon)), _to_vae_range(_ensure_alpha(target)))
-        return rec + self.beta * posterior.kl().mean()
+        """rgba_vae.py:283-316: ``rgb_loss_weight`` x (AlphaVAE map, or rgb MSE in [0,1] with ``use_naive_mse``) +
+        ``white_bg_weight`` / ``black_bg_weight`` x MSE of the composites + ``alpha_loss_weight`` x alpha MSE +
+        ``alpha_l1_weight`` x alpha L1 + ``beta`` x mean KL.  recon / target (B,3|4,H,W) in [0,1].  All pixel terms
+        come from ONE pass over the pair (``rv_rgba_loss_terms``; the reference runs ~40 elementwise kernels).
+        Difference: with ``use_naive_mse`` and the per-sample-sum reduction the reference raises (``.view`` of a
+        channel slice, rgba_vae.py:321); here that combination returns the value ``.reshape`` would give."""
+        sums = ops.rgba_loss_terms(_ensure_alpha(recon), _ensure_alpha(target), self.loss_module._eb, self.loss_module._eb2)
+        b, hw = sums.shape[0], float(recon.shape[2] * recon.shape[3])
+        mean3 = lambda col: sums[:, col].sum() / (b * 3.0 * hw)   # F.mse_loss over (B,3,H,W)
+        mean1 = lambda col: sums[:, col].sum() / (b * hw)         # over the alpha plane
+        total = self.beta * posterior.kl().mean()
+        if self.rgb_loss_weight > 0.0:
+            col = 1 if self.use_naive_mse else 0
+            base = mean3(col) if self.loss_reduce_mean else sums[:, col].mean()   # _reduce_loss, rgba_vae.py:318-322
+            total = total + self.rgb_loss_weight * base
+        if self.white_bg_weight > 0.0:
+            total = total + self.white_bg_weight * mean3(2)
+        if self.black_bg_weight > 0.0:
+            total = total + self.black_bg_weight * mean3(3)
+        if self.alpha_loss_weight > 0.0:
+            total = total + self.alpha_loss_weight * mean1(4)
+        if self.alpha_l1_weight > 0.0:
+            total = total + self.alpha_l1_weight * mean1(5)
+        return total

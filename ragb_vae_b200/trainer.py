@@ -44,7 +44,8 @@ class VaeTrainStep:
                  loss_module: Optional[AlphaVaeLoss] = None, num_buckets: int = 4, encode_triplet: bool = True, group=None,
                  ref_vae: Optional[RgbaAutoencoder] = None, ref_kl_scale: Optional[float] = None):
         if vae.arch != "qwen":
-            raise NotImplementedError("the training step covers the Qwen-Image arch (configs/flux_vae.yaml trains that VAE)")
+            raise NotImplementedError("VaeTrainStep covers arch='qwen' (RMS-norm blocks); the GroupNorm / Linear backward of "
+                                      "arch='flux' (the VAE configs/flux_vae.yaml:73 trains) is not built")
         if vae.dtype != torch.bfloat16:
             raise TypeError("the training step runs the model in bfloat16 (fp32 master weights live in the optimizer)")
         self.vae = vae
@@ -115,12 +116,18 @@ class VaeTrainStep:
         b = st.act if st.act is not None else self._norm(t, blk.norm2)
         y = self._conv(b, blk.conv2, residual=h)
         if tape is not None:
-            tape.append(("res", blk, (x, a, t, b)))
+            # gradient checkpointing (diffusers: per block): keep only the block input, recompute the rest in the backward
+            tape.append(("res", blk, (x, None, None, None) if self.vae.gradient_checkpointing else (x, a, t, b)))
         return y
 
     def _res_bwd(self, blk, saved, dy):
         x, a, t, b = saved
         short = getattr(blk, "conv_shortcut", None)
+        if a is None:  # checkpointed block: same kernels, same bits as the forward
+            a = self._norm(x, blk.norm1)
+            st = self.vae._conv_fused(a, blk.conv1, next_norm=(blk.norm2, True), want_raw=True)
+            t = st.raw
+            b = st.act if st.act is not None else self._norm(t, blk.norm2)
         db = self._conv_bwd(blk.conv2, b, dy)
         dt = self._norm_bwd(blk.norm2, t, db)
         da = self._conv_bwd(blk.conv1, a, dt)
@@ -180,7 +187,7 @@ class VaeTrainStep:
         self._gemm(o, wo, rows=n * t, k=c, cols=c, x_ld=c, w_ld=c, y=out.view(n * t, c), y_ld=c, bias=bo, bias_mode=1,
                    residual=x.view(n * t, c))
         if tape is not None:
-            tape.append(("attn", attn, (x, xn, q, k, v, o)))
+            tape.append(("attn", attn, (x,) if self.vae.gradient_checkpointing else (x, xn, q, k, v, o)))
         return out
 
     @staticmethod
@@ -188,6 +195,14 @@ class VaeTrainStep:
         return max(64, min(t, ((1 << 27) // t) // 64 * 64))
 
     def _attn_bwd(self, attn, saved, dout):
+        if len(saved) == 1:  # checkpointed block: recompute the forward with a scratch tape to get its intermediates back
+            scratch: list = []
+            ckpt, self.vae.gradient_checkpointing = self.vae.gradient_checkpointing, False
+            try:
+                self._attn_fwd(saved[0], attn, scratch)
+            finally:
+                self.vae.gradient_checkpointing = ckpt
+            saved = scratch[0][2]
         x, xn, q, k, v, o = saved
         n, h, w, c = x.shape
         t = h * w
@@ -401,6 +416,7 @@ class VaeTrainStep:
         the decoder's gradients while the encoder's backward still runs); returns the step's loss terms."""
         if not inputs.is_cuda:
             raise RvError("VaeTrainStep runs on CUDA (sm_100a) only; there is no CPU path")
+        self._check_untiled(inputs)
         if noise is None:
             b, _, h, w = inputs.shape
             noise = torch.randn((b, self.vae.config.z_dim, h // 8, w // 8), generator=generator, device=inputs.device,
@@ -410,6 +426,15 @@ class VaeTrainStep:
         self._encoder_backward(ctx)
         self._mark_ready(decoder_done=False)
         return metrics
+
+    def _check_untiled(self, inputs: torch.Tensor) -> None:
+        """The taped step differentiates the untiled encode / decode.  With ``enable_tiling()`` the reference would tile
+        (and seam-blend) any input larger than the tile -- a different function: refuse instead of silently diverging."""
+        if self.vae.use_tiling:
+            tile = self.vae._tiling()[0]
+            if inputs.shape[-1] > tile or inputs.shape[-2] > tile:
+                raise NotImplementedError(f"VaeTrainStep does not differentiate the tiled path: input {tuple(inputs.shape[-2:])} "
+                                          f"exceeds the {tile}-pixel tile; call vae.disable_tiling() (slicing is a no-op and is fine)")
 
     def _mark_ready(self, decoder_done: bool) -> None:
         """Start the all-reduce of every bucket whose parameters all have their gradients (the decoder's parameters come
@@ -438,7 +463,7 @@ class VaeTrainStep:
         metrics = self.forward_backward(inputs, noise, generator)
         scale = self.reducer.wait()
         self.opt.step(grad_scale=scale)
-        self.vae._pack_cache.clear()  # packed weights are stale after the in-place update
+        self.vae.mark_weights_changed()  # packed weights (and captured inference graphs) are stale after the in-place update
         return metrics
 
     # ---- CUDA-graph replay ------------------------------------------------------------------
@@ -448,7 +473,8 @@ class VaeTrainStep:
         NCCL all-reduces are issued eagerly BETWEEN the replays (decoder buckets after graph 1, so they overlap graph 2 on
         NCCL's stream).  ``noise`` must be supplied (the posterior's eps); the returned loss terms are views of graph 1's
         static outputs, valid until the next call."""
-        key = (tuple(inputs.shape), inputs.dtype, tuple(noise.shape), noise.dtype)
+        self._check_untiled(inputs)
+        key = (tuple(inputs.shape), inputs.dtype, tuple(noise.shape), noise.dtype, bool(self.vae.gradient_checkpointing))
         g = self._graphs.get(key)
         if g is None:
             sx, sn = inputs.clone(), noise.clone()
@@ -482,6 +508,9 @@ class VaeTrainStep:
         self._mark_ready(decoder_done=False)
         self.reducer.wait()
         g3.replay()
+        # rv_adamw_step rewrites the parameters through raw pointers (no _version bump): anything an eager call between
+        # two replays packed (validation, vae.encode ...) is stale now
+        self.vae.mark_weights_changed()
         return metrics
 
     def named_grads(self) -> Dict[str, torch.Tensor]:

@@ -58,18 +58,7 @@ def reparam_backward(moments: torch.Tensor, noise: Optional[torch.Tensor], dz: O
     return out
 
 
-def kl_to_reference(moments: torch.Tensor, ref_moments: torch.Tensor, grad_weight: Optional[float] = None):
-    """Per-sample KL(posterior || reference posterior) [n] (fp32) and, with ``grad_weight``, grad_weight * d KL / d moments
-    (rgba_vae_stage.py:489-508; DiagonalGaussianDistribution.kl(other))."""
-    _need_cuda(moments, ref_moments)
-    moments = moments.contiguous()
-    ref_moments = ref_moments.to(moments.dtype).contiguous()
-    n, c2, h, w = moments.shape
-    kl = torch.zeros(n, dtype=torch.float32, device=moments.device)
-    dm = torch.empty_like(moments) if grad_weight is not None else None
-    check(_lib.load().rv_kl_ref(_ptr(moments), _ptr(ref_moments), _ptr(kl), _ptr(dm), n, c2 // 2, h * w, _dt(moments),
-                                0.0 if grad_weight is None else float(grad_weight), _stream(moments)), "rv_kl_ref")
-    return kl, dm
+kl_to_reference = ops.kl_to_reference  # lives with the other posterior ops; kept here for the trainer's imports
 
 
 def rmsnorm_silu_backward(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, silu: bool = True,

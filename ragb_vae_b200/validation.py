@@ -11,7 +11,7 @@ from typing import Dict, Iterable, Optional, Sequence, Union
 import torch
 
 from . import ops
-from .rgba_vae import RgbaVAE, background_rgb
+from .rgba_vae import RgbaVAE, _ensure_alpha, background_rgb
 
 NAMED_BACKGROUNDS = {"white": 1.0, "black": 0.0}
 
@@ -21,7 +21,7 @@ def resolve_background_spec(name: Union[str, float, Sequence[float]]):
     if isinstance(name, str):
         key = name.lower()
         if key not in NAMED_BACKGROUNDS:
-            raise ValueError(f"Unsupported background color '{name}'.")
+            raise ValueError(f"Unknown background spec '{name}'.")
         return NAMED_BACKGROUNDS[key]
     return name
 
@@ -31,7 +31,7 @@ def validation_metrics(recon: torch.Tensor, inputs: torch.Tensor,
     """Per-sample ``{"psnr_<bg>": (B,), ..., "alpha_mae": (B,)}`` in fp32; recon / inputs (B,4,H,W) in [0,1]."""
     specs = [background_rgb(resolve_background_spec(b)) for b in backgrounds]
     out = ops.composite_psnr(recon, inputs, specs)
-    res = {f"psnr_{b}": out[:, i] for i, b in enumerate(backgrounds)}
+    res = {f"psnr_{b}": out[:, i] for i, b in enumerate(backgrounds)}   # keys as the reference prints them (:770)
     res["alpha_mae"] = out[:, len(specs)]
     return res
 
@@ -52,19 +52,16 @@ def evaluate_rgba_vae(model: RgbaVAE, batches: Iterable[torch.Tensor],
     """The loop of evaluate_rgba_vae (rgba_vae_stage.py:718-784): recon = model(inputs), composite
     over each background, PSNR + alpha MAE per sample, mean over all samples.  Metrics stay on the
     device until the end (the reference gathers + .cpu()s every batch)."""
+    names = [f"psnr_{b}" for b in backgrounds] + ["alpha_mae"]
     sums, count = None, 0
     noise_it = iter(noises) if noises is not None else None
-    for inputs in batches:
-        inputs = torch.clamp(inputs, 0.0, 1.0) if inputs.dtype == torch.float32 else inputs
+    for inputs in batches:   # inputs are used as they come, like the reference (no clamp)
         noise = next(noise_it) if noise_it is not None else None
         recon, _ = model(inputs, noise=noise)
-        m = validation_metrics(recon, inputs if inputs.shape[1] == 4 else torch.cat([inputs, torch.ones_like(inputs[:, :1])], 1),
-                               backgrounds)
-        vec = torch.stack([v.double().sum() for v in m.values()])
+        m = validation_metrics(recon, _ensure_alpha(inputs), backgrounds)
+        vec = torch.stack([m[k].double().sum() for k in names])
         sums = vec if sums is None else sums + vec
         count += inputs.shape[0]
-        keys = list(m.keys())
     if sums is None:
         return {}
-    vals = (sums / count).cpu().tolist()
-    return dict(zip(keys, vals))
+    return dict(zip(names, (sums / count).cpu().tolist()))
