@@ -322,3 +322,68 @@ def test_training_on_a_fixed_batch_reduces_the_loss(lib_built):
     assert sum(losses[-10:]) / 10 < 0.6 * losses[0], (losses[:5], losses[-10:])
     assert p1 > p0 + 0.5, (p0, p1)
     assert torch.isfinite(step.opt.master).all()
+
+
+def test_validation_between_graph_replays_sees_the_current_weights(lib_built):
+    """rv_adamw_step rewrites the parameters through raw pointers: neither data_ptr nor _version moves, so an eager
+    evaluation between two replays must not keep serving packed copies of older weights (the reference loop validates
+    periodically during training).  The second evaluation must equal a fresh model loaded from the state dict."""
+    import ragb_vae_b200 as R
+    from ragb_vae_b200.trainer import VaeTrainStep
+
+    oracle = O.build_oracle("qwen", seed=4)
+    x = O.synthetic_rgba(2, 64, 64, seed=41).cuda()
+    noise = torch.randn(2, 16, 8, 8, generator=torch.Generator().manual_seed(42)).cuda()
+    vae = R.RgbaAutoencoder("qwen")
+    vae.load_state_dict(oracle.state_dict())
+    vae = vae.to("cuda", torch.bfloat16)
+    model = R.RgbaVAE(vae)
+    step = VaeTrainStep(vae, lr=1e-2, kl_scale=1e-6)   # large steps so stale weights would be visible
+    xb = x.bfloat16()
+    step.step_graphed(x, noise)
+    first = R.evaluate_rgba_vae(model, [xb], noises=[noise])            # packs the weights eagerly
+    rg_first, _, _ = model.forward_graphed(xb, noise.bfloat16())        # ... and bakes them into an inference graph
+    rg_first = rg_first.clone()
+    step.step_graphed(x, noise)
+    step.step_graphed(x, noise)
+    second = R.evaluate_rgba_vae(model, [xb], noises=[noise])
+    rg_second, _, _ = model.forward_graphed(xb, noise.bfloat16())
+    fresh_vae = R.RgbaAutoencoder("qwen")
+    fresh_vae.load_state_dict({k: v.float().cpu() for k, v in vae.state_dict().items()})
+    fresh_model = R.RgbaVAE(fresh_vae.to("cuda", torch.bfloat16))
+    fresh = R.evaluate_rgba_vae(fresh_model, [xb], noises=[noise])
+    assert second == fresh, "evaluation after further replays served stale packed weights"
+    assert first != second, "three optimizer steps at lr 1e-2 must move the metrics"
+    recon_fresh, _ = fresh_model(xb, noise=noise)
+    assert torch.equal(rg_second, recon_fresh) and not torch.equal(rg_first, rg_second)
+
+
+def test_gradient_checkpointing_recomputes_the_same_gradients(lib_built):
+    """enable_gradient_checkpointing(): residual / attention blocks keep only their input and recompute the rest with
+    the same kernels, so loss terms are identical and gradients agree up to the split-K atomics' summation order."""
+    import ragb_vae_b200 as R
+    from ragb_vae_b200.trainer import VaeTrainStep
+
+    oracle = O.build_oracle("qwen", seed=5)
+    x = O.synthetic_rgba(2, 64, 64, seed=51).cuda()
+    noise = torch.randn(2, 16, 8, 8, generator=torch.Generator().manual_seed(52)).cuda()
+    grads, losses = [], []
+    for ckpt in (False, True):
+        vae = R.RgbaAutoencoder("qwen")
+        vae.load_state_dict(oracle.state_dict())
+        vae = vae.to("cuda", torch.bfloat16)
+        if ckpt:
+            vae.enable_gradient_checkpointing()
+        step = VaeTrainStep(vae, kl_scale=1e-6)
+        m = step.forward_backward(x, noise)
+        step.reducer.wait()
+        losses.append(float(m["train/loss"]))
+        grads.append(step.opt.grad.clone())
+    assert losses[0] == losses[1]
+    assert rel(grads[1], grads[0]) < 1e-4 and cos(grads[1], grads[0]) > 0.99999
+    # the tiled path is a different function: refused, not silently untiled
+    vae.enable_tiling()
+    big = O.synthetic_rgba(1, 264, 264, seed=53).cuda()
+    with pytest.raises(NotImplementedError):
+        step.forward_backward(big)
+    vae.disable_tiling()
