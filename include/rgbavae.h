@@ -26,8 +26,8 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 18
-#define RV_PROF_CATEGORIES 9
+#define RV_ABI_VERSION 19
+#define RV_PROF_CATEGORIES 10
 
 int rv_abi_version(void);
 const char* rv_last_error(void);
@@ -38,9 +38,11 @@ int rv_init(void);
 int64_t rv_launch_count(void);
 /* Per-category device timing with CUDA events recorded on the launching stream, for the
  * roofline figures in bench.py.  Categories: 0 tcgen05 conv/GEMM, 1 direct conv, 2 norm+SiLU,
- * 3 softmax, 4 layout, 5 reparam, 6 recon loss, 7 composite+PSNR, 8 fused attention.
+ * 3 softmax, 4 layout, 5 reparam, 6 recon loss, 7 composite+PSNR, 8 fused attention, 9 the nearest-x2
+ * up-sampling convs (tcgen05, phase-folded: booked at the algorithmic 3x3-on-the-upsampled-grid FLOPs as the
+ * reference computes them, executing 4/9 of that).
  * rv_prof_end synchronises the device and fills ms[c] (summed kernel time), launches[c] and
- * work[c] (algorithmic FLOPs for 0/1/8, algorithmic bytes for the others). */
+ * work[c] (algorithmic FLOPs for 0/1/8/9, algorithmic bytes for the others). */
 int rv_prof_begin(void);
 int rv_prof_end(double* ms, int64_t* launches, double* work);
 
@@ -144,12 +146,6 @@ int rv_nchw_to_nhwc_hpack(const void* x, void* y, int n, int c, int h, int w, in
                           void* stream);
 int rv_nhwc_to_nchw(const void* x, void* y, int n, int c, int64_t hw, int x_cstride, int x_dtype,
                     int y_dtype, void* stream);
-
-/* 3x3 / pad-1 im2col of a few-channel NCHW boundary image (the 4-channel RGBA input of conv_in,
- * src/models/rgba_vae.py:277 with _to_vae_range fused as scale/shift) into NHWC rows of `kpad` elements:
- * y[n][h][w][tap*c + ch], zeros outside the image and past 9*c.  conv_in then is a K=kpad GEMM. */
-int rv_im2col3x3(const void* x, void* y, int n, int c, int h, int w, int kpad, int x_dtype, int y_dtype,
-                 float scale, float shift, void* stream);
 
 /* ---- data formats either side of the VAE ----------------------------------- */
 /* build_detail_augmented_triplet (src/training/rgba_vae_stage.py:606-625): target NCHW [b][4][hw] in [-1,1] ->

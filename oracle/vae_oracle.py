@@ -65,12 +65,12 @@ class DiagonalGaussianDistribution:
         # diffusers draws randn_tensor(mean.shape, generator, device, dtype); a supplied
         # noise tensor is our extension so that parity is definable.
         if noise is None:
-            noise = torch.randn(self.mean.shape, generator=generator, dtype=self.parameters.dtype)
+            noise = torch.randn(self.mean.shape, generator=generator, dtype=self.parameters.dtype, device=self.parameters.device)
         return self.mean + self.std * noise.to(self.mean.dtype)
 
     def kl(self, other: "Optional[DiagonalGaussianDistribution]" = None) -> torch.Tensor:
         if self.deterministic:
-            return torch.tensor([0.0])
+            return torch.tensor([0.0], device=self.parameters.device)
         if other is None:
             return 0.5 * torch.sum(self.mean.pow(2) + self.var - 1.0 - self.logvar, dim=[1, 2, 3])
         return 0.5 * torch.sum(
@@ -445,7 +445,7 @@ def build_oracle(arch: str, seed: int = 0, rgba_random: bool = True) -> OracleVA
 def ensure_alpha(x):  # src/models/rgba_vae.py:25-29
     if x.shape[1] == 4:
         return x
-    return torch.cat([x, torch.ones((x.shape[0], 1, x.shape[2], x.shape[3]), dtype=x.dtype)], dim=1)
+    return torch.cat([x, torch.ones((x.shape[0], 1, x.shape[2], x.shape[3]), dtype=x.dtype, device=x.device)], dim=1)
 
 
 def to_vae_range(x):  # :32-33
@@ -460,7 +460,7 @@ def normalize_background(background, reference):  # :40-72
     dtype = reference.dtype
     batch, _, height, width = reference.shape
     if isinstance(background, torch.Tensor):
-        bg = background.to(dtype=dtype)
+        bg = background.to(device=reference.device, dtype=dtype)
         if bg.dim() == 3:
             bg = bg.unsqueeze(0)
         if bg.dim() != 4:
@@ -475,8 +475,8 @@ def normalize_background(background, reference):  # :40-72
     if isinstance(background, Sequence):
         if len(background) != 3:
             raise ValueError("Background color sequence must contain exactly three values.")
-        return torch.tensor(background, dtype=dtype).view(1, 3, 1, 1).expand(batch, -1, height, width)
-    return torch.full((batch, 3, height, width), float(background), dtype=dtype)
+        return torch.tensor(background, dtype=dtype, device=reference.device).view(1, 3, 1, 1).expand(batch, -1, height, width)
+    return torch.full((batch, 3, height, width), float(background), dtype=dtype, device=reference.device)
 
 
 def composite_over_background(rgba, background):  # :75-84
@@ -489,18 +489,18 @@ def adapt_vae_to_rgba(vae, alpha_bias_init: float = 0.0) -> None:  # :95-123 (ra
     conv_in = vae.encoder.conv_in
     if conv_in.in_channels != 4:
         w = conv_in.weight.data
-        nw = torch.zeros(w.size(0), 4, *w.shape[2:], dtype=w.dtype)
+        nw = torch.zeros(w.size(0), 4, *w.shape[2:], dtype=w.dtype, device=w.device)
         nw[:, :3] = w
         conv_in.in_channels = 4
         conv_in.weight = nn.Parameter(nw)
     conv_out = vae.decoder.conv_out
     if conv_out.out_channels != 4:
         w = conv_out.weight.data
-        nw = torch.zeros(4, w.size(1), *w.shape[2:], dtype=w.dtype)
+        nw = torch.zeros(4, w.size(1), *w.shape[2:], dtype=w.dtype, device=w.device)
         nw[:3] = w
         conv_out.out_channels = 4
         conv_out.weight = nn.Parameter(nw)
-        nb = torch.zeros(4, dtype=w.dtype)
+        nb = torch.zeros(4, dtype=w.dtype, device=w.device)
         nb[:3] = conv_out.bias.data
         nb[3] = alpha_bias_init
         conv_out.bias = nn.Parameter(nb)
@@ -532,8 +532,8 @@ def reconstruction_loss(pred, target, reduce_mean=False, use_naive_mse=False, eb
     """AlphaVaeLoss.reconstruction_loss (src/models/losses.py:67-83); inputs in [-1, 1] RGBA."""
     if use_naive_mse:
         return reduce_loss((pred - target).pow(2), reduce_mean)
-    eb_t = torch.tensor(eb, dtype=torch.float32).view(1, 3, 1, 1)
-    eb2_t = torch.tensor(eb2, dtype=torch.float32).view(1, 3, 1, 1)
+    eb_t = torch.tensor(eb, dtype=torch.float32, device=pred.device).view(1, 3, 1, 1)
+    eb2_t = torch.tensor(eb2, dtype=torch.float32, device=pred.device).view(1, 3, 1, 1)
     ta = (target[:, 3:] + 1.0) * 0.5
     pa = (pred[:, 3:] + 1.0) * 0.5
     d = target[:, :3] * ta - pred[:, :3] * pa

@@ -9,10 +9,10 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "librgbavae.so")
 
 RV_F32, RV_BF16 = 0, 1
-ABI_VERSION = 18
-PROF_CATEGORIES = 9
+ABI_VERSION = 19
+PROF_CATEGORIES = 10
 PROF_NAMES = ("conv_tc", "conv_direct", "norm_silu", "softmax", "layout", "reparam", "recon_loss", "composite_psnr",
-              "attention")
+              "attention", "conv_tc_upsample")
 
 
 class RvError(RuntimeError):
@@ -63,7 +63,6 @@ SIGNATURES = {
     "rv_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _L, _I, _I, _I, _F, _F, _P]),
     "rv_nchw_to_nhwc_hpack": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _F, _P]),
     "rv_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _L, _I, _I, _I, _P]),
-    "rv_im2col3x3": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
     "rv_triplet_augment": (_I, [_P, _P, _I, _L, _I, _P]),
     "rv_background_blend": (_I, [_P, _P, _P, _P, _I, _L, _I, _P]),
     "rv_pack_latents": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _F, _I, _P]),

@@ -332,7 +332,6 @@ class RgbaAutoencoder(nn.Module):
         self.fuse_norm_residual = False
         self.fused_attention = True
         self.hpack_stem = True    # conv_in as 3 vertical taps over a horizontally packed 16-channel image (see _stem)
-        self.im2col_stem = False  # measured slower (3.5 ms) than 16-channel padding + 9 narrow K blocks (2.6 ms) at 8x1024^2
         self.fuse_norm = True  # RMS norm + SiLU in the producing conv's epilogue where one tile holds all channels
         self._pack_cache: Dict[tuple, tuple] = {}
         self.weights_generation = 0
@@ -533,16 +532,6 @@ class RgbaAutoencoder(nn.Module):
 
         return self._cached((id(conv), "hpack"), [conv.weight], build)
 
-    def _im2col_weights(self, conv: Conv, kpad: int):
-        """[cout][cin][3][3] -> bf16 [cout][kpad] in im2col order ([tap][cin], zero padded)."""
-        def build():
-            w = conv.weight2d().detach().to(torch.float32)
-            m = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
-            m = torch.nn.functional.pad(m, (0, kpad - m.shape[1]))
-            return m.to(torch.bfloat16).contiguous()
-
-        return self._cached((id(conv), "im2col", kpad), [conv.weight], build)
-
     # ---- building blocks -----------------------------------------------------------------
     def _mode(self):
         dt = self.dtype
@@ -567,15 +556,13 @@ class RgbaAutoencoder(nn.Module):
     def _conv_fused(self, x: torch.Tensor, conv: Conv, *, upsample: bool = False, residual: Optional[torch.Tensor] = None,
                     y_nchw: bool = False, y_dtype: Optional[torch.dtype] = None, out_scale: float = 1.0,
                     out_shift: float = 0.0, clamp=None, next_norm=None, want_raw: bool = True,
-                    im2col: bool = False, hpack: bool = False) -> "_Stream":
+                    hpack: bool = False) -> "_Stream":
         """Convolution whose result feeds ``next_norm = (norm_module, silu)``: where possible that norm is fused
         into the epilogue (second output ``act``); ``want_raw=False`` drops the raw tensor when only the
         normalised one is consumed (conv1 -> norm2 -> conv2 inside a residual block)."""
         tc, act_dt, code = self._mode()
         n, h, w, cx = x.shape
         cin, cout, k, stride = conv.in_channels, conv.out_channels, conv.k, conv.stride
-        if im2col:  # x already holds the 3x3 neighbourhood per pixel: the conv is a 1x1 over cx = 64 "channels"
-            k = 1
         oh, ow = ops.conv_out_size(h, w, k, stride, upsample)
         y_dt = act_dt if y_dtype is None else y_dtype
         bias = self._f32(conv.bias, "bias")
@@ -593,7 +580,7 @@ class RgbaAutoencoder(nn.Module):
             if hpack:
                 wp = self._hpack_weights(conv)
             else:
-                wp = self._im2col_weights(conv, cx) if im2col else self._conv_weights(conv, True, upsample, cin_pad=cx)
+                wp = self._conv_weights(conv, True, upsample, cin_pad=cx)
             if fuse:
                 norm, silu = next_norm
                 act = torch.empty((n, oh, ow, cout), dtype=y_dt, device=x.device)
@@ -740,10 +727,6 @@ class RgbaAutoencoder(nn.Module):
         tc, act_dt, code = self._mode()
         n, c, h, w = x.shape
         x = x.contiguous()
-        if tc and self.im2col_stem and conv.k == 3 and 9 * c <= 64:
-            # few-channel 3x3 stem (conv_in, Cin = 4): im2col to one 64-wide K block, then a plain GEMM
-            xp = ops.im2col3x3(x, 64, act_dt, in_scale, in_shift)
-            return self._conv_fused(xp, conv, next_norm=next_norm, im2col=True)
         if tc and self.hpack_stem and conv.k == 3 and conv.stride == 1 and 3 * c <= 16:
             # few-channel 3x3 stem (conv_in, Cin = 4): the three horizontal neighbours ride in the pixel's 16 channels,
             # the conv runs as 3 vertical taps of K = 16 (3 MMAs + 3 TMA boxes per tile instead of 9 + 9)

@@ -25,6 +25,7 @@ enum Category {
   CAT_LOSS = 6,
   CAT_PSNR = 7,
   CAT_ATTN = 8,
+  CAT_CONV_UPS = 9,  // phase-folded up-sampling convs: booked at the algorithmic 3x3 cost, executing 4/9 of it
   CAT_COUNT = RV_PROF_CATEGORIES
 };
 

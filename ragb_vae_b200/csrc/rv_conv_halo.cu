@@ -40,9 +40,12 @@ constexpr int HL_BRING_MAX = 8;   // CTA pairs hold half a tap per slot: the sam
 constexpr int HL_EPI_WARPS = 8;
 constexpr int HL_THREADS = 128 + 32 * HL_EPI_WARPS;  // row-TMA, MMA (row 0), weight-TMA, MMA (row 1), 8 epilogue warps
 constexpr int HL_PIX = 130;                          // 128 output columns + halo
-constexpr uint32_t HL_R128_BYTES = 17408;            // 130 x 128 B rounded up to 1024
-constexpr uint32_t HL_R64_BYTES = 9216;              // 130 x 64 B rounded up to 1024
-constexpr uint32_t HL_SMEM_MAX = 227 * 1024 - 7168;  // dynamic budget next to ~6.3 KB of static shared memory
+// Row slots are packed at 128-byte granularity (TMA's destination alignment), not at the 1024-byte swizzle period: TMA and
+// UMMA both derive the swizzle XOR from the ABSOLUTE shared-memory address, so a slot may start at any 128-byte row (the
+// same property that lets the A descriptor start at row dx).  The 10 KB this saves over six slots pays for the staging boxes.
+constexpr uint32_t HL_R128_BYTES = 130 * 128;        // [130 pixels][64 ch] SWIZZLE_128B
+constexpr uint32_t HL_R64_BYTES = 130 * 64;          // [130 pixels][32 ch] SWIZZLE_64B
+constexpr uint32_t HL_SMEM_MAX = 227 * 1024 - 4096;  // dynamic budget next to < 4 KB of static shared memory
 
 struct HaloParams {
   int n_img, h, w;
@@ -90,7 +93,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a128, const __grid_cons
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_bias[128];
   __shared__ __align__(16) float s_gamma[128];
-  __shared__ float s_ss[2][2][2][128];  // [accumulator buffer][tile row][column half][pixel]
+  // [tile row][column half][pixel]: fused-norm partial sums.  One copy serves both accumulator buffers: the two warps that
+  // exchange through a slot meet at the row's named barrier, and meet again (other row) before either reuses the slot.
+  __shared__ float s_ss[2][2][128];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -311,36 +316,36 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a128, const __grid_cons
     const int cb = nsplit == 2 ? half * (p.bn >> 1) : 0;
     const int ce = nsplit == 2 ? cb + (p.bn >> 1) : (half == 0 ? p.bn : 0);
     const float* sbias = p.e.bias_mode == 1 ? s_bias : nullptr;
-    uint32_t tc = 0;
-    for (int u = unit0; u < total_units; u += unit_step) {
-      const StripCoord c = decode_strip<PAIR>(p, PAIR ? 2 * u + (int)rank : u);
-      const int ntiles = c.rows >> 1;
-      const int x = c.x0 + row;
-      for (int j = 0; j < ntiles; ++j) {
-        const uint32_t buf = tc & 1u;
-        mbar_wait(accfull0 + 8u * buf, (tc >> 1) & 1u);
-        tc_fence_after();
-        for (int r = 0; r < 2; ++r) {
-          const int y = c.ys + 2 * j + r;
-          const bool valid = x < p.w && y < p.h;
-          const int64_t pix = ((int64_t)c.img * p.h + y) * p.w + x;
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2u * (uint32_t)p.bn + (uint32_t)r * (uint32_t)p.bn;
-          if (!p.e.fast)  // NCHW / fp32 / affine / clamp outputs (conv_out): generic epilogue
-            epilogue_pixel(p.e, taddr, cb, ce, 0, valid, c.img, y, x, pix);
-          else if (p.e.residual)
-            epilogue_pixel_fast<true>(p.e, sbias, s_gamma, taddr, cb, ce, 0, valid, pix, &s_ss[buf][r][0][0], row, half, nsplit,
-                                      1 + q);
-          else
-            epilogue_pixel_fast<false>(p.e, sbias, s_gamma, taddr, cb, ce, 0, valid, pix, &s_ss[buf][r][0][0], row, half, nsplit,
-                                       1 + q);
+    {
+      uint32_t tc = 0;
+      for (int u = unit0; u < total_units; u += unit_step) {
+        const StripCoord c = decode_strip<PAIR>(p, PAIR ? 2 * u + (int)rank : u);
+        const int ntiles = c.rows >> 1;
+        const int x = c.x0 + row;
+        for (int j = 0; j < ntiles; ++j) {
+          const uint32_t buf = tc & 1u;
+          mbar_wait(accfull0 + 8u * buf, (tc >> 1) & 1u);
+          tc_fence_after();
+          for (int r = 0; r < 2; ++r) {
+            const int y = c.ys + 2 * j + r;
+            const bool valid = x < p.w && y < p.h;
+            const int64_t pix = ((int64_t)c.img * p.h + y) * p.w + x;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2u * (uint32_t)p.bn + (uint32_t)r * (uint32_t)p.bn;
+            if (!p.e.fast)  // NCHW / fp32 / affine / clamp outputs (conv_out): generic epilogue
+              epilogue_pixel(p.e, taddr, cb, ce, 0, valid, c.img, y, x, pix);
+            else if (p.e.residual)
+              epilogue_pixel_fast<true>(p.e, sbias, s_gamma, taddr, cb, ce, 0, valid, pix, &s_ss[r][0][0], row, half, nsplit, 1 + q);
+            else
+              epilogue_pixel_fast<false>(p.e, sbias, s_gamma, taddr, cb, ce, 0, valid, pix, &s_ss[r][0][0], row, half, nsplit, 1 + q);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(lead_accempty0 + 8u * buf);
+            else mbar_arrive(accempty0 + 8u * buf);
+          }
+          ++tc;
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (PAIR) mbar_arrive_cluster(lead_accempty0 + 8u * buf);
-          else mbar_arrive(accempty0 + 8u * buf);
-        }
-        ++tc;
       }
     }
   }
@@ -376,7 +381,7 @@ bool halo_eligible(const rv_conv_desc* d, const EpiParams& e) {
   const int nk128 = d->cin / 64, has64 = (d->cin % 64) ? 1 : 0;
   const uint32_t row_slot = nk128 * HL_R128_BYTES + has64 * HL_R64_BYTES;
   const uint32_t b_slot = ((uint32_t)((d->cout + 15) / 16 * 16) * (uint32_t)d->cin * 2u + 1023u) & ~1023u;
-  return HL_RING * row_slot + HL_BRING * b_slot + 1024u <= HL_SMEM_MAX;
+  return ((HL_RING * row_slot + 1023u) & ~1023u) + HL_BRING * b_slot + 1024u <= HL_SMEM_MAX;
 }
 
 int launch_halo(const rv_conv_desc* d, const void* x, const void* w, int64_t w_ld, const float* bias, const void* residual,
@@ -395,21 +400,21 @@ int launch_halo(const rv_conv_desc* d, const void* x, const void* w, int64_t w_l
   p.row_tx_bytes = (uint32_t)HL_PIX * (uint32_t)(p.nk128 * 128 + p.has64 * 64);
   p.col_blocks = (d->w + 127) / 128;
   // CTA pairs (cta_group::2): the weight tap splits into two halves of whole 8-row swizzle groups and the strips pair up
-  // Opt-in (RGBAVAE_HALO_PAIR=1): measured on the 96-channel 1024^2 layers the pair form is NOT faster today (0.74 vs
-  // 0.78 PFLOP/s) because the kernel is paced by its epilogue / output stream, not by operand reads -- with the epilogue
-  // switched off it reaches ~1.7 PFLOP/s against 1.14 for the single-CTA form.
-  static const bool want_pair = getenv("RGBAVAE_HALO_PAIR") != nullptr;
+  // whenever the image x column-block count is even.  (The pair form lost to the single-CTA one as long as the peer's
+  // accumulator release was a cluster-scope RELEASE arrive -- every epilogue warp drained its global loads / stores before
+  // each arrive; with the plain arrive it is 11-14 % faster on the 96-channel 1024^2 layers: DESIGN.md 4, item 13.)
+  static const bool want_pair = getenv("RGBAVAE_HALO_NO_PAIR") == nullptr;
   const bool pair = want_pair && p.bn % 32 == 0 && ((d->n * p.col_blocks) % 2 == 0);
   const uint32_t bn_cta = pair ? (uint32_t)p.bn / 2u : (uint32_t)p.bn;
   p.b64_off = (uint32_t)p.nk128 * bn_cta * 128u;
   p.b_tx_bytes = bn_cta * (uint32_t)d->cin * 2u;  // per CTA; full box bytes (rows past cout are zero-filled)
   p.b_slot_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
-  p.bring_off = HL_RING * p.row_slot_bytes;
   p.bring_slots = HL_BRING;
   fill_epi(&p.e, d, bias, residual, y, nf);
   p.e.fast = epi_fast_ok(p.e, d, bias, nf, p.bn) ? 1 : 0;
-  if (pair) {  // half-tap slots: the single-CTA ring's bytes (and the smem budget) give a deeper weight ring
-    p.bring_slots = (int)((HL_SMEM_MAX - 1024u - HL_RING * p.row_slot_bytes) / p.b_slot_bytes);
+  p.bring_off = (HL_RING * p.row_slot_bytes + 1023u) & ~1023u;
+  if (pair) {  // half-tap slots: the single-CTA ring's bytes (and the rest of the budget) give a deeper weight ring
+    p.bring_slots = (int)((HL_SMEM_MAX - 1024u - p.bring_off) / p.b_slot_bytes);
     if (p.bring_slots > HL_BRING_MAX) p.bring_slots = HL_BRING_MAX;
   }
   // strips: ~12 per SM, an even number of rows each, at least 8
@@ -440,7 +445,7 @@ int launch_halo(const rv_conv_desc* d, const void* x, const void* w, int64_t w_l
     cuuint32_t box64[2] = {32, (cuuint32_t)bn_cta};
     if (int rc = tc_encode_map(&mb64, w, 2, dims, str, box64, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
   }
-  const size_t smem = (size_t)HL_RING * p.row_slot_bytes + (size_t)p.bring_slots * p.b_slot_bytes + 1024;
+  const size_t smem = (size_t)p.bring_off + (size_t)p.bring_slots * p.b_slot_bytes + 1024;
   {
     std::lock_guard<std::mutex> lk(g_halo_mu);
     int dev = 0;

@@ -687,7 +687,7 @@ static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_
   }
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   const double flops = 2.0 * (double)d->n * d->oh * d->ow * d->cout * d->cin * d->ksize * (d->taps_1d ? 1 : d->ksize) / (phase >= 0 ? 4.0 : 1.0);
-  LaunchScope scope(CAT_CONV_TC, st, flops);
+  LaunchScope scope(phase >= 0 ? CAT_CONV_UPS : CAT_CONV_TC, st, flops);
   if (pair) {
     const int total_pt = ((p.m_tiles + 1) / 2) * p.n_tiles;
     const int max_pairs = num_sms() / 2;

@@ -446,41 +446,6 @@ __global__ void nhwc_to_nchw_kernel(const TX* __restrict__ x, TY* __restrict__ y
 
 
 // ------------------------------------------------------------------------------------------
-// 3x3 im2col of a few-channel NCHW boundary image into a 64-wide NHWC bf16/fp32 row per pixel:
-// y[n][h][w][tap*c + ch] = x[n][ch][h+dy-1][w+dx-1]*scale+shift (zero outside the image / past 9c).
-// It turns conv_in (Cin = 4, K = 36) into a single-K-block GEMM for the tensor-core kernel instead of
-// nine K=16 blocks that are 75 % padding.
-// ------------------------------------------------------------------------------------------
-template <typename TX, typename TY>
-__global__ void __launch_bounds__(256) im2col3x3_kernel(const TX* __restrict__ x, TY* __restrict__ y, int c, int h, int w,
-                                                       int kpad, float scale, float shift) {
-  // one thread per 16-byte chunk of an output row: consecutive threads write consecutive chunks (coalesced)
-  using V = Vec16<TY>;
-  const int n = blockIdx.z;
-  const int py = blockIdx.y;
-  const int cpp = kpad / V::N;  // chunks per pixel
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int px = t / cpp, chunk = t - px * cpp;
-  if (px >= w) return;
-  const int64_t hw = (int64_t)h * w;
-  const TX* xb = x + (int64_t)n * c * hw;
-  V o;
-#pragma unroll
-  for (int j = 0; j < V::N; ++j) {
-    const int k = chunk * V::N + j;
-    float v = 0.f;
-    if (k < 9 * c) {
-      const int tap = k / c, ch = k - tap * c;
-      const int dy = tap / 3, dx = tap - 3 * dy;
-      const int iy = py + dy - 1, ix = px + dx - 1;
-      if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = ldf(xb + (int64_t)ch * hw + (int64_t)iy * w + ix) * scale + shift;
-    }
-    o.set(j, v);
-  }
-  o.store(y + (((int64_t)n * h + py) * w + px) * kpad + chunk * V::N);
-}
-
-// ------------------------------------------------------------------------------------------
 // DiagonalGaussianDistribution.sample with a supplied noise tensor (+ optional KL)
 // ------------------------------------------------------------------------------------------
 template <typename T>
@@ -673,31 +638,6 @@ int rv_nhwc_to_nchw(const void* x, void* y, int n, int c, int64_t hw, int x_cstr
                                                                                (__nv_bfloat16*)y, c, hw, x_cstride);
   else
     RV_CHECK_ARG(false, "nhwc_to_nchw: bad dtype");
-  RV_LAUNCH_CHECK();
-  return 0;
-}
-
-int rv_im2col3x3(const void* x, void* y, int n, int c, int h, int w, int kpad, int x_dtype, int y_dtype, float scale,
-                 float shift, void* stream) {
-  RV_CHECK_ARG(x && y && n > 0 && c > 0 && h > 0 && w > 0, "im2col3x3: bad argument");
-  RV_CHECK_ARG(9 * c <= kpad, "im2col3x3: 9*c (%d) must fit kpad (%d)", 9 * c, kpad);
-  cudaStream_t st = (cudaStream_t)stream;
-  const int vn = y_dtype == RV_F32 ? 4 : 8;
-  RV_CHECK_ARG(kpad % vn == 0 && (uintptr_t)y % 16 == 0, "im2col3x3: kpad must be a multiple of %d and y 16-byte aligned", vn);
-  dim3 grid((unsigned)(((int64_t)w * (kpad / vn) + 255) / 256), (unsigned)h, (unsigned)n);
-  rv::LaunchScope scope(rv::CAT_LAYOUT, st,
-                        (double)n * h * w * (c * (x_dtype == RV_F32 ? 4.0 : 2.0) + kpad * (y_dtype == RV_F32 ? 4.0 : 2.0)));
-  if (x_dtype == RV_F32 && y_dtype == RV_BF16)
-    rv::im2col3x3_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)x, (__nv_bfloat16*)y, c, h, w, kpad, scale, shift);
-  else if (x_dtype == RV_BF16 && y_dtype == RV_BF16)
-    rv::im2col3x3_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, c, h, w, kpad,
-                                                                            scale, shift);
-  else if (x_dtype == RV_F32 && y_dtype == RV_F32)
-    rv::im2col3x3_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, c, h, w, kpad, scale, shift);
-  else if (x_dtype == RV_BF16 && y_dtype == RV_F32)
-    rv::im2col3x3_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (float*)y, c, h, w, kpad, scale, shift);
-  else
-    RV_CHECK_ARG(false, "im2col3x3: bad dtype");
   RV_LAUNCH_CHECK();
   return 0;
 }

@@ -117,8 +117,12 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Arrive on a barrier that may live in the peer CTA.  Default semantics (.release at CTA scope), NOT .release.cluster: the
+// barriers signalled this way hand over TMEM accumulators / operand slots, whose ordering comes from tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync; a cluster-scope release made every epilogue warp drain its outstanding global loads and
+// stores first (MEMBAR.ALL + ERRBAR: 22 % of all stall samples of the CTA-pair halo kernel, profiles/r02_*).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads whose completion is signalled on a barrier that may live in the peer CTA (the leader's full barrier)
 __device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2,

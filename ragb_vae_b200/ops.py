@@ -207,17 +207,6 @@ def nchw_to_nhwc_hpack(x: torch.Tensor, scale: float = 1.0, shift: float = 0.0) 
     return y
 
 
-def im2col3x3(x: torch.Tensor, kpad: int, out_dtype: torch.dtype, scale: float = 1.0, shift: float = 0.0):
-    """(N,C,H,W) -> (N,H,W,kpad): the 3x3 neighbourhood of every pixel, tap-major ([tap][c]), zero padded."""
-    _need_cuda(x)
-    n, c, h, w = x.shape
-    x = x.contiguous()
-    y = torch.empty((n, h, w, kpad), dtype=out_dtype, device=x.device)
-    check(_lib.load().rv_im2col3x3(_ptr(x), _ptr(y), n, c, h, w, kpad, _dt(x), _dt(y), scale, shift, _stream(x)),
-          "rv_im2col3x3")
-    return y
-
-
 def nhwc_to_nchw(x: torch.Tensor, c: int, out_dtype: torch.dtype):
     _need_cuda(x)
     n, h, w, cs = x.shape

@@ -239,6 +239,10 @@ class GradientAllReducer:
         edges = [n - (n * i) // num_buckets for i in range(num_buckets + 1)]  # n ... 0
         self.buckets = [(edges[i + 1], edges[i]) for i in range(num_buckets)]  # last parameters first
         self._work = []
+        # measurement (bench.py): with ``timing`` on, ``wait`` brackets every bucket's join with CUDA events on the compute
+        # stream; ``exposed_ms()`` then gives, per bucket, how long the compute stream sat blocked on that all-reduce
+        self.timing = False
+        self._events = []
 
     def world(self) -> int:
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
@@ -254,7 +258,29 @@ class GradientAllReducer:
 
     def wait(self) -> float:
         """Joins outstanding all-reduces; returns the gradient scale (1/world) to hand to ``FlatAdamW.step``."""
-        for w in self._work:
-            w.wait()
+        if self.timing and self._work:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(self._work) + 1)]
+            ev[0].record()
+            for i, w in enumerate(self._work):
+                w.wait()
+                ev[i + 1].record()
+            self._events.append(ev)
+        else:
+            for w in self._work:
+                w.wait()
         self._work = []
         return 1.0 / self.world()
+
+    def bytes_per_step(self) -> int:
+        """Payload of one step's all-reduces (fp32 gradients, every bucket once)."""
+        return int(self.grad.numel() * self.grad.element_size())
+
+    def exposed_ms(self):
+        """Mean exposed time per join (in the order the joins were issued) over the steps recorded with ``timing`` on;
+        call after a device synchronize.  Clears the record."""
+        if not self._events:
+            return []
+        n = len(self._events[0]) - 1
+        out = [sum(ev[i].elapsed_time(ev[i + 1]) for ev in self._events) / len(self._events) for i in range(n)]
+        self._events = []
+        return out

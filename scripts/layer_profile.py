@@ -41,7 +41,6 @@ ops.conv2d_tc_norm = wrap("conv_tc+norm", ops.conv2d_tc_norm, d_conv)
 ops.conv2d_direct = wrap("conv_direct", ops.conv2d_direct, d_conv)
 ops.rmsnorm_silu = wrap("rmsnorm", ops.rmsnorm_silu, d_norm)
 ops.groupnorm_silu = wrap("groupnorm", ops.groupnorm_silu, d_gn)
-ops.im2col3x3 = wrap("im2col", ops.im2col3x3, lambda x, kpad, dt, *a: dict(shape=str(tuple(x.shape)), bytes=x.numel() * x.element_size() + x.numel() // x.shape[1] * kpad * 2.0))
 ops.nchw_to_nhwc = wrap("nchw2nhwc", ops.nchw_to_nhwc, lambda x, cp, dt, *a: dict(shape=str(tuple(x.shape)), bytes=x.numel() * x.element_size() * (1 + cp / x.shape[1])))
 ops.reparam = wrap("reparam", ops.reparam, lambda m, *a, **k: dict(shape=str(tuple(m.shape)), bytes=m.numel() * m.element_size() * 2.0))
 ops.composite_psnr = wrap("psnr", ops.composite_psnr, lambda r, t, b: dict(shape=str(tuple(r.shape)), bytes=2.0 * r.numel() * r.element_size()))

@@ -155,15 +155,3 @@ def test_validation_helpers(ops):
         validation_metrics(x.cuda(), y.cuda(), backgrounds=("magenta",))
 
 
-def test_im2col3x3(ops):
-    g = torch.Generator().manual_seed(21)
-    x = torch.rand(2, 4, 9, 13, generator=g)
-    y = ops.im2col3x3(x.cuda(), 64, torch.float32, 2.0, -1.0).cpu()
-    assert y.shape == (2, 9, 13, 64)
-    ref = F.unfold(x * 2 - 1, 3, padding=1).view(2, 4, 9, 9, 13)      # [n][c][tap][h][w]
-    ref = ref.permute(0, 3, 4, 2, 1).reshape(2, 9, 13, 36)              # [n][h][w][tap*4 + c]
-    assert torch.equal(y[..., :36], ref)
-    assert torch.all(y[..., 36:] == 0)
-    yb = ops.im2col3x3(x.cuda().bfloat16(), 64, torch.bfloat16).cpu()
-    assert torch.equal(yb[..., :36].float(), F.unfold(x.bfloat16().float(), 3, padding=1).view(2, 4, 9, 9, 13)
-                       .permute(0, 3, 4, 2, 1).reshape(2, 9, 13, 36))
