@@ -482,7 +482,7 @@ def c4_arm(cx: Ctx, a, steps=None):
     world, rank, dev = cx.world, cx.rank, cx.dev
     steps = steps or a.steps
     torch.manual_seed(0)
-    vae = R.RgbaAutoencoder("qwen").to(dev, torch.bfloat16)
+    vae = R.RgbaAutoencoder(a.arch).to(dev, torch.bfloat16)   # --arch flux: the VAE configs/flux_vae.yaml:73 trains
     step = VaeTrainStep(vae, lr=1e-5, kl_scale=1e-6, loss_module=R.AlphaVaeLoss(reduce_mean=True))
     B, S = a.train_batch, a.train_size
     g = torch.Generator().manual_seed(100 + rank)
@@ -554,7 +554,7 @@ def c4_arm(cx: Ctx, a, steps=None):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"c4: rgba_vae training step, batch {B} x {S}x{S} per GPU, recon (reduce_mean) + 1e-6 KL, "
                                    "no LPIPS, bucketed NCCL gradient all-reduce, clip 1.0, AdamW",
-                       "arch": "qwen", "parallelism": f"data parallel x{world}",
+                       "arch": a.arch, "parallelism": f"data parallel x{world}",
                        "launch": "eager launches" if a.no_graph else "three CUDA graphs per step, all-reduces issued between the replays",
                        "l2": "multi-GB activation tape per step (inputs and working set exceed the 126 MB L2)"},
             "e2e": {"value": mpix * steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / steps,

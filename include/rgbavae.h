@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 19
+#define RV_ABI_VERSION 20
 #define RV_PROF_CATEGORIES 10
 
 int rv_abi_version(void);
@@ -227,6 +227,13 @@ int rv_kl_ref(const void* moments, const void* ref_moments, float* kl_out, void*
  * added to dx: the gradient of the skip branch that meets the normalised one at this point. */
 int rv_rmsnorm_silu_bwd(const void* x, const float* gamma_scaled, const void* dy, const void* add, void* dx,
                         float* dgamma, float dgamma_scale, int64_t pixels, int c, int dtype, int apply_silu, void* stream);
+/* Backward of rv_groupnorm_stats + rv_groupnorm_silu (GroupNorm(32) + SiLU of the Flux AutoencoderKL blocks; the VAE that
+ * configs/flux_vae.yaml:73 trains).  x / dy / dx / add NHWC [n][hw][c]; stats = the forward's [n][groups][2] raw sums;
+ * dgamma / dbeta [c] fp32 are ACCUMULATED (they may point into a gradient buffer); add (optional) is added to dx (the skip
+ * branch's gradient); scratch: n * c * 2 doubles. */
+int rv_groupnorm_silu_bwd(const void* x, const double* stats, const float* gamma, const float* beta, const void* dy,
+                          const void* add, void* dx, float* dgamma, float* dbeta, double* scratch, int n, int64_t hw, int c,
+                          int groups, float eps, int dtype, int apply_silu, void* stream);
 /* Weight (and bias) gradient of a stride-1 3x3 or 1x1 convolution on the tensor cores: x NHWC bf16 [n][h][w][cin],
  * dy NHWC bf16 [n][h][w][cout].  Element (co, ci, tap) is ACCUMULATED (fp32 atomics) at
  * dw[co*dw_co_stride + ci*dw_ci_stride + tap*dw_tap_stride], so the gradient can land directly in the parameter's own

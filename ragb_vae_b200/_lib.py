@@ -9,7 +9,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "librgbavae.so")
 
 RV_F32, RV_BF16 = 0, 1
-ABI_VERSION = 19
+ABI_VERSION = 20
 PROF_CATEGORIES = 10
 PROF_NAMES = ("conv_tc", "conv_direct", "norm_silu", "softmax", "layout", "reparam", "recon_loss", "composite_psnr",
               "attention", "conv_tc_upsample")
@@ -86,6 +86,7 @@ SIGNATURES = {
     "rv_grad_sqnorm_scratch_bytes": (_I, []),
     "rv_adamw_step": (_I, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _F, _P, _F, _P]),
     "rv_adamw_advance": (_I, [_P, _F, _F, _P]),
+    "rv_groupnorm_silu_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _I, _I, _P]),
     "rv_kl_ref": (_I, [_P, _P, _P, _P, _I, _I, _L, _I, _F, _P]),
 }
 

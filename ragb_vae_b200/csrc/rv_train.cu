@@ -386,6 +386,204 @@ static inline dim3 train_grid(int64_t items, int n) {
   return dim3(bx, (unsigned)n);
 }
 
+// ------------------------------------------------------------------------------------------
+// Backward of GroupNorm(32) + SiLU (rv_groupnorm_stats / rv_groupnorm_silu; diffusers ResnetBlock2D.norm1/norm2,
+// Attention.group_norm, conv_norm_out of the Flux AutoencoderKL).  With xh = (x - mean) * rstd, u = xh * gamma + beta,
+// y = silu(u):   du = dy * silu'(u),  dgamma_c = sum du * xh,  dbeta_c = sum du,
+//                dx = rstd * (du * gamma - S1 / m - xh * S2 / m),  S1 = sum_group du * gamma, S2 = sum_group du * gamma * xh.
+// Pass 1 leaves per (sample, channel) the two sums (A = sum du, B = sum du * xh; fp32 per thread, fp64 across threads) --
+// they give dbeta / dgamma AND, weighted by gamma over a group's channels, S1 / S2.  Pass 2 streams dx (+ the skip branch).
+// Same block geometry as the forward kernels (the partition depends on H*W only).
+// ------------------------------------------------------------------------------------------
+template <typename T, bool SILU>
+__global__ void __launch_bounds__(512) groupnorm_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                                  const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, double* __restrict__ chan,
+                                                                  int64_t hw, int c, int groups, int cpp, float eps,
+                                                                  int64_t rows_per_block) {
+  using V = Vec16<T>;
+  extern __shared__ double sacc[];  // [c][2]
+  const int tid = threadIdx.x;
+  const int n = blockIdx.y;
+  for (int i = tid; i < c * 2; i += blockDim.x) sacc[i] = 0.0;
+  __syncthreads();
+  const int col = tid % cpp;
+  const int rows_per_iter = blockDim.x / cpp;
+  const int cg = c / groups;
+  const double cnt = (double)hw * (double)cg;
+  float mean[V::N], rstd[V::N], ga[V::N], be[V::N], a[V::N], b[V::N];
+#pragma unroll
+  for (int j = 0; j < V::N; ++j) {
+    const int ch = col * V::N + j, g = ch / cg;
+    const double m = stats[((int64_t)n * groups + g) * 2] / cnt;
+    double var = stats[((int64_t)n * groups + g) * 2 + 1] / cnt - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[j] = (float)m;
+    rstd[j] = (float)(1.0 / sqrt(var + (double)eps));
+    ga[j] = gamma[ch];
+    be[j] = beta[ch];
+    a[j] = b[j] = 0.f;
+  }
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(hw, r0 + rows_per_block);
+  const T* xb = x + (int64_t)n * hw * c;
+  const T* gb = dy + (int64_t)n * hw * c;
+#pragma unroll 2
+  for (int64_t r = r0 + tid / cpp; r < r1; r += rows_per_iter) {
+    V vx, vg;
+    vx.load(xb + r * c + col * V::N);
+    vg.load(gb + r * c + col * V::N);
+#pragma unroll
+    for (int j = 0; j < V::N; ++j) {
+      const float xh = (vx.get(j) - mean[j]) * rstd[j];
+      float du = vg.get(j);
+      if (SILU) {
+        const float u = fmaf(xh, ga[j], be[j]);
+        const float sg = 1.0f / (1.0f + __expf(-u));
+        du *= sg * (1.0f + u * (1.0f - sg));
+      }
+      a[j] += du;
+      b[j] = fmaf(du, xh, b[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < V::N; ++j) {
+    const int ch = col * V::N + j;
+    atomicAdd(&sacc[2 * ch], (double)a[j]);
+    atomicAdd(&sacc[2 * ch + 1], (double)b[j]);
+  }
+  __syncthreads();
+  for (int i = tid; i < c * 2; i += blockDim.x) atomicAdd(&chan[(int64_t)n * c * 2 + i], sacc[i]);
+}
+
+template <typename T, bool SILU>
+__global__ void __launch_bounds__(512) groupnorm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                                 const T* __restrict__ add, const double* __restrict__ stats,
+                                                                 const double* __restrict__ chan, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, T* __restrict__ dx,
+                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t hw,
+                                                                 int c, int groups, int cpp, float eps, int64_t rows_per_block) {
+  using V = Vec16<T>;
+  extern __shared__ float sgrp[];  // [groups][2]: S1 / m, S2 / m
+  const int tid = threadIdx.x;
+  const int n = blockIdx.y;
+  const int cg = c / groups;
+  const double cnt = (double)hw * (double)cg;
+  const double* ch_n = chan + (int64_t)n * c * 2;
+  for (int g = tid; g < groups; g += blockDim.x) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k < cg; ++k) {
+      const int ch = g * cg + k;
+      s1 += (double)gamma[ch] * ch_n[2 * ch];
+      s2 += (double)gamma[ch] * ch_n[2 * ch + 1];
+    }
+    sgrp[2 * g] = (float)(s1 / cnt);
+    sgrp[2 * g + 1] = (float)(s2 / cnt);
+  }
+  if (blockIdx.x == 0) {  // parameter gradients: one block per sample adds the sample's channel sums
+    for (int ch = tid; ch < c; ch += blockDim.x) {
+      atomicAdd(&dbeta[ch], (float)ch_n[2 * ch]);
+      atomicAdd(&dgamma[ch], (float)ch_n[2 * ch + 1]);
+    }
+  }
+  __syncthreads();
+  const int col = tid % cpp;
+  const int rows_per_iter = blockDim.x / cpp;
+  float mean[V::N], rstd[V::N], ga[V::N], be[V::N], m1[V::N], m2[V::N];
+#pragma unroll
+  for (int j = 0; j < V::N; ++j) {
+    const int ch = col * V::N + j, g = ch / cg;
+    const double m = stats[((int64_t)n * groups + g) * 2] / cnt;
+    double var = stats[((int64_t)n * groups + g) * 2 + 1] / cnt - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[j] = (float)m;
+    rstd[j] = (float)(1.0 / sqrt(var + (double)eps));
+    ga[j] = gamma[ch];
+    be[j] = beta[ch];
+    m1[j] = sgrp[2 * g];
+    m2[j] = sgrp[2 * g + 1];
+  }
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(hw, r0 + rows_per_block);
+  const int64_t base = (int64_t)n * hw * c;
+#pragma unroll 2
+  for (int64_t r = r0 + tid / cpp; r < r1; r += rows_per_iter) {
+    V vx, vg, va, o;
+    const int64_t off = base + r * c + col * V::N;
+    vx.load(x + off);
+    vg.load(dy + off);
+    if (add) va.load(add + off);
+#pragma unroll
+    for (int j = 0; j < V::N; ++j) {
+      const float xh = (vx.get(j) - mean[j]) * rstd[j];
+      float du = vg.get(j);
+      if (SILU) {
+        const float u = fmaf(xh, ga[j], be[j]);
+        const float sg = 1.0f / (1.0f + __expf(-u));
+        du *= sg * (1.0f + u * (1.0f - sg));
+      }
+      float d = rstd[j] * (du * ga[j] - m1[j] - xh * m2[j]);
+      if (add) d += va.get(j);
+      o.set(j, d);
+    }
+    o.store(dx + off);
+  }
+}
+
+struct GnBwdGeom {
+  int cpp, block;
+  int64_t rows_per_block;
+  unsigned blocks_x;
+};
+template <typename T>
+static int gn_bwd_geometry(int64_t hw, int c, int groups, GnBwdGeom* g) {  // = gn_geometry of rv_elementwise.cu
+  constexpr int VN = Vec16<T>::N;
+  RV_CHECK_ARG(groups > 0 && c % groups == 0 && c % VN == 0, "groupnorm_bwd: bad channel/group count %d/%d", c, groups);
+  g->cpp = c / VN;
+  RV_CHECK_ARG(g->cpp <= 512, "groupnorm_bwd: too many channels (%d)", c);
+  int rows = 256 / g->cpp;
+  if (rows < 1) rows = 1;
+  g->block = rows * g->cpp;
+  g->rows_per_block = (int64_t)rows * 64;
+  g->blocks_x = (unsigned)((hw + g->rows_per_block - 1) / g->rows_per_block);
+  return 0;
+}
+
+template <typename T>
+static int groupnorm_bwd_launch(const void* x, const void* dy, const void* add, const double* stats, const float* gamma,
+                                const float* beta, void* dx, float* dgamma, float* dbeta, double* chan, int n, int64_t hw, int c,
+                                int groups, float eps, int apply_silu, cudaStream_t st) {
+  GnBwdGeom g;
+  if (int rc = gn_bwd_geometry<T>(hw, c, groups, &g)) return rc;
+  RV_CUDA(cudaMemsetAsync(chan, 0, sizeof(double) * 2 * (size_t)n * c, st));
+  const double bytes = (double)n * hw * c * sizeof(T);
+  {
+    LaunchScope scope(CAT_NORM, st, 2.0 * bytes);
+    const size_t smem = sizeof(double) * 2 * c;
+    if (apply_silu)
+      groupnorm_bwd_reduce_kernel<T, true><<<dim3(g.blocks_x, n), g.block, smem, st>>>((const T*)x, (const T*)dy, stats, gamma, beta, chan, hw,
+                                                                                     c, groups, g.cpp, eps, g.rows_per_block);
+    else
+      groupnorm_bwd_reduce_kernel<T, false><<<dim3(g.blocks_x, n), g.block, smem, st>>>((const T*)x, (const T*)dy, stats, gamma, beta, chan, hw,
+                                                                                      c, groups, g.cpp, eps, g.rows_per_block);
+    RV_LAUNCH_CHECK();
+  }
+  {
+    LaunchScope scope(CAT_NORM, st, (add ? 4.0 : 3.0) * bytes);
+    const size_t smem = sizeof(float) * 2 * groups;
+    if (apply_silu)
+      groupnorm_bwd_apply_kernel<T, true><<<dim3(g.blocks_x, n), g.block, smem, st>>>((const T*)x, (const T*)dy, (const T*)add, stats, chan, gamma,
+                                                                                    beta, (T*)dx, dgamma, dbeta, hw, c, groups, g.cpp, eps,
+                                                                                    g.rows_per_block);
+    else
+      groupnorm_bwd_apply_kernel<T, false><<<dim3(g.blocks_x, n), g.block, smem, st>>>((const T*)x, (const T*)dy, (const T*)add, stats, chan,
+                                                                                     gamma, beta, (T*)dx, dgamma, dbeta, hw, c, groups, g.cpp,
+                                                                                     eps, g.rows_per_block);
+    RV_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 }  // namespace rv
 
 extern "C" {
@@ -576,6 +774,20 @@ int rv_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, in
                                                      grad_scale, sqnorm, max_norm, state);
   RV_LAUNCH_CHECK();
   return 0;
+}
+
+int rv_groupnorm_silu_bwd(const void* x, const double* stats, const float* gamma, const float* beta, const void* dy, const void* add,
+                          void* dx, float* dgamma, float* dbeta, double* scratch, int n, int64_t hw, int c, int groups, float eps,
+                          int dtype, int apply_silu, void* stream) {
+  RV_CHECK_ARG(x && stats && gamma && beta && dy && dx && dgamma && dbeta && scratch && n > 0 && hw > 0, "groupnorm_silu_bwd: bad argument");
+  RV_CHECK_ARG(dtype == RV_F32 || dtype == RV_BF16, "groupnorm_silu_bwd: bad dtype %d", dtype);
+  RV_CHECK_ARG(((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)dx % 16 == 0) && ((uintptr_t)add % 16 == 0),
+               "groupnorm_silu_bwd: unaligned tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == RV_F32)
+    return rv::groupnorm_bwd_launch<float>(x, dy, add, stats, gamma, beta, dx, dgamma, dbeta, scratch, n, hw, c, groups, eps, apply_silu, st);
+  return rv::groupnorm_bwd_launch<__nv_bfloat16>(x, dy, add, stats, gamma, beta, dx, dgamma, dbeta, scratch, n, hw, c, groups, eps,
+                                                 apply_silu, st);
 }
 
 }  // extern "C"

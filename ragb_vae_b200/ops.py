@@ -144,8 +144,9 @@ def rmsnorm_silu(x: torch.Tensor, gamma: torch.Tensor, silu: bool = True, out: O
 
 
 def groupnorm_silu(x: torch.Tensor, gamma, beta, groups: int = 32, eps: float = 1e-6, silu: bool = True,
-                   out: Optional[torch.Tensor] = None):
-    """x: [N, H, W, C] (or [N, HW, C]) NHWC-dense."""
+                   out: Optional[torch.Tensor] = None, return_stats: bool = False):
+    """x: [N, H, W, C] (or [N, HW, C]) NHWC-dense.  ``return_stats``: also the [N, groups, 2] fp64 (sum, sum of squares)
+    the backward pass needs."""
     _need_cuda(x, gamma, beta)
     n, c = x.shape[0], x.shape[-1]
     hw = x.numel() // (n * c)
@@ -155,7 +156,7 @@ def groupnorm_silu(x: torch.Tensor, gamma, beta, groups: int = 32, eps: float = 
     y = torch.empty_like(x) if out is None else out
     check(lib.rv_groupnorm_silu(_ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(y), n, hw, c, groups, eps, _dt(x),
                                 int(silu), _stream(x)), "rv_groupnorm_silu")
-    return y
+    return (y, stats) if return_stats else y
 
 
 FUSED_ATTENTION_D = 384            # Qwen-Image mid block

@@ -43,9 +43,7 @@ class VaeTrainStep:
                  weight_decay: float = 0.01, max_grad_norm: Optional[float] = 1.0, kl_scale: Optional[float] = 1e-6,
                  loss_module: Optional[AlphaVaeLoss] = None, num_buckets: int = 4, encode_triplet: bool = True, group=None,
                  ref_vae: Optional[RgbaAutoencoder] = None, ref_kl_scale: Optional[float] = None):
-        if vae.arch != "qwen":
-            raise NotImplementedError("VaeTrainStep covers arch='qwen' (RMS-norm blocks); the GroupNorm / Linear backward of "
-                                      "arch='flux' (the VAE configs/flux_vae.yaml:73 trains) is not built")
+        self.flux = vae.arch == "flux"   # GroupNorm blocks, Linear q/k/v/out attention, no quant convs, no decode clamp
         if vae.dtype != torch.bfloat16:
             raise TypeError("the training step runs the model in bfloat16 (fp32 master weights live in the optimizer)")
         self.vae = vae
@@ -77,8 +75,23 @@ class VaeTrainStep:
     def _norm(self, x, norm, silu=True):
         return self.vae._norm(x, norm, silu)
 
-    def _norm_bwd(self, norm, x, dy, silu=True, add=None):
+    def _norm_fwd(self, x, norm, silu=True):
+        """-> (act(norm(x)), what the backward needs besides x: the GroupNorm statistics, or None for the RMS norm)."""
+        if self.flux:
+            v = self.vae
+            return ops.groupnorm_silu(x, v._f32(norm.weight, "gn_w"), v._f32(norm.bias, "gn_b"), norm.num_groups, norm.eps, silu,
+                                      return_stats=True)
+        return self.vae._norm(x, norm, silu), None
+
+    def _norm_bwd(self, norm, x, dy, silu=True, add=None, aux=None):
         """``add``: gradient of the skip branch meeting this one at x (fused into the norm backward's store)."""
+        if self.flux:
+            if aux is None:  # checkpointed block: the statistics are recomputed with the forward
+                aux = self._norm_fwd(x, norm, silu)[1]
+            dx, _, _ = T.groupnorm_silu_backward(x, aux, norm.weight, norm.bias, dy, norm.num_groups, norm.eps, silu,
+                                                 dgamma_out=self._gview[id(norm.weight)].view(-1),
+                                                 dbeta_out=self._gview[id(norm.bias)].view(-1), add=add)
+            return dx
         dx, _ = T.rmsnorm_silu_backward(x, norm.gamma, dy, silu, dgamma_out=self._gview[id(norm.gamma)].view(-1), add=add)
         return dx
 
@@ -107,38 +120,52 @@ class VaeTrainStep:
     # ---- residual block --------------------------------------------------------------------
     def _res_fwd(self, x, blk, tape: Optional[list]):
         short = getattr(blk, "conv_shortcut", None)
-        a = self._norm(x, blk.norm1)
+        a, s1 = self._norm_fwd(x, blk.norm1)
         h = x if short is None else self._conv(x, short)
         # conv1 writes its raw output (the norm backward needs it) AND act(norm2(.)) from the same epilogue where one tile holds
-        # the pixel's whole channel vector (Cout <= 256); else the norm kernel runs
+        # the pixel's whole channel vector (RMS norm, Cout <= 256); else the norm kernel runs
         st = self.vae._conv_fused(a, blk.conv1, next_norm=(blk.norm2, True), want_raw=True)
-        t = st.raw
-        b = st.act if st.act is not None else self._norm(t, blk.norm2)
+        t, s2 = st.raw, None
+        if st.act is not None:
+            b = st.act
+        else:
+            b, s2 = self._norm_fwd(t, blk.norm2)
         y = self._conv(b, blk.conv2, residual=h)
         if tape is not None:
             # gradient checkpointing (diffusers: per block): keep only the block input, recompute the rest in the backward
-            tape.append(("res", blk, (x, None, None, None) if self.vae.gradient_checkpointing else (x, a, t, b)))
+            tape.append(("res", blk, (x, None, None, None, None, None) if self.vae.gradient_checkpointing else (x, a, t, b, s1, s2)))
         return y
 
     def _res_bwd(self, blk, saved, dy):
-        x, a, t, b = saved
+        x, a, t, b, s1, s2 = saved
         short = getattr(blk, "conv_shortcut", None)
         if a is None:  # checkpointed block: same kernels, same bits as the forward
-            a = self._norm(x, blk.norm1)
+            a, s1 = self._norm_fwd(x, blk.norm1)
             st = self.vae._conv_fused(a, blk.conv1, next_norm=(blk.norm2, True), want_raw=True)
             t = st.raw
-            b = st.act if st.act is not None else self._norm(t, blk.norm2)
+            if st.act is not None:
+                b = st.act
+            else:
+                b, s2 = self._norm_fwd(t, blk.norm2)
         db = self._conv_bwd(blk.conv2, b, dy)
-        dt = self._norm_bwd(blk.norm2, t, db)
+        dt = self._norm_bwd(blk.norm2, t, db, aux=s2)
         da = self._conv_bwd(blk.conv1, a, dt)
         skip = dy if short is None else self._conv_bwd(short, x, dy)
-        return self._norm_bwd(blk.norm1, x, da, add=skip)
+        return self._norm_bwd(blk.norm1, x, da, add=skip, aux=s1)
 
     # ---- attention -------------------------------------------------------------------------
     def _gemm(self, *a, **k):
         return self.vae._gemm(*a, **k)
 
     def _attn_weights(self, attn):
+        """(Wqkv bf16 [3C, C], bqkv fp32 [3C], Wo bf16 [C, C], bo fp32 [C]) -- Qwen: one 1x1 conv C -> 3C and a 1x1 proj;
+        Flux: three Linear(C, C) stacked, and to_out[0]."""
+        if self.flux:
+            lins = (attn.to_q, attn.to_k, attn.to_v)
+            wqkv = torch.cat([l.weight.detach() for l in lins], 0).to(torch.bfloat16).contiguous()
+            bqkv = torch.cat([l.bias.detach() for l in lins], 0).to(torch.float32).contiguous()
+            out = attn.to_out[0]
+            return wqkv, bqkv, out.weight.detach().to(torch.bfloat16).contiguous(), out.bias.detach().to(torch.float32).contiguous()
         c = attn.proj.in_channels
         wqkv = attn.to_qkv.weight.detach().reshape(3 * c, c).to(torch.bfloat16).contiguous()
         bqkv = attn.to_qkv.bias.detach().to(torch.float32).contiguous()
@@ -146,11 +173,14 @@ class VaeTrainStep:
         bo = attn.proj.bias.detach().to(torch.float32).contiguous()
         return wqkv, bqkv, wo, bo
 
+    def _attn_norm(self, attn):
+        return attn.group_norm if self.flux else attn.norm
+
     def _attn_fwd(self, x, attn, tape: Optional[list]):
         n, h, w, c = x.shape
         t = h * w
         dev = x.device
-        xn = self._norm(x, attn.norm, silu=False)
+        xn, sn = self._norm_fwd(x, self._attn_norm(attn), silu=False)
         wqkv, bqkv, wo, bo = self._attn_weights(attn)
         xn2 = xn.view(n * t, c)
         q = torch.empty((n * t, c), dtype=torch.bfloat16, device=dev)
@@ -187,7 +217,7 @@ class VaeTrainStep:
         self._gemm(o, wo, rows=n * t, k=c, cols=c, x_ld=c, w_ld=c, y=out.view(n * t, c), y_ld=c, bias=bo, bias_mode=1,
                    residual=x.view(n * t, c))
         if tape is not None:
-            tape.append(("attn", attn, (x,) if self.vae.gradient_checkpointing else (x, xn, q, k, v, o)))
+            tape.append(("attn", attn, (x,) if self.vae.gradient_checkpointing else (x, xn, q, k, v, o, sn)))
         return out
 
     @staticmethod
@@ -203,7 +233,7 @@ class VaeTrainStep:
             finally:
                 self.vae.gradient_checkpointing = ckpt
             saved = scratch[0][2]
-        x, xn, q, k, v, o = saved
+        x, xn, q, k, v, o, sn = saved
         n, h, w, c = x.shape
         t = h * w
         dev = x.device
@@ -211,9 +241,10 @@ class VaeTrainStep:
         as_img = lambda a, ch: a.view(1, 1, a.shape[0], ch)  # [rows][ch] as a one-row NHWC image
         dout2 = dout.view(n * t, c)
         # proj: out = o Wo^T + bo + x
-        T.conv_wgrad(as_img(o, c), as_img(dout2, c), 1, dw_out=self._gview[id(attn.proj.weight)],
-                     dbias_out=self._gview[id(attn.proj.bias)])
-        d_o = T.conv_dgrad(as_img(dout2, c), attn.proj.weight.detach().reshape(c, c, 1, 1)).view(n * t, c)
+        proj = attn.to_out[0] if self.flux else attn.proj
+        T.conv_wgrad(as_img(o, c), as_img(dout2, c), 1, dw_out=self._gview[id(proj.weight)].view(c, c, 1, 1),
+                     dbias_out=self._gview[id(proj.bias)])
+        d_o = T.conv_dgrad(as_img(dout2, c), proj.weight.detach().reshape(c, c, 1, 1)).view(n * t, c)
         dqkv = torch.empty((n * t, 3 * c), dtype=torch.bfloat16, device=dev)
         q_chunk = self._q_chunk(t)
         s = torch.empty((q_chunk, t), dtype=torch.float32, device=dev)
@@ -246,10 +277,19 @@ class VaeTrainStep:
                 self._gemm(ds[:rows], kt, rows=rows, k=t, cols=c, x_ld=t, w_ld=t, y=dqkv[rs, :c], y_ld=3 * c)
             dqkv[sl, c:2 * c] = dk
             dqkv[sl, 2 * c:] = dv
-        T.conv_wgrad(as_img(xn.view(n * t, c), c), as_img(dqkv, 3 * c), 1, dw_out=self._gview[id(attn.to_qkv.weight)],
-                     dbias_out=self._gview[id(attn.to_qkv.bias)])
-        dxn = T.conv_dgrad(as_img(dqkv, 3 * c), attn.to_qkv.weight.detach().reshape(3 * c, c, 1, 1)).view(x.shape)
-        return self._norm_bwd(attn.norm, x, dxn, silu=False, add=dout)
+        if self.flux:  # three Linear(C, C): one stacked [3C, C] weight gradient, then a slice into each parameter's view
+            dw = torch.zeros((3 * c, c, 1, 1), dtype=torch.float32, device=dev)
+            db = torch.zeros(3 * c, dtype=torch.float32, device=dev)
+            T.conv_wgrad(as_img(xn.view(n * t, c), c), as_img(dqkv, 3 * c), 1, dw_out=dw, dbias_out=db)
+            for i, lin in enumerate((attn.to_q, attn.to_k, attn.to_v)):
+                self._gview[id(lin.weight)].add_(dw[i * c:(i + 1) * c].view(c, c))
+                self._gview[id(lin.bias)].add_(db[i * c:(i + 1) * c])
+            dxn = T.conv_dgrad(as_img(dqkv, 3 * c), wqkv.view(3 * c, c, 1, 1)).view(x.shape)
+        else:
+            T.conv_wgrad(as_img(xn.view(n * t, c), c), as_img(dqkv, 3 * c), 1, dw_out=self._gview[id(attn.to_qkv.weight)],
+                         dbias_out=self._gview[id(attn.to_qkv.bias)])
+            dxn = T.conv_dgrad(as_img(dqkv, 3 * c), attn.to_qkv.weight.detach().reshape(3 * c, c, 1, 1)).view(x.shape)
+        return self._norm_bwd(self._attn_norm(attn), x, dxn, silu=False, add=dout, aux=sn)
 
     # ---- encoder / decoder -----------------------------------------------------------------
     def _run_fwd(self, x, items, tape):
@@ -274,9 +314,9 @@ class VaeTrainStep:
                     tape.append(("conv", m, x))
                 x = y
             elif kind == "norm":
-                y = self._norm(x, m)
+                y, aux = self._norm_fwd(x, m)
                 if tape is not None:
-                    tape.append(("norm", m, x))
+                    tape.append(("norm", m, (x, aux)))
                 x = y
             else:
                 raise AssertionError(kind)
@@ -294,7 +334,7 @@ class VaeTrainStep:
             elif kind == "conv":
                 dy = self._conv_bwd(m, saved, dy)
             elif kind == "norm":
-                dy = self._norm_bwd(m, saved, dy)
+                dy = self._norm_bwd(m, saved[0], dy, aux=saved[1])
             elif kind == "stem":  # first conv of a network: input has no gradient (or it is returned as is)
                 conv, need_dx = m
                 dy = self._conv_bwd(conv, saved, dy, need_dx=need_dx)
@@ -305,6 +345,13 @@ class VaeTrainStep:
     def _encoder_items(self):
         enc = self.vae.encoder
         items = []
+        if self.flux:
+            for blk in enc.down_blocks:
+                items += [("res", r) for r in blk.resnets]
+                if getattr(blk, "downsamplers", None) is not None:
+                    items.append(("down", blk.downsamplers[0].conv))
+            mid = enc.mid_block
+            return items + [("res", mid.resnets[0]), ("attn", mid.attentions[0]), ("res", mid.resnets[1]), ("norm", enc.conv_norm_out)]
         for blk in enc.down_blocks:
             items.append(("res", blk) if blk._kind == "res" else ("down", blk.resample[1]))
         mid = enc.mid_block
@@ -315,12 +362,14 @@ class VaeTrainStep:
     def _decoder_items(self):
         dec = self.vae.decoder
         mid = dec.mid_block
-        items = [("conv", dec.conv_in), ("res", mid.resnets[0]), ("attn", mid.attentions[0]), ("res", mid.resnets[1])]
+        items = [] if self.flux else [("conv", dec.conv_in)]
+        items += [("res", mid.resnets[0]), ("attn", mid.attentions[0]), ("res", mid.resnets[1])]
         for blk in dec.up_blocks:
             items += [("res", r) for r in blk.resnets]
             if getattr(blk, "upsamplers", None) is not None:
-                items.append(("up", blk.upsamplers[0].resample[1]))
-        items.append(("norm", dec.norm_out))
+                up = blk.upsamplers[0]
+                items.append(("up", up.conv if self.flux else up.resample[1]))
+        items.append(("norm", dec.conv_norm_out if self.flux else dec.norm_out))
         return items
 
     def encode_moments(self, x_vae: torch.Tensor, tape: Optional[list]) -> torch.Tensor:
@@ -332,21 +381,26 @@ class VaeTrainStep:
         if tape is not None:
             tape.append(("stem", (vae.encoder.conv_in, False), xp))
         h = self._run_fwd(y, self._encoder_items(), tape)
+        last = vae.encoder.conv_out if self.flux else vae.quant_conv   # Flux: conv_out yields the moments (no quant conv)
         if tape is not None:
-            tape.append(("conv", vae.quant_conv, h))
-        return self._conv(h, vae.quant_conv, y_nchw=True, y_dtype=torch.float32)
+            tape.append(("conv", last, h))
+        return self._conv(h, last, y_nchw=True, y_dtype=torch.float32)
 
     def decode(self, z: torch.Tensor, tape: Optional[list]) -> torch.Tensor:
-        """fp32 latents (B,16,h,w) -> fp32 image (B,4,8h,8w) clamped to [-1,1] (AutoencoderKLQwenImage._decode)."""
+        """fp32 latents (B,16,h,w) -> fp32 image (B,4,8h,8w); Qwen: clamped to [-1,1] (AutoencoderKLQwenImage._decode)."""
         vae = self.vae
         zp = ops.nchw_to_nhwc(z.contiguous(), 16, torch.bfloat16)
-        y = self._conv(zp, vae.post_quant_conv)
+        first = vae.decoder.conv_in if self.flux else vae.post_quant_conv
+        y = self._conv(zp, first)
         if tape is not None:
-            tape.append(("stem", (vae.post_quant_conv, True), zp))
+            tape.append(("stem", (first, True), zp))
         h = self._run_fwd(y, self._decoder_items(), tape)
         if tape is not None:
             tape.append(("conv", vae.decoder.conv_out, h))
-        return self._conv(h, vae.decoder.conv_out, y_nchw=True, y_dtype=torch.float32, clamp=(-1.0, 1.0))
+        return self._conv(h, vae.decoder.conv_out, y_nchw=True, y_dtype=torch.float32, clamp=self._decode_clamp())
+
+    def _decode_clamp(self):
+        return None if self.flux else (-1.0, 1.0)
 
     # ---- the step --------------------------------------------------------------------------
     def _forward_and_decoder_backward(self, inputs: torch.Tensor, noise: torch.Tensor):
@@ -396,7 +450,7 @@ class VaeTrainStep:
         metrics["train/loss"] = total
         # ---- backward ----
         self.opt.zero_grad()
-        dpred = T.recon_loss_backward(pred, target_vae, lm._eb, lm._eb2, lm.reduce_mean, lm.use_naive_mse, clamp=(-1.0, 1.0))
+        dpred = T.recon_loss_backward(pred, target_vae, lm._eb, lm._eb2, lm.reduce_mean, lm.use_naive_mse, clamp=self._decode_clamp())
         dy = ops.nchw_to_nhwc(dpred, 16, torch.bfloat16)
         dzp = self._run_bwd(dec_tape, dy)  # NHWC [B,h,w,16]
         return metrics, (enc_tape, moments, noise, dzp, kl_w, dm_ref)
@@ -419,7 +473,7 @@ class VaeTrainStep:
         self._check_untiled(inputs)
         if noise is None:
             b, _, h, w = inputs.shape
-            noise = torch.randn((b, self.vae.config.z_dim, h // 8, w // 8), generator=generator, device=inputs.device,
+            noise = torch.randn((b, int(self.vae.config.latent_channels), h // 8, w // 8), generator=generator, device=inputs.device,
                                 dtype=torch.float32)
         metrics, ctx = self._forward_and_decoder_backward(inputs, noise)
         self._mark_ready(decoder_done=True)

@@ -79,6 +79,29 @@ def rmsnorm_silu_backward(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor
     return dx, dg.reshape(gamma.shape)
 
 
+def groupnorm_silu_backward(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, dy: torch.Tensor,
+                            groups: int = 32, eps: float = 1e-6, silu: bool = True, dgamma_out: Optional[torch.Tensor] = None,
+                            dbeta_out: Optional[torch.Tensor] = None, add: Optional[torch.Tensor] = None):
+    """Backward of ops.groupnorm_silu (``stats`` = its ``return_stats`` output): returns (dx, dgamma, dbeta).  ``dgamma_out`` /
+    ``dbeta_out``: contiguous fp32 [C] buffers the parameter gradients are ACCUMULATED into (views of the flat gradient);
+    ``add``: the skip branch's gradient, added to dx in the same pass."""
+    _need_cuda(x, stats, gamma, beta, dy)
+    n, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (n * c)
+    x, dy = x.contiguous(), dy.to(x.dtype).contiguous()
+    g32 = gamma.detach().to(torch.float32).reshape(-1).contiguous()
+    b32 = beta.detach().to(torch.float32).reshape(-1).contiguous()
+    dx = torch.empty_like(x)
+    dg = torch.zeros(c, dtype=torch.float32, device=x.device) if dgamma_out is None else dgamma_out
+    db = torch.zeros(c, dtype=torch.float32, device=x.device) if dbeta_out is None else dbeta_out
+    if add is not None:
+        add = add.to(x.dtype).contiguous()
+    scratch = torch.empty(n * c * 2, dtype=torch.float64, device=x.device)
+    check(_lib.load().rv_groupnorm_silu_bwd(_ptr(x), _ptr(stats), _ptr(g32), _ptr(b32), _ptr(dy), _ptr(add), _ptr(dx), _ptr(dg), _ptr(db),
+                                            _ptr(scratch), n, hw, c, groups, eps, _dt(x), int(silu), _stream(x)), "rv_groupnorm_silu_bwd")
+    return dx, dg, db
+
+
 def conv_dgrad_weights(weight2d: torch.Tensor, cout_pad: int = 0) -> torch.Tensor:
     """[cout][cin][k][k] (any outer strides, e.g. the last temporal slice of a causal 3-D kernel) -> packed bf16 weights
     of the convolution that maps dY to dX for a stride-1 conv: W'[cin][k-1-dy][k-1-dx][cout (zero padded)]."""

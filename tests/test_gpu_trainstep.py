@@ -122,11 +122,17 @@ def _block_case(pair, gpu_blk, oracle_blk, fwd, bwd, cin, n=2, h=8, w=8, tol=3e-
     grads = step.named_grads()
     prefix = next(nm for nm, mod in step.vae.named_modules() if mod is gpu_blk) + "."
     checked = 0
+    gmax = max(float(p.grad.abs().max()) for p in oracle_blk.parameters() if p.grad is not None)
     for name, p in oracle_blk.named_parameters():
         if p.grad is None:
             continue
         got = grads[prefix + name]
         want = p.grad
+        if float(want.abs().max()) < 1e-4 * gmax:
+            # a mathematically zero gradient (the key bias of an attention block: softmax ignores a row-constant shift of the
+            # scores): autograd leaves rounding noise, so does bf16 -- hold it to "small", not to a relative error
+            assert float(got.abs().max()) < 2e-2 * gmax, name
+            continue
         if want.dim() == 5:  # causal 3-D kernel: only the last temporal tap sees the frame
             if got.shape[2] > 1:
                 assert float(got[:, :, :-1].abs().max()) == 0.0
@@ -387,3 +393,120 @@ def test_gradient_checkpointing_recomputes_the_same_gradients(lib_built):
     with pytest.raises(NotImplementedError):
         step.forward_backward(big)
     vae.disable_tiling()
+
+
+# ---- arch = "flux" (GroupNorm blocks, Linear attention): the VAE configs/flux_vae.yaml:73 trains ------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("silu,with_add", [(True, False), (False, True), (True, True)])
+def test_groupnorm_silu_backward_matches_autograd(lib_built, dtype, silu, with_add):
+    from ragb_vae_b200 import ops
+    from ragb_vae_b200 import training as T
+
+    g = torch.Generator().manual_seed(9)
+    n, h, w, c = 3, 12, 20, 128
+    x = torch.randn(n, c, h, w, generator=g) * 1.5 + 0.3
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.2
+    dy = torch.randn(n, c, h, w, generator=g)
+    add = torch.randn(n, c, h, w, generator=g) if with_add else None
+    rnd = (lambda t: t) if dtype == torch.float32 else bf16r
+    xr = rnd(x).requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = F.group_norm(xr, 32, gr, br, eps=1e-6)
+    y = F.silu(y) if silu else y
+    (y * rnd(dy)).sum().backward()
+    want_dx = xr.grad + (rnd(add) if with_add else 0)
+    to = lambda t: t.permute(0, 2, 3, 1).contiguous().cuda().to(dtype)
+    yg, stats = ops.groupnorm_silu(to(x), gamma.cuda(), beta.cuda(), 32, 1e-6, silu, return_stats=True)
+    assert rel(nchw(yg), y) < (1e-5 if dtype == torch.float32 else 1e-2)
+    dg0 = torch.full((c,), 2.0, device="cuda")   # accumulated into, not overwritten
+    db0 = torch.full((c,), -1.0, device="cuda")
+    dx, dg, db = T.groupnorm_silu_backward(to(x), stats, gamma.cuda(), beta.cuda(), to(dy), 32, 1e-6, silu, dgamma_out=dg0, dbeta_out=db0,
+                                           add=to(add) if with_add else None)
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    assert rel(nchw(dx), want_dx) < tol
+    assert rel(dg - 2.0, gr.grad) < tol and rel(db + 1.0, br.grad) < tol
+
+
+@pytest.fixture(scope="module")
+def pair_flux(lib_built):
+    import ragb_vae_b200 as R
+    from ragb_vae_b200.trainer import VaeTrainStep
+
+    oracle = copy.deepcopy(O.build_oracle("flux", seed=0))
+    with torch.no_grad():
+        for p in oracle.parameters():
+            p.copy_(bf16r(p))
+    vae = R.RgbaAutoencoder("flux")
+    vae.load_state_dict(oracle.state_dict())
+    step = VaeTrainStep(vae.to("cuda", torch.bfloat16), lr=1e-3, kl_scale=1e-6)
+    return oracle, step
+
+
+def test_flux_resblock_backward(pair_flux):
+    oracle, step = pair_flux
+    # 128 -> 256 with a 1x1 shortcut, and an identity-shortcut block
+    _block_case(pair_flux, step.vae.encoder.down_blocks[1].resnets[0], oracle.encoder.down_blocks[1].resnets[0], step._res_fwd,
+                step._res_bwd, 128, h=16, w=16)
+    _block_case(pair_flux, step.vae.decoder.up_blocks[3].resnets[1], oracle.decoder.up_blocks[3].resnets[1], step._res_fwd,
+                step._res_bwd, 128, h=16, w=24)
+
+
+def test_flux_attention_backward(pair_flux):
+    oracle, step = pair_flux
+    _block_case(pair_flux, step.vae.decoder.mid_block.attentions[0], oracle.decoder.mid_block.attentions[0], step._attn_fwd,
+                step._attn_bwd, 512, h=16, w=24)
+
+
+def test_flux_full_step_gradients_match_oracle_autograd(pair_flux):
+    """The whole Flux-arch step at 2 x 64 x 64 against torch autograd on the oracle: every parameter's gradient."""
+    oracle, step = pair_flux
+    x = O.synthetic_rgba(2, 64, 64, seed=11)
+    noise = torch.randn(2, 16, 8, 8, generator=torch.Generator().manual_seed(12))
+    metrics, want = O.training_step(oracle, x, noise, kl_scale=1e-6)
+    got_metrics = step.forward_backward(x.cuda(), noise.cuda())
+    step.reducer.wait()
+    for k in ("train/recon", "train/kl", "train/loss"):
+        assert abs(float(got_metrics[k]) - float(metrics[k])) <= 2e-2 * abs(float(metrics[k])), k
+    grads = step.named_grads()
+    assert set(want) == set(grads), (set(want) ^ set(grads))
+    flat_g = torch.cat([grads[k].reshape(-1).cpu() for k in want])
+    flat_w = torch.cat([want[k].reshape(-1) for k in want])
+    worst = {k: rel(grads[k], want[k]) for k in want if want[k].norm() > 1e-3 * flat_w.norm()}
+    import json, os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "trainstep_grad_report_flux.json"), "w") as f:
+            json.dump({"flat_rel": rel(flat_g, flat_w), "flat_cos": cos(flat_g, flat_w),
+                       "per_tensor": dict(sorted(worst.items(), key=lambda kv: -kv[1])[:20])}, f, indent=1)
+    except OSError:
+        pass
+    assert rel(flat_g, flat_w) < 3e-2 and cos(flat_g, flat_w) > 0.999
+    bad = {k: v for k, v in worst.items() if v > 8e-2}
+    assert not bad, bad
+
+
+def test_flux_step_graphed_and_checkpointed_match_eager(lib_built):
+    """Two optimizer steps of the Flux arch: CUDA-graph replay and gradient checkpointing against the plain eager step."""
+    import ragb_vae_b200 as R
+    from ragb_vae_b200.trainer import VaeTrainStep
+
+    oracle = O.build_oracle("flux", seed=3)
+    x = O.synthetic_rgba(2, 64, 64, seed=31).cuda()
+    noise = torch.randn(2, 16, 8, 8, generator=torch.Generator().manual_seed(32)).cuda()
+    deltas, losses = [], []
+    for mode in ("eager", "graphed", "checkpointed"):
+        vae = R.RgbaAutoencoder("flux")
+        vae.load_state_dict(oracle.state_dict())
+        vae = vae.to("cuda", torch.bfloat16)
+        if mode == "checkpointed":
+            vae.enable_gradient_checkpointing()
+        step = VaeTrainStep(vae, lr=1e-4, kl_scale=1e-6)
+        start = step.opt.master.clone()
+        for _ in range(2):
+            m = (step.step_graphed if mode == "graphed" else step.step)(x, noise)
+        losses.append(float(m["train/loss"]))
+        deltas.append((step.opt.master - start).cpu())
+    for i in (1, 2):
+        assert abs(losses[0] - losses[i]) <= 1e-3 * abs(losses[0])
+        assert cos(deltas[0], deltas[i]) > 0.99
