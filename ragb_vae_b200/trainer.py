@@ -55,11 +55,15 @@ class VaeTrainStep:
         self.ref_kl_scale = ref_kl_scale
         # parameters autograd would give a gradient to: everything except the video-only temporal convs
         named = [(n, p) for n, p in vae.named_parameters() if ".time_conv." not in n]
+        # flat-buffer order: encoder side first, decoder side last, so that the tail buckets hold decoder gradients only and
+        # their all-reduce starts while the encoder's backward still runs (quant_conv belongs to the encoder's backward)
+        named = [np for np in named if not self._decoder_side(np[0])] + [np for np in named if self._decoder_side(np[0])]
+        boundary = sum(p.numel() for n, p in named if not self._decoder_side(n))
         self.names = [n for n, _ in named]
         self.opt = T.FlatAdamW([p for _, p in named], lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
                                max_grad_norm=max_grad_norm)
         self._gview: Dict[int, torch.Tensor] = {id(p): self.opt.grad_view(i) for i, (_, p) in enumerate(named)}
-        self.reducer = T.GradientAllReducer(self.opt.grad, num_buckets=num_buckets, group=group)
+        self.reducer = T.GradientAllReducer(self.opt.grad, num_buckets=num_buckets, group=group, boundary=boundary)
         self._graphs: Dict[tuple, tuple] = {}
         self.launches_per_replay = 0
 
@@ -506,9 +510,13 @@ class VaeTrainStep:
                 if b not in self._started:
                     self.reducer.ready(b)
 
+    @staticmethod
+    def _decoder_side(name: str) -> bool:
+        return name.startswith(("decoder.", "post_quant_conv."))
+
     def _bucket_is_decoder(self, lo: int, hi: int) -> bool:
         for i, n in enumerate(self.names):
-            if self.opt.offsets[i + 1] > lo and self.opt.offsets[i] < hi and not n.startswith(("decoder.", "post_quant_conv.")):
+            if self.opt.offsets[i + 1] > lo and self.opt.offsets[i] < hi and not self._decoder_side(n):
                 return False
         return True
 

@@ -255,12 +255,23 @@ class GradientAllReducer:
     (SUM) asynchronously as soon as it is marked ready, and ``wait`` joins them before the optimizer step.  On the GPUs
     this is one NCCL all-reduce per bucket over NVLink/NVSwitch; the division by the world size is fused into AdamW."""
 
-    def __init__(self, flat_grad: torch.Tensor, num_buckets: int = 4, group=None):
+    def __init__(self, flat_grad: torch.Tensor, num_buckets: int = 4, group=None, boundary: Optional[int] = None):
+        """``boundary``: offset in the flat buffer where the parameters whose gradients come FIRST in the backward pass
+        begin (the decoder side of a VAE).  Bucket edges then never straddle it: [boundary, n) and [0, boundary) are cut
+        separately, in proportion to their sizes, so every late-side bucket can start before the early side's backward."""
         self.grad, self.group = flat_grad, group
         n = flat_grad.numel()
         num_buckets = max(1, min(num_buckets, n))
-        edges = [n - (n * i) // num_buckets for i in range(num_buckets + 1)]  # n ... 0
-        self.buckets = [(edges[i + 1], edges[i]) for i in range(num_buckets)]  # last parameters first
+
+        def cut(lo, hi, k):  # k contiguous buckets of [lo, hi), last elements first
+            edges = [hi - ((hi - lo) * i) // k for i in range(k + 1)]
+            return [(edges[i + 1], edges[i]) for i in range(k)]
+
+        if boundary is None or boundary <= 0 or boundary >= n or num_buckets < 2:
+            self.buckets = cut(0, n, num_buckets)  # last parameters first
+        else:
+            k_late = min(num_buckets - 1, max(1, round(num_buckets * (n - boundary) / n)))
+            self.buckets = cut(boundary, n, k_late) + cut(0, boundary, num_buckets - k_late)
         self._work = []
         # measurement (bench.py): with ``timing`` on, ``wait`` brackets every bucket's join with CUDA events on the compute
         # stream; ``exposed_ms()`` then gives, per bucket, how long the compute stream sat blocked on that all-reduce

@@ -67,6 +67,10 @@ def _allreduce_worker(rank, world, port, tmp):
     g = torch.arange(1000, dtype=torch.float32) * (rank + 1)
     red = GradientAllReducer(g, num_buckets=4)
     assert [hi - lo for lo, hi in red.buckets] == [250] * 4 and red.buckets[0] == (750, 1000)  # last parameters first
+    # a boundary (decoder side begins at 600): no bucket straddles it, both sides are cut in proportion to their sizes
+    red2 = GradientAllReducer(g, num_buckets=4, boundary=600)
+    assert red2.buckets == [(800, 1000), (600, 800), (300, 600), (0, 300)]
+    assert GradientAllReducer(g, num_buckets=4, boundary=950).buckets[0] == (950, 1000)
     for b in range(4):      # buckets become ready in backward order
         red.ready(b)
     scale = red.wait()
