@@ -127,13 +127,16 @@ __device__ __forceinline__ float warp_max(float v) {
 // the accurate form costs ~40 instructions per element, which makes a streaming kernel ALU-bound
 // (measured 2.8 TB/s instead of HBM speed).
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
-// sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5: ONE MUFU op (tanh.approx, 2^-11 relative) and three FMA-pipe ops per element instead of
-// ex2 + rcp and four -- the SFU runs 16 lanes per clock per SM, and a fused-norm conv epilogue spends two of them per element.
-__device__ __forceinline__ float silu_fast(float x) {
+// silu(x) = x * sigmoid(x) with sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5, i.e. with h = x / 2:  silu = h * tanh(h) + h.
+// ONE MUFU op (tanh.approx, 2^-11 relative) and two FMA-pipe ops per element (mul, fma) instead of ex2 + rcp and four -- the
+// SFU runs 16 lanes per clock per SM, and at HBM speed a norm kernel has ~10 instruction slots per element in total.
+// silu_from_half takes h directly: callers that scale by a constant anyway fold the 1/2 into it.
+__device__ __forceinline__ float silu_from_half(float h) {
   float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
-  return x * fmaf(t, 0.5f, 0.5f);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
 }
+__device__ __forceinline__ float silu_fast(float x) { return silu_from_half(0.5f * x); }
 template <typename T> __device__ __forceinline__ float silu_t(float x);
 template <> __device__ __forceinline__ float silu_t<float>(float x) { return silu(x); }
 template <> __device__ __forceinline__ float silu_t<__nv_bfloat16>(float x) { return silu_fast(x); }

@@ -142,7 +142,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a128, const __grid_cons
   if (p.e.fast && p.e.bias_mode == 1)
     for (int i = threadIdx.x; i < p.e.cout; i += HL_THREADS) s_bias[i] = p.e.bias[i];
   if (p.e.norm_gamma)
-    for (int i = threadIdx.x; i < p.e.cout; i += HL_THREADS) s_gamma[i] = p.e.norm_gamma[i];
+    for (int i = threadIdx.x; i < p.e.cout; i += HL_THREADS) s_gamma[i] = p.e.norm_gamma[i] * (p.e.norm_silu ? 0.5f : 1.0f);  // SiLU's 1/2 rides in gamma
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / TMA signal

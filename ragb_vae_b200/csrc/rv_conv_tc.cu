@@ -118,7 +118,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (bias_smem)
     for (int i = threadIdx.x; i < p.e.cout; i += TC_THREADS) s_bias[i] = p.e.bias[i];
   if (p.e.norm_gamma)
-    for (int i = threadIdx.x; i < p.e.cout; i += TC_THREADS) s_gamma[i] = p.e.norm_gamma[i];
+    for (int i = threadIdx.x; i < p.e.cout; i += TC_THREADS) s_gamma[i] = p.e.norm_gamma[i] * (p.e.norm_silu ? 0.5f : 1.0f);  // SiLU's 1/2 rides in gamma
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -319,7 +319,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (bias_smem)
     for (int i = threadIdx.x; i < p.e.cout; i += TC_THREADS) s_bias[i] = p.e.bias[i];
   if (p.e.norm_gamma)
-    for (int i = threadIdx.x; i < p.e.cout; i += TC_THREADS) s_gamma[i] = p.e.norm_gamma[i];
+    for (int i = threadIdx.x; i < p.e.cout; i += TC_THREADS) s_gamma[i] = p.e.norm_gamma[i] * (p.e.norm_silu ? 0.5f : 1.0f);  // SiLU's 1/2 rides in gamma
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / TMA signal

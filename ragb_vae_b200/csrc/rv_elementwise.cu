@@ -89,11 +89,13 @@ __global__ void __launch_bounds__(256) rmsnorm_silu_warp_kernel(const T* __restr
   const int grp = lane / L;                // pixel group within the warp
   const int ppw = 32 / L;                  // pixels per warp per step
   const int64_t c = (int64_t)L * CPL * V::N;
+  // bf16 + SiLU: the 1/2 of silu(f) = h tanh(h) + h, h = f / 2, rides in gamma (one multiply less per element)
+  constexpr bool HALF = SILU && sizeof(T) == 2;
   float g[CPL][V::N];
 #pragma unroll
   for (int k = 0; k < CPL; ++k)
 #pragma unroll
-    for (int j = 0; j < V::N; ++j) g[k][j] = gamma[(k * L + sub) * V::N + j] * sqrt_c;
+    for (int j = 0; j < V::N; ++j) g[k][j] = gamma[(k * L + sub) * V::N + j] * sqrt_c * (HALF ? 0.5f : 1.0f);
   const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t p0 = warp_global * ppw * PIX; p0 < pixels; p0 += warps_total * ppw * PIX) {
@@ -128,8 +130,8 @@ __global__ void __launch_bounds__(256) rmsnorm_silu_warp_kernel(const T* __restr
           V o;
 #pragma unroll
           for (int j = 0; j < V::N; ++j) {
-            float f = v[u][k].get(j) * rinv * g[k][j];
-            o.set(j, SILU ? silu_t<T>(f) : f);
+            float f = v[u][k].get(j) * (rinv * g[k][j]);
+            o.set(j, HALF ? silu_from_half(f) : (SILU ? silu_t<T>(f) : f));
           }
           o.store(y + pix * c + (int64_t)(k * L + sub) * V::N);
         }

@@ -12,7 +12,7 @@
 
 namespace rv {
 
-constexpr int RB_PIX_PER_BLOCK = 16384;   // 8 sweeps of 256 threads x 8 bf16: B = 8 x 1024^2 is ONE wave of 512 blocks
+constexpr int RB_PIX_PER_BLOCK = 8192;    // 4 sweeps of 256 threads x 8 bf16 (measured best of 2048 ... 65536 at B = 8 and B = 32)
 constexpr int RB_MAX = 512;
 constexpr int MAX_BG = 4;
 constexpr int TICKET_SLOTS = 64;          // distinct streams that can use the single-launch path

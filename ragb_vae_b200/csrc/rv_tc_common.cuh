@@ -492,9 +492,9 @@ __device__ __forceinline__ void fast_norm_pass2(const EpiParams& e, const float*
       v[4 * j + 2] *= rinv * g.z;
       v[4 * j + 3] *= rinv * g.w;
     }
-    if (e.norm_silu) {
+    if (e.norm_silu) {  // sgamma carries the 1/2: v is h = f / 2 here and silu(f) = h tanh(h) + h
 #pragma unroll
-      for (int j = 0; j < W; ++j) v[j] = silu_fast(v[j]);
+      for (int j = 0; j < W; ++j) v[j] = silu_from_half(v[j]);
     }
     fast_store<W>(e.y_act + pix * e.y_cstride + co0, v);
   }
