@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 20
+#define RV_ABI_VERSION 21
 #define RV_PROF_CATEGORIES 10
 
 int rv_abi_version(void);
@@ -89,6 +89,13 @@ int rv_conv2d_direct(const rv_conv_desc* d, const void* x, const float* w, const
  * bf16 with pitch y_cstride. */
 int rv_conv2d_tc(const rv_conv_desc* d, const void* x, const void* w_packed, int64_t w_ld,
                  const float* bias, const void* residual, void* y, void* stream);
+
+/* conv_out of the decoder (the last call inside vae.decode: src/models/rgba_vae.py:279, rgba_vae_stage.py:452,
+ * flux_kontext_textalpha.py:497): 3x3 / stride 1 / pad 1, cin = 64 | 96 | 128 NHWC bf16 -> cout <= 5 NCHW (bf16 or fp32) with
+ * bias, out_scale / out_shift and clamp of the descriptor (the (y+1)/2 + clamp(0,1) of RgbaVAE.forward).  HBM-bound: the
+ * kernel-row index rides in the MMA's N (3 * cout <= 16) so that every input row is multiplied once.  w_taps: bf16
+ * [3 (dx)][16 rows: dy * cout + co, zero padded][cin]. */
+int rv_conv_out(const rv_conv_desc* d, const void* x, const void* w_taps, const float* bias, void* y, void* stream);
 
 /* rv_conv2d_tc plus the consumer's QwenImageRMS_norm (+SiLU) fused into the epilogue: besides (or, with
  * y == NULL, instead of) the raw output it writes y_act = act(v / max(||v||_2 over cout, 1e-12) * gamma_scaled)

@@ -576,6 +576,11 @@ class RgbaAutoencoder(nn.Module):
         y = None
         if want_raw or not fuse:
             y = torch.empty((n, cout, oh, ow) if y_nchw else (n, oh, ow, cout), dtype=y_dt, device=x.device)
+        if tc and y_nchw and residual is None and not hpack and ops.conv_out_eligible(n, h, w, cin, cx, cout, k, stride, upsample):
+            # conv_out: an HBM-bound layer (Cout = 4) on its own kernel -- the kernel-row index rides in the MMA's N
+            wt = self._cached((id(conv), "conv_out_taps"), [conv.weight], lambda: ops.pack_conv_out_weights(conv.weight2d()))
+            ops.conv_out(desc, x, wt, bias, y)
+            return _Stream(y, None, None)
         if tc:
             if hpack:
                 wp = self._hpack_weights(conv)

@@ -18,7 +18,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(PKG, "librgbavae.so")
-SOURCES = ["rv_common.cu", "rv_elementwise.cu", "rv_reduce.cu", "rv_conv_direct.cu", "rv_conv_tc.cu", "rv_conv_halo.cu", "rv_attention.cu", "rv_plumbing.cu", "rv_train.cu", "rv_conv_wgrad.cu"]
+SOURCES = ["rv_common.cu", "rv_elementwise.cu", "rv_reduce.cu", "rv_conv_direct.cu", "rv_conv_tc.cu", "rv_conv_halo.cu", "rv_conv_out.cu", "rv_attention.cu", "rv_plumbing.cu", "rv_train.cu", "rv_conv_wgrad.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr",

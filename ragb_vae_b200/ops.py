@@ -97,6 +97,26 @@ def conv2d_tc(desc: ConvDesc, x, w_packed, w_ld: int, bias, residual, y) -> None
                                    _stream(x)), "rv_conv2d_tc")
 
 
+def conv_out(desc: ConvDesc, x, w_taps, bias, y) -> None:
+    """The decoder's conv_out (3x3, 64/96/128 -> <= 5 channels, NCHW output) on its HBM-bound kernel (rv_conv_out)."""
+    _need_cuda(x, w_taps, bias, y)
+    check(_lib.load().rv_conv_out(C.byref(desc), _ptr(x), _ptr(w_taps), _ptr(bias), _ptr(y), _stream(x)), "rv_conv_out")
+
+
+def pack_conv_out_weights(w: torch.Tensor) -> torch.Tensor:
+    """[cout][cin][3][3] -> bf16 [3 (dx)][16 rows: dy * cout + co, zero padded][cin] as one [48][cin] matrix."""
+    cout, cin = w.shape[0], w.shape[1]
+    if 3 * cout > 16 or tuple(w.shape[2:]) != (3, 3):
+        raise ValueError(f"conv_out weights must be [<=5][cin][3][3], got {tuple(w.shape)}")
+    t = w.detach().to(torch.float32).permute(3, 2, 0, 1).reshape(3, 3 * cout, cin)   # [dx][dy * cout + co][c]
+    t = torch.nn.functional.pad(t, (0, 0, 0, 16 - 3 * cout))
+    return t.reshape(48, cin).to(torch.bfloat16).contiguous()
+
+
+def conv_out_eligible(n: int, h: int, w: int, cin: int, cx: int, cout: int, k: int, stride: int, upsample: bool) -> bool:
+    return k == 3 and stride == 1 and not upsample and cin in (64, 96, 128) and cx == cin and 3 * cout <= 16 and w >= 64
+
+
 def conv2d_tc_norm(desc: ConvDesc, x, w_packed, w_ld: int, bias, residual, y, y_act, gamma_scaled, silu: bool) -> None:
     """conv2d_tc with the consumer's RMS norm (+SiLU) fused into the epilogue; y may be None (activated output only)."""
     _need_cuda(x, w_packed, bias, residual, y, y_act, gamma_scaled)

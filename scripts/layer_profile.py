@@ -38,6 +38,8 @@ def d_sm(s, dt):
 
 ops.conv2d_tc = wrap("conv_tc", ops.conv2d_tc, d_conv)
 ops.conv2d_tc_norm = wrap("conv_tc+norm", ops.conv2d_tc_norm, d_conv)
+ops.conv_out = wrap("conv_out", ops.conv_out, d_conv)
+ops.attention = wrap("attention", ops.attention, lambda q, k, vt, n, t: dict(shape=f"n{n} tokens {t} d{vt.shape[1]}", flops=4.0 * n * t * t * vt.shape[1]))
 ops.conv2d_direct = wrap("conv_direct", ops.conv2d_direct, d_conv)
 ops.rmsnorm_silu = wrap("rmsnorm", ops.rmsnorm_silu, d_norm)
 ops.groupnorm_silu = wrap("groupnorm", ops.groupnorm_silu, d_gn)

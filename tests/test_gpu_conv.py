@@ -219,3 +219,30 @@ def test_hpack_stem_matches_conv2d(ops, shape):
         outs.append(st.raw.float().permute(0, 3, 1, 2).cpu())
     for o in outs:
         assert float((o - ref).norm() / ref.norm()) < 1e-2
+
+
+@pytest.mark.parametrize("cin,cout", [(96, 4), (128, 4), (64, 4), (96, 3), (96, 5)])
+@pytest.mark.parametrize("shape,f32", [((2, 40, 200), False), ((1, 133, 64), True), ((1, 1024, 1024), False)])
+def test_conv_out_kernel_matches_conv2d(ops, cin, cout, shape, f32):
+    """rv_conv_out (kernel rows in the MMA's N, weights stationary, dy summed from TMEM by the pixel's thread) against
+    F.conv2d on the same bf16-rounded operands, incl. ragged widths / heights, image borders, several strips per column,
+    the fused affine + clamp of RgbaVAE.forward and fp32 / bf16 NCHW outputs."""
+    n, h, w = shape
+    if h * w >= 1 << 20 and (cin, cout) != (96, 4):
+        pytest.skip("full resolution once")
+    g = torch.Generator(device="cuda").manual_seed(cin * 7 + cout + h)
+    x = torch.randn(n, h, w, cin, generator=g, device="cuda").bfloat16()
+    wt = (torch.randn(cout, cin, 3, 3, generator=g, device="cuda") / (3.0 * cin ** 0.5)).bfloat16().float()
+    b = torch.randn(cout, generator=g, device="cuda") * 0.1
+    y = torch.empty(n, cout, h, w, dtype=torch.float32 if f32 else torch.bfloat16, device="cuda")
+    d = ops.make_desc(n, h, w, cin, cout, 3, 1, False, x_dtype=RV_BF16, y_dtype=RV_F32 if f32 else RV_BF16, y_nchw=True,
+                      out_scale=0.5, out_shift=0.5, clamp=(0.0, 1.0))
+    assert ops.conv_out_eligible(n, h, w, cin, cin, cout, 3, 1, False)
+    ops.conv_out(d, x, ops.pack_conv_out_weights(wt), b, y)
+    ref = torch.clamp(F.conv2d(x.float().permute(0, 3, 1, 2), wt, b, padding=1) * 0.5 + 0.5, 0.0, 1.0)
+    err = float((y.float() - ref).abs().max())
+    assert err < (2e-4 if f32 else 5e-3), err
+    # borders and the strip seams specifically (the first / last rows and columns are where halo handling lives)
+    for sl in ((slice(None), slice(None), slice(0, 2)), (slice(None), slice(None), slice(-2, None)),
+               (slice(None), slice(None), slice(None), slice(0, 2)), (slice(None), slice(None), slice(None), slice(-2, None))):
+        assert float((y.float()[sl] - ref[sl]).abs().max()) < (2e-4 if f32 else 5e-3)
