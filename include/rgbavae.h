@@ -134,7 +134,8 @@ int rv_groupnorm_silu(const void* x, const double* stats, const float* gamma, co
 int rv_softmax_rows(const float* s, void* p, int64_t rows, int64_t cols, int64_t ld_s, int64_t ld_p,
                     int dtype, void* stream);
 
-/* Fused single-head attention O = softmax(Q K^T / sqrt(d)) V for d = 384 (QwenImageAttentionBlock): scores and
+/* Fused single-head attention O = softmax(Q K^T / sqrt(d)) V for d = 384 (QwenImageAttentionBlock) and d = 512 (the
+ * diffusers Attention block of the Flux AutoencoderKL; two output-column passes inside the kernel): scores and
  * probabilities stay in TMEM / shared memory.  q, k: bf16 [n_img*tokens][ld_qk] (row pitch in elements; q and k may
  * be column slices of one tensor); vt: bf16 V transposed, [n_img][d][tokens]; out: bf16 [n_img*tokens][ld_out].
  * tokens % 128 == 0. */

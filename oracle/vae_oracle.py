@@ -5,11 +5,15 @@ executes below its drop-in boundary.  It is used only by ``tests/``,
 ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
 reference`` legs, as the checker.  Nothing under ``ragb_vae_b200/`` imports it.
 
-PARITY UNPINNED: the reference (jaejung-dev/ragb-vae) ships no tests, golden
-vectors or fixtures, and the arithmetic lives in the
-un-vendored, un-pinned third-party package ``diffusers`` (requirements.txt:2),
-which is not installable here.  The restatement below follows the published
-diffusers algorithms:
+PARITY, what is pinned and what is not.  The reference (jaejung-dev/ragb-vae) ships no tests, golden vectors or
+fixtures.  Its OWN pure-torch functions restated here (losses, composites, PSNR, triplet,
+blend, batch assembly, adapt_vae_to_rgba, RgbaVAE.forward / .loss, the validation loop) ARE pinned to the reference
+itself: scripts/make_reference_fixtures.py executes the unmodified reference files through the sys.modules shim of
+tests/refshim.py and commits their outputs under tests/golden/ref_*; tests/test_reference_pin.py holds this file
+to them (and re-derives them live where /root/reference exists).  PARITY UNPINNED for the diffusers-internal half:
+the conv / norm / attention stacks and the posterior live in the un-vendored, un-pinned third-party package
+``diffusers`` (requirements.txt:2), which is not installable here.  That half follows the published diffusers
+algorithms:
 
 * ``arch="flux"``  -- ``diffusers.AutoencoderKL`` with the FLUX.1 vae config
   (``models/autoencoders/autoencoder_kl.py``, ``vae.py::Encoder/Decoder``,
