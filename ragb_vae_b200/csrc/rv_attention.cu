@@ -75,11 +75,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
-// PAIR: two CTAs (256 queries) issue M = 256 MMAs and split every K / V^T chunk between their shared memories
-// (cta_group::2), which halves the B-operand reads that bound the single-CTA form.
+// (A CTA-pair form -- M = 256 MMAs, K / V^T chunks split between two shared memories -- was built and measured in rounds 1 and
+// 2: 933 vs 958 TFLOP/s; the kernel is paced by its softmax warps, not by operand reads.  Removed.)
 // DCH: 64-wide chunks of d; OPARTS: N = 128 parts of O per pass; NPASS: key-loop passes; RING: K / V^T ring slots
 // (6, 3, 1, 5 for d = 384; 8, 2, 2, 3 for d = 512) -- compile-time so that the d = 384 loops stay fully unrolled
-template <bool PAIR, int DCH, int OPARTS, int NPASS, int RING>
+template <int DCH, int OPARTS, int NPASS, int RING>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                   const __grid_constant__ CUtensorMap map_vt, const __grid_constant__ FaParams p) {
@@ -102,11 +102,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const int nb = p.tokens / FA_BK;
   const int qblocks = p.tokens / FA_BQ;
   const int img = blockIdx.x / qblocks;
-  const int q0 = (blockIdx.x - img * qblocks) * FA_BQ;   // consecutive blocks = the two CTAs of a pair
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
-  const bool leader = rank == 0;
-  const uint32_t slot_bytes = PAIR ? FA_SLOT / 2 : FA_SLOT;
-  const int nshare = PAIR ? 2 : 1;
+  const int q0 = (blockIdx.x - img * qblocks) * FA_BQ;
+  constexpr uint32_t slot_bytes = FA_SLOT;
 
   if (warp == 0 && lane == 0) {
     mbar_init(smem_u32(&bar_q), 1);
@@ -116,46 +113,30 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     mbar_init(smem_u32(&bar_sfull), 1);
-    mbar_init(smem_u32(&bar_sempty), FA_SM_WARPS * nshare);
-    mbar_init(smem_u32(&bar_pfull), FA_SM_WARPS * nshare);
+    mbar_init(smem_u32(&bar_sempty), FA_SM_WARPS);
+    mbar_init(smem_u32(&bar_pfull), FA_SM_WARPS);
     mbar_init(smem_u32(&bar_pvdone), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     __syncwarp();
-    if (PAIR) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u)
-                   : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u)
-                   : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
   const uint32_t fullk0 = smem_u32(&bar_fullk[0]), fullv0 = smem_u32(&bar_fullv[0]), empty0 = smem_u32(&bar_empty[0]);
   const uint32_t sfull = smem_u32(&bar_sfull), sempty = smem_u32(&bar_sempty), pfull = smem_u32(&bar_pfull),
                  pvdone = smem_u32(&bar_pvdone), qbar = smem_u32(&bar_q);
-  // barriers the MMA issuer (leader CTA) waits on, as cluster addresses, for signals that come from both CTAs
-  const uint32_t lead_fullk0 = PAIR ? mapa_rank(fullk0, 0) : fullk0;
-  const uint32_t lead_fullv0 = PAIR ? mapa_rank(fullv0, 0) : fullv0;
-  const uint32_t lead_q = PAIR ? mapa_rank(qbar, 0) : qbar;
-  const uint32_t lead_sempty = PAIR ? mapa_rank(sempty, 0) : sempty;
-  const uint32_t lead_pfull = PAIR ? mapa_rank(pfull, 0) : pfull;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
-      if (leader) mbar_arrive_expect_tx(qbar, q_bytes * nshare);
-      for (int c = 0; c < DCH; ++c) {
-        if (PAIR) tma2_load_2d(q_smem + c * 16384u, &map_q, lead_q, c * 64, img * p.tokens + q0);
-        else tma_load_2d(q_smem + c * 16384u, &map_q, qbar, c * 64, img * p.tokens + q0);
-      }
+      mbar_arrive_expect_tx(qbar, q_bytes);
+      for (int c = 0; c < DCH; ++c) tma_load_2d(q_smem + c * 16384u, &map_q, qbar, c * 64, img * p.tokens + q0);
     }
     __syncwarp();
     uint32_t slot = 0, par = 0;
@@ -166,12 +147,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int c = 0; c < DCH; ++c) {
           mbar_wait(empty0 + 8u * slot, par ^ 1u);
           if (elect_one()) {
-            if (leader) mbar_arrive_expect_tx(fullk0 + 8u * slot, slot_bytes * nshare);
-            if (PAIR)   // this CTA's 64 of the block's 128 keys
-              tma2_load_2d(ring + slot * slot_bytes, &map_k, lead_fullk0 + 8u * slot, c * 64,
-                           img * p.tokens + step * FA_BK + (int)rank * 64);
-            else
-              tma_load_2d(ring + slot * slot_bytes, &map_k, fullk0 + 8u * slot, c * 64, img * p.tokens + step * FA_BK);
+            mbar_arrive_expect_tx(fullk0 + 8u * slot, slot_bytes);
+            tma_load_2d(ring + slot * slot_bytes, &map_k, fullk0 + 8u * slot, c * 64, img * p.tokens + step * FA_BK);
           }
           __syncwarp();
           if (++slot == nring) { slot = 0; par ^= 1u; }
@@ -184,12 +161,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           for (int h = 0; h < OPARTS; ++h) {
             mbar_wait(empty0 + 8u * slot, par ^ 1u);
             if (elect_one()) {
-              if (leader) mbar_arrive_expect_tx(fullv0 + 8u * slot, slot_bytes * nshare);
-              if (PAIR)  // this CTA's 64 of the 128 d-rows of the chunk
-                tma2_load_3d(ring + slot * slot_bytes, &map_vt, lead_fullv0 + 8u * slot, j * FA_BK + kc * 64,
-                             vrow0 + h * 128 + (int)rank * 64, img);
-              else
-                tma_load_3d(ring + slot * slot_bytes, &map_vt, fullv0 + 8u * slot, j * FA_BK + kc * 64, vrow0 + h * 128, img);
+              mbar_arrive_expect_tx(fullv0 + 8u * slot, slot_bytes);
+              tma_load_3d(ring + slot * slot_bytes, &map_vt, fullv0 + 8u * slot, j * FA_BK + kc * 64, vrow0 + h * 128, img);
             }
             __syncwarp();
             if (++slot == nring) { slot = 0; par ^= 1u; }
@@ -201,24 +174,18 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     // Both walk the producer's push sequence (per pass: K(0) | K(1) V(0) | K(2) V(1) | ... | V(nb-1)); each consumes its own
     // kind of ring slot and only counts past the other's.
     const bool is_qk = warp == 1;
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((128u >> 4) << 24);
     const uint64_t hi = make_smem_desc(0u, 1024u, 2u);
     const uint32_t q_lo = (q_smem & 0x3FFFFu) >> 4, p_lo = (p_smem & 0x3FFFFu) >> 4, ring_lo = (ring & 0x3FFFFu) >> 4;
     const uint32_t s_tmem = tmem_base + 384u;
     uint32_t slot = 0, use_par = 0;  // bit s of use_par: parity of this issuer's next use of slot s
-    auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accf) {
-      if (PAIR) umma2_bf16(d, a, b, idesc, accf);
-      else umma_bf16(d, a, b, idesc, accf);
-    };
-    auto commit = [&](uint32_t bar) {
-      if (PAIR) umma2_commit_both(bar);
-      else umma_commit(bar);
-    };
+    auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accf) { umma_bf16(d, a, b, idesc, accf); };
+    auto commit = [&](uint32_t bar) { umma_commit(bar); };
     auto skip = [&](int n) {
       for (int i = 0; i < n; ++i)
         if (++slot == nring) slot = 0;
     };
-    if (leader) {
+    {
       if (is_qk) mbar_wait(qbar, 0);
       int g = 0;  // key blocks issued so far over all passes: every per-block barrier flips once per block
       for (int pass = 0; pass < NPASS; ++pass)
@@ -282,7 +249,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             }
           }
         }
-    }  // leader
+    }
   } else if (warp >= 2 && warp < FA_PV_WARP) {
     // ------------------------------ softmax / correction / output ------------------------------
     const int q = warp & 3, part = (warp - 2) >> 2;
@@ -305,7 +272,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { if (PAIR) mbar_arrive_cluster(lead_sempty); else mbar_arrive(sempty); }
+        if (lane == 0) mbar_arrive(sempty);
         float mx = -INFINITY;
 #pragma unroll
         for (int i = 0; i < FA_KCOLS; ++i) mx = fmaxf(mx, __uint_as_float(s0[i]));
@@ -359,11 +326,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                        "r"(pk[4 * u + 3])
                        : "memory");
         }
-        if (PAIR) asm volatile("fence.proxy.async;" ::: "memory");
-        else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { if (PAIR) mbar_arrive_cluster(lead_pfull); else mbar_arrive(pfull); }
+        if (lane == 0) mbar_arrive(pfull);
       }
       // ---- output of this pass: O / l into columns [pass * oparts * 128, ...) ----
       s_xsum[part][row] = l;
@@ -393,12 +359,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -422,24 +386,19 @@ extern "C" int rv_attention(const void* q, const void* k, int64_t ld_qk, const v
   RV_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)vt % 16 == 0) && ((uintptr_t)out % 16 == 0),
                "attention: tensors must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  // CTA pairs are built (template PAIR) but off by default: measured 7.9 ms vs 7.4 ms per step for the single-CTA
-  // form -- the kernel is bound by the softmax warps, not by the B-operand reads a pair would halve.
-  static const bool want_pair = getenv("RGBAVAE_ATTN_PAIR") != nullptr;
-  const bool pair = want_pair && tokens % 256 == 0;  // the two CTAs of a pair take adjacent query blocks of one image
-  const cuuint32_t share = pair ? 2u : 1u;
   CUtensorMap mq, mk, mv;
   {
     cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)((int64_t)n_img * tokens)};
     cuuint64_t str[1] = {(cuuint64_t)ld_qk * 2u};
     cuuint32_t box[2] = {64, 128};
     if (int rc = tc_encode_map(&mq, q, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    cuuint32_t boxk[2] = {64, 128u / share};
+    cuuint32_t boxk[2] = {64, 128};
     if (int rc = tc_encode_map(&mk, k, 2, dims, str, boxk, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   }
   {
     cuuint64_t dims[3] = {(cuuint64_t)tokens, (cuuint64_t)d, (cuuint64_t)n_img};
     cuuint64_t str[2] = {(cuuint64_t)tokens * 2u, (cuuint64_t)tokens * 2u * d};
-    cuuint32_t box[3] = {64, 128u / share, 1};
+    cuuint32_t box[3] = {64, 128, 1};
     if (int rc = tc_encode_map(&mv, vt, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   }
   const int ring_slots = d == 384 ? FA_RING : 3;
@@ -450,10 +409,8 @@ extern "C" int rv_attention(const void* q, const void* k, int64_t ld_qk, const v
     RV_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !g_fa_attr[dev]) {
       const int smem_max = 6 * 16384 + FA_RING * (int)FA_SLOT + (int)FA_P_BYTES + 1024;  // d = 384: 214 016 B; d = 512 needs the same
-      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<false, 6, 3, 1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<true, 6, 3, 1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<false, 8, 2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<true, 8, 2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<6, 3, 1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8, 2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
       g_fa_attr[dev] = true;
     }
   }
@@ -465,25 +422,8 @@ extern "C" int rv_attention(const void* q, const void* k, int64_t ld_qk, const v
   p.out = (__nv_bfloat16*)out;
   const int grid = n_img * (tokens / FA_BQ);
   LaunchScope scope(CAT_ATTN, st, 4.0 * (double)n_img * tokens * tokens * d);
-  if (pair) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(FA_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (d == 384) RV_CUDA(cudaLaunchKernelEx(&cfg, flash_attn_kernel<true, 6, 3, 1, 5>, mq, mk, mv, p));
-    else RV_CUDA(cudaLaunchKernelEx(&cfg, flash_attn_kernel<true, 8, 2, 2, 3>, mq, mk, mv, p));
-  } else {
-    if (d == 384) flash_attn_kernel<false, 6, 3, 1, 5><<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, p);
-    else flash_attn_kernel<false, 8, 2, 2, 3><<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, p);
-  }
+  if (d == 384) flash_attn_kernel<6, 3, 1, 5><<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, p);
+  else flash_attn_kernel<8, 2, 2, 3><<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, p);
   RV_LAUNCH_CHECK();
   return 0;
 }
