@@ -10,8 +10,9 @@
 // one-pixel shift of X, i.e. by one 128-byte row of the X box, so the CTA loads ONE dY box and ONE (KP + ksize - 1)-pixel
 // X box per K block and issues the MMAs of all ksize taps from them (descriptor start address + tx * 128 B) into ksize
 // TMEM accumulators: operand traffic per MMA is a third of the tap-per-CTA form.  It streams its image rows through a
-// TMA ring and adds the tiles to dW with fp32 atomics (split-K over pixels); dW is addressed through three strides so
-// the gradient lands directly in the parameter's own layout.  Warps: 0 TMA, 1 MMA, 2-5 epilogue.
+// TMA ring and adds the tiles to dW with fp32 atomics (split-K over pixels; the bias gradient = column sums of dY rides along as
+// one more N = 16 MMA against a tile of ones); dW is addressed through three strides so
+// the gradient lands directly in the parameter's own layout.  Warps: 0 TMA, 1 / 6 / 7 MMA (one per tap), 2-5 epilogue.
 #include <cstring>
 #include <mutex>
 
@@ -19,8 +20,9 @@
 
 namespace rv {
 
-constexpr int WG_THREADS = 192;
-constexpr int WG_KP = 64;            // pixels per K block (4 MMAs of K = 16)
+constexpr int WG_THREADS = 288;        // 0 TMA, 1 / 6 / 7 MMA issuers (one per tap of the kernel row), 8 bias issuer, 2-5 epilogue
+constexpr int WG_KP = 64;            // pixels per K block (4 MMAs of K = 16: the issue loop is written out)
+static_assert(WG_KP == 64, "conv_wgrad_kernel issues exactly four K = 16 MMAs per block");
 constexpr int WG_MAX_STAGES = 8;
 constexpr uint32_t WG_A_BOX = WG_KP * 128;  // one (64 channels x KP pixels) dY box
 constexpr uint32_t WG_B_BOX = 9 * 1024;     // one (64 channels x (KP + 2) pixels) X box, padded to the swizzle atom
@@ -31,6 +33,9 @@ struct WgParams {
   int co_tiles, ci_tiles, bn, nboxes_b;  // bn: Cin columns per tile (multiple of 16, ksize * bn <= 512)
   int splits, rows_per_split, x_blocks;
   float* dw;      // element (co, ci, tap) at dw[co * s_co + ci * s_ci + tap * s_tap], accumulated
+  float* dbias;   // optional [cout_valid], accumulated: the column sums of dY ride along as one extra N = 16 MMA per K block
+                  // against a constant tile of ones (first kernel row / first Cin tile only) -- no second pass over dY
+  uint32_t ones_off;
   long long s_co, s_ci, s_tap;
   int stages;
   uint32_t stage_bytes, tx_bytes, tmem_cols;
@@ -65,12 +70,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   const int row_hi = min(total_rows, row_lo + p.rows_per_split);
   const int num_kb = max(0, row_hi - row_lo) * p.x_blocks;
 
+  const bool do_bias = p.dbias != nullptr && ty == 0 && ci_t == 0;
+  const uint32_t issuers = (uint32_t)p.ksize + (do_bias ? 1u : 0u);
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
-      mbar_init(smem_u32(&bar_empty[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), issuers);  // released by every issuer
     }
-    mbar_init(smem_u32(&bar_done), 1);
+    mbar_init(smem_u32(&bar_done), issuers);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -78,6 +85,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (do_bias) {  // [KP pixels][64 ch] of bf16 1.0: an all-ones tile looks the same under any swizzle
+    for (uint32_t i = threadIdx.x; i < WG_A_BOX / 16u; i += WG_THREADS)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(smem_base + p.ones_off + i * 16u), "r"(0x3F803F80u) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -105,40 +117,59 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    // D fp32, A/B bf16, both MN-major (bits 15, 16), N = bn, M = 128
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.bn >> 3) << 17) |
-                           ((128u >> 4) << 24);
-    // MN-major SW128 descriptors: LBO = distance between 64-element MN blocks (one box), SBO = 8 K-rows = 1024 B
-    uint64_t hi_a = 0, hi_b = 0;
-    hi_a |= (uint64_t)(WG_A_BOX >> 4) << 16;
-    hi_b |= (uint64_t)(WG_B_BOX >> 4) << 16;
-    hi_a |= (uint64_t)(1024u >> 4) << 32;
-    hi_b |= (uint64_t)(1024u >> 4) << 32;
-    hi_a |= ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-    hi_b |= ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-    uint32_t stage = 0, phase = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      mbar_wait(full0 + 8u * stage, phase);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a_lo = ((smem_base + stage * p.stage_bytes) & 0x3FFFFu) >> 4;
-        const uint32_t b_lo = a_lo + (a_bytes >> 4);
-        for (int tx = 0; tx < p.ksize; ++tx) {
-#pragma unroll
-          for (int ks = 0; ks < WG_KP / 16; ++ks) {
-            // 16 pixels = two 8-row groups = 2048 bytes further down the box; tap tx starts tx pixel rows (128 B) in
-            umma_bf16(tmem_base + (uint32_t)(tx * p.bn), hi_a | (uint64_t)(a_lo + ks * 128u),
-                      hi_b | (uint64_t)(b_lo + ks * 128u + tx * 8u), idesc, (kb | ks) ? 1u : 0u);
+  } else if (warp == 1 || warp >= 6) {
+    // One issuing warp per tap of the kernel row (warp 1: tx = 0, warps 6 / 7: tx = 1 / 2), each into its own accumulator: a
+    // tcgen05.mma costs its issuing thread a fixed ~46 cycles on top of the N/2 the tensor pipe needs, so
+    // one issuer left the pipe 54 % idle at N = 96; independent instruction streams overlap that cost.
+    const int tx = warp == 1 ? 0 : warp - 5;   // 3: the bias issuer
+    const bool bias_warp = tx == 3;
+    if (tx < p.ksize || (bias_warp && do_bias)) {
+      // D fp32, A/B bf16, both MN-major (bits 15, 16), N = bn, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.bn >> 3) << 17) |
+                             ((128u >> 4) << 24);
+      // MN-major SW128 descriptors: LBO = distance between 64-element MN blocks (one box), SBO = 8 K-rows = 1024 B
+      uint64_t hi_a = 0, hi_b = 0;
+      hi_a |= (uint64_t)(WG_A_BOX >> 4) << 16;
+      hi_b |= (uint64_t)(WG_B_BOX >> 4) << 16;
+      hi_a |= (uint64_t)(1024u >> 4) << 32;
+      hi_b |= (uint64_t)(1024u >> 4) << 32;
+      hi_a |= ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+      hi_b |= ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(tx * p.bn);
+      // bias gradient (its own issuer, so that its ~46 cycles per MMA overlap the taps'): D[co][0..15] += dY^T . ones
+      const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t d_bias = tmem_base + (uint32_t)(p.ksize * p.bn);
+      const uint64_t ones_d = hi_a | (uint64_t)(((smem_base + p.ones_off) & 0x3FFFFu) >> 4);
+      const uint32_t stage_lo = p.stage_bytes >> 4;
+      const uint32_t a_lo0 = (smem_base & 0x3FFFFu) >> 4;
+      const uint32_t b_off = (a_bytes >> 4) + (uint32_t)tx * 8u;  // tap tx starts tx pixel rows (128 B) into the X box
+      uint32_t stage = 0, phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full0 + 8u * stage, phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_lo = a_lo0 + stage * stage_lo;
+          const uint64_t ad = hi_a | (uint64_t)a_lo, bd = hi_b | (uint64_t)(a_lo + b_off);
+          // 16 pixels = two 8-row groups = 2048 bytes further down the box
+          if (bias_warp) {
+            umma_bf16(d_bias, ad, ones_d, idesc1, kb ? 1u : 0u);
+            umma_bf16(d_bias, ad + 128u, ones_d + 128u, idesc1, 1u);
+            umma_bf16(d_bias, ad + 256u, ones_d + 256u, idesc1, 1u);
+            umma_bf16(d_bias, ad + 384u, ones_d + 384u, idesc1, 1u);
+          } else {
+            umma_bf16(d_tmem, ad, bd, idesc, kb ? 1u : 0u);
+            umma_bf16(d_tmem, ad + 128u, bd + 128u, idesc, 1u);
+            umma_bf16(d_tmem, ad + 256u, bd + 256u, idesc, 1u);
+            umma_bf16(d_tmem, ad + 384u, bd + 384u, idesc, 1u);
           }
+          umma_commit(empty0 + 8u * stage);
+          if (kb == num_kb - 1) umma_commit(done);
         }
-        umma_commit(empty0 + 8u * stage);
-        if (kb == num_kb - 1) umma_commit(done);
+        __syncwarp();
+        if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
       }
-      __syncwarp();
-      if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
     }
-  } else if (num_kb > 0) {
+  } else if (warp >= 2 && warp < 6 && num_kb > 0) {
     const int q = warp & 3;
     const int co = co0 + q * 32 + lane;
     mbar_wait(done, 0);
@@ -156,6 +187,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
             if (ci0 + c0 + j < p.cin_valid) atomicAdd(out + (long long)(ci0 + c0 + j) * p.s_ci, __uint_as_float(r[j]));
         }
       }
+    }
+    if (do_bias) {
+      uint32_t r[16];
+      tmem_ld16(taddr + (uint32_t)(p.ksize * p.bn), r);
+      tmem_ld_wait();
+      if (co < p.cout_valid) atomicAdd(p.dbias + co, __uint_as_float(r[0]));
     }
   }
   tc_fence_before();
@@ -227,7 +264,12 @@ extern "C" int rv_conv2d_wgrad(const void* x, const void* dy, float* dw, int64_t
   p.nboxes_b = (p.bn + 63) / 64;
   p.x_blocks = (w + WG_KP - 1) / WG_KP;
   p.tmem_cols = 32;
-  while ((int)p.tmem_cols < ksize * p.bn) p.tmem_cols <<= 1;
+  // The bias gradient (column sums of dY) rides along as one more N = 16 MMA against a tile of ones in the CTAs of the first
+  // kernel row / first Cin tile.  Measured: a win where those are a small share of the CTAs (384-channel layers: 9+ tiles per
+  // split, 0.97 -> 1.10 PFLOP/s incl. the bias), a loss where they are a third of them (96 / 192 channels: the extra work
+  // unbalances the grid) -- there a separate streaming pass over dY (colsum_kernel) is cheaper.
+  const bool fuse_bias = dbias != nullptr && ksize * p.co_tiles * p.ci_tiles >= 9;
+  while ((int)p.tmem_cols < ksize * p.bn + (fuse_bias ? 16 : 0)) p.tmem_cols <<= 1;
   const int tiles = ksize * p.co_tiles * p.ci_tiles;
   const int total_rows = n * h;
   int splits = (num_sms() * 2) / tiles;
@@ -240,8 +282,10 @@ extern "C" int rv_conv2d_wgrad(const void* x, const void* dy, float* dw, int64_t
   const uint32_t b_rows = (uint32_t)(WG_KP + ksize - 1);
   p.tx_bytes = 2u * WG_A_BOX + (uint32_t)p.nboxes_b * b_rows * 128u;
   p.stage_bytes = 2u * WG_A_BOX + (uint32_t)p.nboxes_b * WG_B_BOX;
-  p.stages = (int)((200u * 1024u) / p.stage_bytes);
+  p.stages = (int)((200u * 1024u - (fuse_bias ? WG_A_BOX : 0u)) / p.stage_bytes);
   if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
+  p.dbias = fuse_bias ? dbias : nullptr;
+  p.ones_off = (uint32_t)p.stages * p.stage_bytes;
   CUtensorMap mdy, mx;
   {
     cuuint64_t dims[4] = {(cuuint64_t)cout, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
@@ -255,7 +299,7 @@ extern "C" int rv_conv2d_wgrad(const void* x, const void* dy, float* dw, int64_t
     cuuint32_t box[4] = {64, b_rows, 1, 1};
     if (int rc = tc_encode_map(&mx, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   }
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + (fuse_bias ? WG_A_BOX : 0u) + 1024;
   {
     std::lock_guard<std::mutex> lk(g_wg_mu);
     int dev = 0;
@@ -270,7 +314,7 @@ extern "C" int rv_conv2d_wgrad(const void* x, const void* dy, float* dw, int64_t
     conv_wgrad_kernel<<<tiles * p.splits, WG_THREADS, smem, st>>>(mdy, mx, p);
     RV_LAUNCH_CHECK();
   }
-  if (dbias) {
+  if (dbias && !fuse_bias) {
     const int64_t pixels = (int64_t)n * h * w;
     LaunchScope scope(CAT_NORM, st, (double)pixels * cout * 2.0);
     RV_CHECK_ARG(cout <= 8192, "conv2d_wgrad: bias gradient supports up to 8192 output channels");
