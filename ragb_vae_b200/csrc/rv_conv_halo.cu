@@ -34,7 +34,8 @@
 
 namespace rv {
 
-constexpr int HL_RING = 6;
+constexpr int HL_RING = 6;         // input-row slots; 5 for Cin = 128 (two 64-channel parts per row: six would not fit)
+constexpr int hl_ring_slots(int nk128) { return nk128 >= 2 ? 5 : HL_RING; }
 constexpr int HL_BRING = 3;       // weight-tap ring slots of the single-CTA form
 constexpr int HL_BRING_MAX = 8;   // CTA pairs hold half a tap per slot: the same bytes give a deeper ring
 constexpr int HL_EPI_WARPS = 8;
@@ -97,6 +98,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a128, const __grid_cons
   // exchange through a slot meet at the row's named barrier, and meet again (other row) before either reuses the slot.
   __shared__ float s_ss[2][2][128];
 
+  // A tile keeps four input rows live (y-1 .. y+2) and frees two when it completes.  With six slots both rows of the next tile
+  // prefetch during the current one; with five (Cin = 128) the second one loads right after the free -- it is needed only by
+  // the last third of output row 1's taps, ~2 us into a 5.8 us tile.
+  constexpr uint32_t RING = (uint32_t)hl_ring_slots(NK128);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -109,7 +114,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a128, const __grid_cons
   const int total_units = PAIR ? (p.total_strips >> 1) : p.total_strips;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < HL_RING; ++s) {
+    for (int s = 0; s < (int)RING; ++s) {
       mbar_init(smem_u32(&bar_rowfull[s]), 1);
       mbar_init(smem_u32(&bar_rowempty[s]), 2);  // released by both MMA issuers
     }
@@ -164,7 +169,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a128, const __grid_cons
     for (int u = unit0; u < total_units; u += unit_step) {
       const StripCoord c = decode_strip<PAIR>(p, PAIR ? 2 * u + (int)rank : u);
       for (int y = c.ys - 1; y <= c.ys + c.rows; ++y) {
-        const uint32_t slot = g % HL_RING, par = (g / HL_RING) & 1u;
+        const uint32_t slot = g % RING, par = (g / RING) & 1u;
         mbar_wait(rowempty0 + 8u * slot, par ^ 1u);
         if (elect_one()) {
           const uint32_t dst = ring + slot * p.row_slot_bytes;
@@ -252,9 +257,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a128, const __grid_cons
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint32_t g = g0 + 2u * j + i;
-          rslot[i] = g % HL_RING;
+          rslot[i] = g % RING;
           a_lo[i] = ((ring + rslot[i] * p.row_slot_bytes) & 0x3FFFFu) >> 4;
-          if ((j == 0 || i >= 2) && i >= my_r && i <= my_r + 2) mbar_wait(rowfull0 + 8u * rslot[i], (g / HL_RING) & 1u);
+          if ((j == 0 || i >= 2) && i >= my_r && i <= my_r + 2) mbar_wait(rowfull0 + 8u * rslot[i], (g / RING) & 1u);
         }
         tc_fence_after();
         // the three input rows this issuer's output row reads (static indices: no local-memory array)
@@ -372,6 +377,15 @@ bool epi_fast_ok(const EpiParams& e, const rv_conv_desc* d, const float* bias, c
 static std::mutex g_halo_mu;
 static bool g_halo_attr[64] = {false};
 
+// CTA pairs (cta_group::2): the weight tap splits into two halves of whole 8-row swizzle groups and the strips pair up whenever
+// the image x column-block count is even.  (The pair form lost to the single-CTA one as long as the peer's accumulator release
+// was a cluster-scope RELEASE arrive -- every epilogue warp drained its global loads / stores before each arrive; with the plain
+// arrive it is 11-14 % faster on the 96-channel 1024^2 layers: DESIGN.md 4, item 13.)
+static bool halo_pair_ok(const rv_conv_desc* d, int bn) {
+  static const bool want_pair = getenv("RGBAVAE_HALO_NO_PAIR") == nullptr;
+  return want_pair && bn % 32 == 0 && ((d->n * ((d->w + 127) / 128)) % 2 == 0);
+}
+
 // Can this convolution run on the halo kernel?  (3x3 stride-1, Cout <= 128, operands fit the rings.)
 bool halo_eligible(const rv_conv_desc* d, const EpiParams& e) {
   if (d->ksize != 3 || d->stride != 1 || d->upsample || d->pad_lo != 1 || d->taps_1d) return false;
@@ -380,8 +394,11 @@ bool halo_eligible(const rv_conv_desc* d, const EpiParams& e) {
   if (d->bias_mode == 2 || d->w < 64 || d->h < 2) return false;
   const int nk128 = d->cin / 64, has64 = (d->cin % 64) ? 1 : 0;
   const uint32_t row_slot = nk128 * HL_R128_BYTES + has64 * HL_R64_BYTES;
-  const uint32_t b_slot = ((uint32_t)((d->cout + 15) / 16 * 16) * (uint32_t)d->cin * 2u + 1023u) & ~1023u;
-  return ((HL_RING * row_slot + 1023u) & ~1023u) + HL_BRING * b_slot + 1024u <= HL_SMEM_MAX;
+  const int bn = (d->cout + 15) / 16 * 16;
+  // the CTA-pair form holds half a weight tap per slot (what makes Cin = 128 fit at all)
+  const uint32_t rows_cta = halo_pair_ok(d, bn) ? (uint32_t)bn / 2u : (uint32_t)bn;
+  const uint32_t b_slot = (rows_cta * (uint32_t)d->cin * 2u + 1023u) & ~1023u;
+  return (((uint32_t)hl_ring_slots(nk128) * row_slot + 1023u) & ~1023u) + HL_BRING * b_slot + 1024u <= HL_SMEM_MAX;
 }
 
 int launch_halo(const rv_conv_desc* d, const void* x, const void* w, int64_t w_ld, const float* bias, const void* residual,
@@ -399,12 +416,7 @@ int launch_halo(const rv_conv_desc* d, const void* x, const void* w, int64_t w_l
   p.r64_off = p.nk128 * HL_R128_BYTES;
   p.row_tx_bytes = (uint32_t)HL_PIX * (uint32_t)(p.nk128 * 128 + p.has64 * 64);
   p.col_blocks = (d->w + 127) / 128;
-  // CTA pairs (cta_group::2): the weight tap splits into two halves of whole 8-row swizzle groups and the strips pair up
-  // whenever the image x column-block count is even.  (The pair form lost to the single-CTA one as long as the peer's
-  // accumulator release was a cluster-scope RELEASE arrive -- every epilogue warp drained its global loads / stores before
-  // each arrive; with the plain arrive it is 11-14 % faster on the 96-channel 1024^2 layers: DESIGN.md 4, item 13.)
-  static const bool want_pair = getenv("RGBAVAE_HALO_NO_PAIR") == nullptr;
-  const bool pair = want_pair && p.bn % 32 == 0 && ((d->n * p.col_blocks) % 2 == 0);
+  const bool pair = halo_pair_ok(d, p.bn);
   const uint32_t bn_cta = pair ? (uint32_t)p.bn / 2u : (uint32_t)p.bn;
   p.b64_off = (uint32_t)p.nk128 * bn_cta * 128u;
   p.b_tx_bytes = bn_cta * (uint32_t)d->cin * 2u;  // per CTA; full box bytes (rows past cout are zero-filled)
@@ -412,7 +424,7 @@ int launch_halo(const rv_conv_desc* d, const void* x, const void* w, int64_t w_l
   p.bring_slots = HL_BRING;
   fill_epi(&p.e, d, bias, residual, y, nf);
   p.e.fast = epi_fast_ok(p.e, d, bias, nf, p.bn) ? 1 : 0;
-  p.bring_off = (HL_RING * p.row_slot_bytes + 1023u) & ~1023u;
+  p.bring_off = ((uint32_t)hl_ring_slots(p.nk128) * p.row_slot_bytes + 1023u) & ~1023u;
   if (pair) {  // half-tap slots: the single-CTA ring's bytes (and the rest of the budget) give a deeper weight ring
     p.bring_slots = (int)((HL_SMEM_MAX - 1024u - p.bring_off) / p.b_slot_bytes);
     if (p.bring_slots > HL_BRING_MAX) p.bring_slots = HL_BRING_MAX;
