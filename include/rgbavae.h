@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 21
+#define RV_ABI_VERSION 22
 #define RV_PROF_CATEGORIES 10
 
 int rv_abi_version(void);
@@ -141,6 +141,12 @@ int rv_softmax_rows(const float* s, void* p, int64_t rows, int64_t cols, int64_t
  * tokens % 128 == 0. */
 int rv_attention(const void* q, const void* k, int64_t ld_qk, const void* vt, void* out, int64_t ld_out,
                  int n_img, int tokens, int d, void* stream);
+/* rv_attention that also leaves, per query row, the base-2 log-sum-exp of its scaled scores in lse (fp32
+ * [n_img*tokens]): softmax(QK^T/sqrt(d))[i][j] = exp2(q_i.k_j * log2(e)/sqrt(d) - lse[i]).  The training step keeps it so
+ * that the backward of the attention block (loss.backward() through scaled_dot_product_attention,
+ * src/training/rgba_vae_stage.py:516) recomputes probabilities without a second softmax pass. */
+int rv_attention_lse(const void* q, const void* k, int64_t ld_qk, const void* vt, void* out, int64_t ld_out, float* lse,
+                     int n_img, int tokens, int d, void* stream);
 
 /* ---- layout plumbing at the NCHW boundary ----------------------------------------------- */
 /* y[n][hw][c_pad] = x[n][c][hw]*scale+shift (extra channels zero). */
@@ -267,6 +273,19 @@ int rv_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream);
  * dp fp32 [rows][cols]. */
 int rv_softmax_bwd(const void* p, const float* dp, void* ds, void* ds_t, int64_t rows, int64_t cols, int64_t ld_t,
                    int64_t row0, float scale, void* stream);
+/* The two score-matrix GEMMs of the attention backward with their elementwise step fused into the tensor-core
+ * epilogue (rv_conv2d_tc run as a plain GEMM y[row][col] = sum_k x[row][k] w[col][k], d = a 1x1 descriptor with
+ * n = h = 1, w = rows; bf16 output), so that fp32 scores never reach HBM:
+ *   mode 1: y = exp2(alpha * acc - rowstat[row])     P from Q K^T with alpha = log2(e)/sqrt(d), rowstat = rv_attention_lse's lse
+ *   mode 2: y = mul_in * (alpha * acc - rowstat[row])  dS from dO V^T with alpha = 1/sqrt(d), mul_in = P (bf16, pitch
+ *           y_cstride), rowstat = rv_rowdot(dO, O) / sqrt(d)
+ * mul_in must be NULL in mode 1. */
+int rv_gemm_rowstat(const rv_conv_desc* d, const void* x, const void* w, int64_t w_ld, const float* rowstat, int mode,
+                    const void* mul_in, void* y, void* stream);
+/* out[row] = scale * sum_c a[row][c] * b[row][c] for bf16 matrices of `cols` (% 8 == 0) columns and row pitches ld_a, ld_b:
+ * the delta = rowsum(dO * O) = rowsum(dP * P) term of the softmax backward. */
+int rv_rowdot(const void* a, const void* b, int64_t rows, int cols, int64_t ld_a, int64_t ld_b, float scale, float* out,
+              void* stream);
 /* *out += sum(g^2) over a flat fp32 gradient buffer (accelerator.clip_grad_norm_, rgba_vae_stage.py:520-521).
  * Deterministic (fixed partition and summation order, fp64 partials in `scratch`, a device buffer of
  * rv_grad_sqnorm_scratch_bytes() bytes): data-parallel replicas get bit-identical clip factors. */

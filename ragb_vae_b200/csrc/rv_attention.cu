@@ -49,6 +49,7 @@ struct FaParams {
   int ld_out;          // row pitch of O in elements
   float scale_log2;    // 1/sqrt(d) * log2(e)
   __nv_bfloat16* out;  // [n_img*tokens][ld_out]
+  float* lse;          // optional [n_img*tokens]: log2-domain log-sum-exp of the scaled scores, P = exp2(s * scale_log2 - lse)
 };
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -340,6 +341,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #pragma unroll
       for (int pp = 0; pp < FA_NSPLIT; ++pp) lt += s_xsum[pp][row];
       const float inv = 1.0f / lt;
+      if (p.lse && part == 0 && pass == 0) p.lse[(int64_t)img * p.tokens + q0 + row] = m_used + log2f(lt);
       __nv_bfloat16* orow = p.out + ((int64_t)img * p.tokens + q0 + row) * p.ld_out + pass * OPARTS * 128 + part * ocols;
       for (int c = 0; c < ocols / 32; ++c) {
         uint32_t o[32];
@@ -377,6 +379,11 @@ static bool g_fa_attr[64] = {false};
 
 extern "C" int rv_attention(const void* q, const void* k, int64_t ld_qk, const void* vt, void* out, int64_t ld_out, int n_img,
                             int tokens, int d, void* stream) {
+  return rv_attention_lse(q, k, ld_qk, vt, out, ld_out, nullptr, n_img, tokens, d, stream);
+}
+
+extern "C" int rv_attention_lse(const void* q, const void* k, int64_t ld_qk, const void* vt, void* out, int64_t ld_out, float* lse,
+                                int n_img, int tokens, int d, void* stream) {
   using namespace rv;
   if (int rc = tc_ensure_init()) return rc;
   RV_CHECK_ARG(q && k && vt && out && n_img > 0 && tokens > 0, "attention: bad argument");
@@ -420,6 +427,7 @@ extern "C" int rv_attention(const void* q, const void* k, int64_t ld_qk, const v
   p.ld_out = (int)ld_out;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
   p.out = (__nv_bfloat16*)out;
+  p.lse = lse;
   const int grid = n_img * (tokens / FA_BQ);
   LaunchScope scope(CAT_ATTN, st, 4.0 * (double)n_img * tokens * tokens * d);
   if (d == 384) flash_attn_kernel<6, 3, 1, 5><<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, p);

@@ -567,6 +567,8 @@ void fill_epi(EpiParams* e, const rv_conv_desc* d, const float* bias, const void
   e->y_act = nf ? (__nv_bfloat16*)nf->y_act : nullptr;
   e->norm_silu = nf ? nf->silu : 0;
   e->fast = 0;  // decided by the launcher once the N tiling is known
+  e->rowstat = nullptr;
+  e->rowstat_mode = 0;
   e->vec_ok = (d->y_cstride % 8 == 0) && (!y || (uintptr_t)y % 16 == 0) && (!residual || (uintptr_t)residual % 16 == 0) &&
               (!nf || (uintptr_t)nf->y_act % 16 == 0);
 }
@@ -585,7 +587,7 @@ int launch_halo(const rv_conv_desc* d, const void* x, const void* w, int64_t w_l
 
 static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_t w_ld, const float* bias,
                      const void* residual, void* y, cudaStream_t st, int phase /* -1: not upsample */,
-                     const NormFuse* nf = nullptr) {
+                     const NormFuse* nf = nullptr, const RowStat* rs = nullptr) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.n_img = d->n;
@@ -648,6 +650,11 @@ static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_
   RV_CHECK_ARG(!nf || p.n_tiles == 1, "conv_tc: fused norm needs all %d output channels in one tile (<= 256)", d->cout);
   fill_epi(&p.e, d, bias, residual, y, nf);
   p.e.fast = epi_fast_ok(p.e, d, bias, nf, p.bn * p.n_tiles);
+  if (rs) {  // per-row statistic: generic epilogue only
+    p.e.rowstat = rs->stat;
+    p.e.rowstat_mode = rs->mode;
+    p.e.fast = 0;
+  }
   RV_CHECK_ARG(!nf || p.e.fast, "conv_tc: fused norm needs cout %% 16 == 0, aligned NHWC bf16 tensors, per-channel bias, no affine");
   // CTA pairs (cta_group::2) whenever the B tile splits into two swizzle-aligned halves
   static const bool no_pair = getenv("RGBAVAE_DISABLE_PAIR") != nullptr;
@@ -743,7 +750,7 @@ extern "C" {
 int rv_init(void) { return rv::tc_ensure_init(); }
 
 static int conv2d_tc_impl(const rv_conv_desc* d, const void* x, const void* w_packed, int64_t w_ld, const float* bias,
-                          const void* residual, void* y, void* stream, const rv::NormFuse* nf) {
+                          const void* residual, void* y, void* stream, const rv::NormFuse* nf, const rv::RowStat* rs = nullptr) {
   if (int rc = rv::check_conv_desc(d)) return rc;
   if (int rc = rv::tc_ensure_init()) return rc;
   RV_CHECK_ARG(x && w_packed && (y || nf), "conv_tc: null tensor");
@@ -759,6 +766,12 @@ static int conv2d_tc_impl(const rv_conv_desc* d, const void* x, const void* w_pa
   RV_CHECK_ARG(!nf || (nf->gamma_scaled && nf->y_act && !d->y_nchw && d->y_dtype == RV_BF16),
                "conv_tc: fused norm needs gamma, y_act and an NHWC bf16 layout");
   cudaStream_t st = (cudaStream_t)stream;
+  if (rs) {
+    RV_CHECK_ARG(d->ksize == 1 && d->stride == 1 && !d->upsample && !nf && !d->y_nchw, "gemm_rowstat: plain GEMMs (1x1, NHWC) only");
+    RV_CHECK_ARG(rs->stat && (rs->mode == 1 || rs->mode == 2), "gemm_rowstat: mode must be 1 (exp2) or 2 (multiply) with a statistic");
+    RV_CHECK_ARG((rs->mode == 2) == (residual != nullptr), "gemm_rowstat: mode 2 needs the multiplicand, mode 1 takes none");
+    return rv::launch_tc(d, x, w_packed, w_ld, bias, residual, y, st, -1, nullptr, rs);
+  }
   if (d->upsample) {
     for (int phase = 0; phase < 4; ++phase)
       if (int rc = rv::launch_tc(d, x, w_packed, w_ld, bias, residual, y, st, phase, nf)) return rc;
@@ -784,6 +797,12 @@ int rv_conv2d_tc_norm(const rv_conv_desc* d, const void* x, const void* w_packed
                       const void* residual, void* y, void* y_act, const float* gamma_scaled, int apply_silu, void* stream) {
   rv::NormFuse nf{gamma_scaled, y_act, apply_silu};
   return conv2d_tc_impl(d, x, w_packed, w_ld, bias, residual, y, stream, &nf);
+}
+
+int rv_gemm_rowstat(const rv_conv_desc* d, const void* x, const void* w, int64_t w_ld, const float* rowstat, int mode,
+                    const void* mul_in, void* y, void* stream) {
+  rv::RowStat rs{rowstat, mode};
+  return conv2d_tc_impl(d, x, w, w_ld, nullptr, mul_in, y, stream, nullptr, &rs);
 }
 
 int rv_pack_conv_weights(const float* w, int cout, int cin, int ksize, int upsample, void* out_bf16, int64_t* w_ld,

@@ -229,7 +229,24 @@ struct EpiParams {
   __nv_bfloat16* y_act;
   int norm_silu;
   int fast;                  // 1: epilogue_pixel_fast preconditions hold (set by the host)
+  // per-row statistic of a GEMM whose rows are attention queries (generic path only; rv_gemm_rowstat):
+  //   1: y = exp2(alpha * acc - rowstat[row])              probabilities from the forward's log-sum-exp
+  //   2: y = residual * (alpha * acc - rowstat[row])       dS = P * (dP - delta) * scale (residual holds P)
+  const float* rowstat;
+  int rowstat_mode;
 };
+
+// optional per-row statistic (host-side description; see EpiParams::rowstat_mode)
+struct RowStat {
+  const float* stat;
+  int mode;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // optional fused RMS-norm second output (host-side description)
 struct NormFuse {
@@ -264,7 +281,29 @@ __device__ __forceinline__ void epi_values(const EpiParams& e, const uint32_t (&
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] += b;
   }
-  if (e.residual) {
+  if (e.rowstat_mode) {
+    const float s = __ldg(e.rowstat + pix);
+    if (e.rowstat_mode == 1) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = ex2_approx(v[j] - s);
+    } else {
+      const __nv_bfloat16* rp = e.residual + pix * e.y_cstride + co0;
+      if (full16) {
+        uint4 a = *reinterpret_cast<const uint4*>(rp);
+        uint4 b = *reinterpret_cast<const uint4*>(rp + 8);
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[2 * j] = __uint_as_float(w[j] << 16) * (v[2 * j] - s);
+          v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u) * (v[2 * j + 1] - s);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (co0 + j < e.cout) v[j] = __bfloat162float(rp[j]) * (v[j] - s);
+      }
+    }
+  } else if (e.residual) {
     const __nv_bfloat16* rp = e.residual + pix * e.y_cstride + co0;
     if (full16) {
       uint4 a = *reinterpret_cast<const uint4*>(rp);

@@ -366,6 +366,29 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* _
   }
 }
 
+// out[row] = scale * <a[row], b[row]> (bf16 rows of `cols` elements): one warp per row, 16-byte loads
+__global__ void __launch_bounds__(256) rowdot_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                                    int64_t rows, int cols, int64_t ld_a, int64_t ld_b, float scale,
+                                                    float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = blockIdx.x * 8ll + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * 8) {
+    const uint4* ar = reinterpret_cast<const uint4*>(a + row * ld_a);
+    const uint4* br = reinterpret_cast<const uint4*>(b + row * ld_b);
+    float acc = 0.f;
+    for (int i = lane; i < cols / 8; i += 32) {
+      const uint4 u = ar[i], v = br[i];
+      const uint32_t uw[4] = {u.x, u.y, u.z, u.w}, vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc = fmaf(__uint_as_float(uw[j] << 16), __uint_as_float(vw[j] << 16), acc);
+        acc = fmaf(__uint_as_float(uw[j] & 0xffff0000u), __uint_as_float(vw[j] & 0xffff0000u), acc);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[row] = acc * scale;
+  }
+}
+
 // dgrad weights straight from the parameter: out[ci][tap'][co] = W[co][ci][taps-1-tap'], zero for co >= cout
 __global__ void __launch_bounds__(256) pack_dgrad_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout,
                                                         int cin, int cout_pad, int taps, int64_t s_co, int64_t s_ci) {
@@ -728,6 +751,21 @@ int rv_softmax_bwd(const void* p, const float* dp, void* ds, void* ds_t, int64_t
   rv::LaunchScope scope(rv::CAT_SOFTMAX, st, (double)rows * cols * 10.0);
   rv::softmax_bwd_kernel<<<(unsigned)rows, 256, 0, st>>>((const __nv_bfloat16*)p, dp, (__nv_bfloat16*)ds, (__nv_bfloat16*)ds_t, cols, ld_t,
                                                          row0, scale);
+  RV_LAUNCH_CHECK();
+  return 0;
+}
+
+int rv_rowdot(const void* a, const void* b, int64_t rows, int cols, int64_t ld_a, int64_t ld_b, float scale, float* out,
+              void* stream) {
+  RV_CHECK_ARG(a && b && out && rows > 0 && cols > 0 && cols % 8 == 0 && ld_a % 8 == 0 && ld_b % 8 == 0 &&
+                   (uintptr_t)a % 16 == 0 && (uintptr_t)b % 16 == 0,
+               "rowdot: bad argument (bf16 rows, 16-byte aligned, cols %% 8 == 0)");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t blocks = (rows + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  rv::LaunchScope scope(rv::CAT_SOFTMAX, st, (double)rows * cols * 4.0);
+  rv::rowdot_kernel<<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, rows, cols, ld_a, ld_b, scale,
+                                                     out);
   RV_LAUNCH_CHECK();
   return 0;
 }

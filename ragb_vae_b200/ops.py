@@ -183,16 +183,52 @@ FUSED_ATTENTION_D = 384            # Qwen-Image mid block
 FUSED_ATTENTION_DIMS = (384, 512)  # + the Flux AutoencoderKL mid block (two output passes inside the kernel)
 
 
-def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, n_img: int, tokens: int) -> torch.Tensor:
+def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, n_img: int, tokens: int, return_lse: bool = False):
     """Fused softmax(Q K^T / sqrt(d)) V.  q, k: bf16 [n_img*tokens, d] row views (may be column slices of one
-    tensor, same row stride); vt: bf16 [n_img, d, tokens].  Returns bf16 [n_img*tokens, d]."""
+    tensor, same row stride); vt: bf16 [n_img, d, tokens].  Returns bf16 [n_img*tokens, d]; with ``return_lse`` also the
+    per-row base-2 log-sum-exp of the scaled scores (fp32 [n_img*tokens]) the attention backward recomputes P from."""
     _need_cuda(q, k, vt)
     d = vt.shape[1]
     if q.stride(0) != k.stride(0) or q.stride(1) != 1 or k.stride(1) != 1 or not vt.is_contiguous():
         raise ValueError("attention: q/k must share a row stride and be unit-stride in d; vt must be contiguous")
     out = torch.empty((n_img * tokens, d), dtype=torch.bfloat16, device=q.device)
+    if return_lse:
+        lse = torch.empty((n_img * tokens,), dtype=torch.float32, device=q.device)
+        check(_lib.load().rv_attention_lse(_ptr(q), _ptr(k), q.stride(0), _ptr(vt), _ptr(out), d, _ptr(lse), n_img, tokens, d,
+                                           _stream(q)), "rv_attention_lse")
+        return out, lse
     check(_lib.load().rv_attention(_ptr(q), _ptr(k), q.stride(0), _ptr(vt), _ptr(out), d, n_img, tokens, d, _stream(q)),
           "rv_attention")
+    return out
+
+
+def gemm_rowstat(x: torch.Tensor, w: torch.Tensor, rowstat: torch.Tensor, mode: int, alpha: float,
+                 mul_in: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bf16 y[rows][cols] from acc = x[rows][k] . w[cols][k]^T with the attention backward's elementwise step in the
+    tensor-core epilogue: mode 1 -> exp2(alpha * acc - rowstat[row]); mode 2 -> mul_in * (alpha * acc - rowstat[row])."""
+    _need_cuda(x, w, rowstat, mul_in, out)
+    rows, k = x.shape
+    cols = w.shape[0]
+    if x.stride(1) != 1 or w.stride(1) != 1 or rowstat.dtype != torch.float32 or rowstat.numel() != rows or not rowstat.is_contiguous():
+        raise ValueError("gemm_rowstat: unit-stride bf16 operands and one fp32 statistic per row")
+    y = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device) if out is None else out
+    if mul_in is not None and (mul_in.shape != y.shape or mul_in.stride(0) != y.stride(0) or mul_in.dtype != torch.bfloat16):
+        raise ValueError("gemm_rowstat: mul_in must have the shape, pitch and dtype of the output")
+    desc = make_desc(1, 1, rows, k, cols, 1, 1, False, x_dtype=RV_BF16, y_dtype=RV_BF16, x_cstride=x.stride(0),
+                     y_cstride=y.stride(0), bias_mode=0, alpha=alpha)
+    check(_lib.load().rv_gemm_rowstat(C.byref(desc), _ptr(x), _ptr(w), w.stride(0), _ptr(rowstat), int(mode), _ptr(mul_in),
+                                      _ptr(y), _stream(x)), "rv_gemm_rowstat")
+    return y
+
+
+def rowdot(a: torch.Tensor, b: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """fp32 [rows]: scale * sum_c a[row][c] * b[row][c] for two bf16 matrices (unit stride in c)."""
+    _need_cuda(a, b)
+    if a.shape != b.shape or a.dim() != 2 or a.stride(1) != 1 or b.stride(1) != 1 or a.dtype != torch.bfloat16 or b.dtype != a.dtype:
+        raise ValueError("rowdot: two bf16 [rows][cols] matrices with unit column stride")
+    out = torch.empty((a.shape[0],), dtype=torch.float32, device=a.device)
+    check(_lib.load().rv_rowdot(_ptr(a), _ptr(b), a.shape[0], a.shape[1], a.stride(0), b.stride(0), float(scale), _ptr(out),
+                                _stream(a)), "rv_rowdot")
     return out
 
 

@@ -200,8 +200,9 @@ class VaeTrainStep:
             for i in range(n):
                 self._gemm(wqkv[2 * c:], xn2[i * t:(i + 1) * t], rows=c, k=c, cols=t, x_ld=c, w_ld=c, y=vt_all[i], y_ld=t,
                            bias=bqkv[2 * c:].contiguous(), bias_mode=2)
-            o = ops.attention(q, k, vt_all, n, t)
+            o, lse = ops.attention(q, k, vt_all, n, t, return_lse=True)
         else:
+            lse = None
             o = torch.empty_like(q)
             vt = torch.empty((c, t), dtype=torch.bfloat16, device=dev)
             q_chunk = self._q_chunk(t)
@@ -221,7 +222,7 @@ class VaeTrainStep:
         self._gemm(o, wo, rows=n * t, k=c, cols=c, x_ld=c, w_ld=c, y=out.view(n * t, c), y_ld=c, bias=bo, bias_mode=1,
                    residual=x.view(n * t, c))
         if tape is not None:
-            tape.append(("attn", attn, (x,) if self.vae.gradient_checkpointing else (x, xn, q, k, v, o, sn)))
+            tape.append(("attn", attn, (x,) if self.vae.gradient_checkpointing else (x, xn, q, k, v, o, sn, lse)))
         return out
 
     @staticmethod
@@ -237,7 +238,7 @@ class VaeTrainStep:
             finally:
                 self.vae.gradient_checkpointing = ckpt
             saved = scratch[0][2]
-        x, xn, q, k, v, o, sn = saved
+        x, xn, q, k, v, o, sn, lse = saved
         n, h, w, c = x.shape
         t = h * w
         dev = x.device
@@ -250,10 +251,18 @@ class VaeTrainStep:
                      dbias_out=self._gview[id(proj.bias)])
         d_o = T.conv_dgrad(as_img(dout2, c), proj.weight.detach().reshape(c, c, 1, 1)).view(n * t, c)
         dqkv = torch.empty((n * t, 3 * c), dtype=torch.bfloat16, device=dev)
-        q_chunk = self._q_chunk(t)
-        s = torch.empty((q_chunk, t), dtype=torch.float32, device=dev)
-        dp = torch.empty((q_chunk, t), dtype=torch.float32, device=dev)
+        # With the forward's log-sum-exp the probabilities come straight out of the QK^T GEMM's epilogue (exp2(s - lse)) and dS
+        # out of the dO V^T GEMM's (P * (dP - delta), delta = rowsum(dO * O)): no fp32 score matrix, no softmax pass.
+        fused = lse is not None
+        q_chunk = max(128, min(t, ((1 << 28) // t) // 128 * 128)) if fused else self._q_chunk(t)
         ds = torch.empty((q_chunk, t), dtype=torch.bfloat16, device=dev)
+        if fused:
+            pbuf = torch.empty((q_chunk, t), dtype=torch.bfloat16, device=dev)
+            delta = ops.rowdot(d_o, o, scale)
+            scale_log2 = scale * 1.4426950408889634
+        else:
+            s = torch.empty((q_chunk, t), dtype=torch.float32, device=dev)
+            dp = torch.empty((q_chunk, t), dtype=torch.float32, device=dev)
         kt = torch.empty((c, t), dtype=torch.bfloat16, device=dev)
         wqkv, bqkv, _, _ = self._attn_weights(attn)
         xn2 = xn.view(n * t, c)
@@ -268,12 +277,16 @@ class VaeTrainStep:
             for r0 in range(0, t, q_chunk):
                 rows = min(q_chunk, t - r0)
                 rs = slice(i * t + r0, i * t + r0 + rows)
-                self._gemm(q[rs], k[sl], rows=rows, k=c, cols=t, x_ld=c, w_ld=c, y=s[:rows], y_ld=t, alpha=scale)
-                p = ops.softmax_rows(s[:rows], torch.bfloat16)
-                # dP = dO V^T
-                self._gemm(d_o[rs], v[sl], rows=rows, k=c, cols=t, x_ld=c, w_ld=c, y=dp[:rows], y_ld=t)
-                T.check(_lib.load().rv_softmax_bwd(ops._ptr(p), ops._ptr(dp), ops._ptr(ds), None, rows, t, t, r0, scale,
-                                                   ops._stream(p)), "rv_softmax_bwd")
+                if fused:
+                    p = ops.gemm_rowstat(q[rs], k[sl], lse[rs], 1, scale_log2, out=pbuf[:rows])
+                    ops.gemm_rowstat(d_o[rs], v[sl], delta[rs], 2, scale, mul_in=p, out=ds[:rows])
+                else:
+                    self._gemm(q[rs], k[sl], rows=rows, k=c, cols=t, x_ld=c, w_ld=c, y=s[:rows], y_ld=t, alpha=scale)
+                    p = ops.softmax_rows(s[:rows], torch.bfloat16)
+                    # dP = dO V^T
+                    self._gemm(d_o[rs], v[sl], rows=rows, k=c, cols=t, x_ld=c, w_ld=c, y=dp[:rows], y_ld=t)
+                    T.check(_lib.load().rv_softmax_bwd(ops._ptr(p), ops._ptr(dp), ops._ptr(ds), None, rows, t, t, r0, scale,
+                                                       ops._stream(p)), "rv_softmax_bwd")
                 # dV += P^T dO ; dK += dS^T Q   (reduction over this block's query rows: wgrad-form GEMMs)
                 T.gemm_tn_accumulate(dv, p, d_o[rs])
                 T.gemm_tn_accumulate(dk, ds[:rows], q[rs])

@@ -50,7 +50,10 @@ wrap(T, "rmsnorm_silu_backward", lambda x, g, dy, *a, **k: (str(tuple(x.shape)),
 wrap(ops, "groupnorm_silu", lambda x, *a, **k: (str(tuple(x.shape)), 0.0, 3.0 * el(x)))
 wrap(T, "groupnorm_silu_backward", lambda x, *a, **k: (str(tuple(x.shape)), 0.0, 5.0 * el(x)))
 wrap(T, "resample2x", lambda x, mode: (f"{tuple(x.shape)} {mode}", 0.0, el(x) * (5.0 if mode != "sum_pool" else 1.25)))
-wrap(ops, "attention", lambda q, k, vt, n, t: (f"n{n} t{t} d{vt.shape[1]}", 4.0 * n * t * t * vt.shape[1], 0.0))
+wrap(ops, "attention", lambda q, k, vt, n, t, **kw: (f"n{n} t{t} d{vt.shape[1]}", 4.0 * n * t * t * vt.shape[1], 0.0))
+wrap(ops, "gemm_rowstat", lambda x, w, st, mode, alpha, **kw: (f"{tuple(x.shape)} x {tuple(w.shape)}^T mode {mode}",
+                                                              2.0 * x.shape[0] * x.shape[1] * w.shape[0], 0.0))
+wrap(ops, "rowdot", lambda a, b, s=1.0: (str(tuple(a.shape)), 0.0, 2.0 * el(a)))
 wrap(ops, "softmax_rows", lambda s, dt: (str(tuple(s.shape)), 0.0, s.numel() * 6.0))
 wrap(T, "gemm_tn_accumulate", lambda out, a, b: (f"{tuple(a.shape)}^T {tuple(b.shape)}", 2.0 * a.shape[0] * a.shape[1] * b.shape[1], 0.0))
 wrap(ops, "nchw_to_nhwc", lambda x, cp, dt, *a: (str(tuple(x.shape)), 0.0, el(x) * 3))

@@ -191,6 +191,42 @@ def test_fused_attention(ops, n_img, tokens, scale_up, d):
     assert rel(out.float().view(n_img, tokens, d), ref) < 1e-2
 
 
+@pytest.mark.parametrize("d", [384, 512])
+@pytest.mark.parametrize("tokens", [256, 1152])
+def test_attention_lse_and_fused_score_gemms(ops, tokens, d):
+    """rv_attention_lse's log-sum-exp, and the two score-matrix GEMMs of the attention backward with their elementwise step
+    in the epilogue (rv_gemm_rowstat): P = exp2(s - lse) equals softmax(QK^T/sqrt(d)), dS = P * (dP - delta) / sqrt(d) with
+    delta = rowdot(dO, O) equals torch autograd's gradient of the scores."""
+    g = torch.Generator().manual_seed(tokens + d)
+    q = torch.randn(tokens, d, generator=g).bfloat16()
+    k = (torch.randn(tokens, d, generator=g) * torch.linspace(0.3, 1.4, tokens).view(-1, 1)).bfloat16()
+    v = torch.randn(tokens, d, generator=g).bfloat16()
+    d_o = torch.randn(tokens, d, generator=g).bfloat16()
+    scale = 1.0 / d ** 0.5
+    s_ref = (q.float() @ k.float().t()) * scale
+    p_ref = torch.softmax(s_ref, -1)
+    o_ref = p_ref @ v.float()
+    qc, kc, vc, doc = q.cuda(), k.cuda(), v.cuda(), d_o.cuda()
+    out, lse = ops.attention(qc, kc, vc.t().contiguous().view(1, d, tokens), 1, tokens, return_lse=True)
+    lse_ref = torch.logsumexp(s_ref, -1) * 1.4426950408889634
+    assert float((lse.cpu() - lse_ref).abs().max()) < 2e-3
+    assert rel(out.float().cpu(), o_ref) < 1e-2
+    p = ops.gemm_rowstat(qc, kc, lse, 1, scale * 1.4426950408889634)
+    assert p.dtype == torch.bfloat16 and rel(p.float().cpu(), p_ref) < 6e-3
+    assert float((p.float().sum(-1) - 1).abs().max()) < 1e-2
+    delta = ops.rowdot(doc, out, scale)
+    delta_ref = (d_o.float() * o_ref).sum(-1) * scale
+    assert float((delta.cpu() - delta_ref).abs().max()) < 2e-2 * float(delta_ref.abs().max()) + 1e-3
+    ds = ops.gemm_rowstat(doc, vc, delta, 2, scale, mul_in=p)
+    dp_ref = d_o.float() @ v.float().t()
+    ds_ref = p_ref * (dp_ref - (dp_ref * p_ref).sum(-1, keepdim=True)) * scale
+    assert rel(ds.float().cpu(), ds_ref) < 2e-2
+    with pytest.raises(Exception):
+        ops.gemm_rowstat(qc, kc, lse, 2, scale)          # mode 2 without its multiplicand
+    with pytest.raises(Exception):
+        ops.gemm_rowstat(qc, kc, lse, 1, scale, mul_in=p)  # mode 1 takes none
+
+
 @pytest.mark.parametrize("shape", [(2, 4, 40, 72), (1, 4, 16, 200), (1, 3, 24, 24)])
 def test_hpack_stem_matches_conv2d(ops, shape):
     """conv_in through the horizontally packed loader + 3 vertical taps == the plain 3x3 conv (incl. image borders)."""
