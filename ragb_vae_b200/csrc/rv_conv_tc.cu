@@ -229,7 +229,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_wait(bar_accf0 + 8u * (uint32_t)acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
-      if (p.e.fast) {
+      if (p.e.fast == 1) {
         if (p.e.residual)
           epilogue_pixel_fast<true>(p.e, sbias, s_gamma, taddr, cb, ce, t.n0, valid, pix, &s_ss[acc][0][0], row, half,
                                     nsplit, 1 + q);
@@ -270,7 +270,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 //   * the peer's epilogue warps release the accumulator on the leader's barrier through a remote mbarrier arrive;
 //   * TMEM is allocated / freed with the cta_group::2 forms; cluster barriers fence set-up and tear-down.
 // ---------------------------------------------------------------------------------------
-template <int KSTEPS>
+// RS: 0, or the row-statistic mode (1 / 2) of rv_gemm_rowstat's lean epilogue -- its own instantiations, so that the 64 registers
+// of prefetched multiplicand never weigh on the convolutions' epilogue
+template <int KSTEPS, int RS = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ TcParams p) {
@@ -428,10 +430,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const bool valid = m_tile < p.m_tiles && ty < p.th && tx < p.tw;
       const int oy = ty * p.osy + p.ooy, ox = tx * p.osx + p.oox;
       const int64_t pix = ((int64_t)t.img * p.e.out_h + oy) * p.e.out_w + ox;
+      RowstatPrefetch pf;
+      if (RS) rowstat_prefetch<RS>(p.e, cb, ce, t.n0, valid, pix, pf);
       mbar_wait(bar_accf0 + 8u * (uint32_t)acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
-      if (p.e.fast) {
+      if (RS) {
+        epilogue_pixel_rowstat<RS ? RS : 1>(p.e, taddr, cb, ce, t.n0, valid, pix, pf);
+      } else if (p.e.fast == 1) {
         if (p.e.residual)
           epilogue_pixel_fast<true>(p.e, sbias, s_gamma, taddr, cb, ce, t.n0, valid, pix, &s_ss[acc][0][0], row, half, nsplit,
                                     1 + q);
@@ -490,6 +496,8 @@ int tc_ensure_init() {
     RV_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 2048)));
     RV_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 2048)));
     RV_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 2048)));
+    RV_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 2048)));
+    RV_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 2048)));
     g_attr_set[dev] = true;
   }
   return 0;
@@ -653,7 +661,11 @@ static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_
   if (rs) {  // per-row statistic: generic epilogue only
     p.e.rowstat = rs->stat;
     p.e.rowstat_mode = rs->mode;
-    p.e.fast = 0;
+    // lean form: whole 32-column steps per epilogue warp, 32-byte aligned bf16 rows, nothing but alpha and the statistic
+    const bool lean = p.e.vec_ok && !d->y_nchw && d->y_dtype == RV_BF16 && d->bias_mode == 0 && d->out_scale == 1.0f &&
+                      d->out_shift == 0.0f && !d->clamp && p.bn % 64 == 0 && p.bn * p.n_tiles == d->cout &&
+                      d->y_cstride % 16 == 0 && (uintptr_t)y % 32 == 0 && (!residual || (uintptr_t)residual % 32 == 0);
+    p.e.fast = lean && p.bk == 64 ? 2 : 0;  // (confirmed below: the lean form lives in the CTA-pair kernel only)
   }
   RV_CHECK_ARG(!nf || p.e.fast, "conv_tc: fused norm needs cout %% 16 == 0, aligned NHWC bf16 tensors, per-channel bias, no affine");
   // CTA pairs (cta_group::2) whenever the B tile splits into two swizzle-aligned halves
@@ -695,11 +707,14 @@ static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   const double flops = 2.0 * (double)d->n * d->oh * d->ow * d->cout * d->cin * d->ksize * (d->taps_1d ? 1 : d->ksize) / (phase >= 0 ? 4.0 : 1.0);
   LaunchScope scope(phase >= 0 ? CAT_CONV_UPS : CAT_CONV_TC, st, flops);
+  if (!pair && p.e.fast == 2) p.e.fast = 0;
   if (pair) {
     const int total_pt = ((p.m_tiles + 1) / 2) * p.n_tiles;
     const int max_pairs = num_sms() / 2;
     const int grid = 2 * (total_pt < max_pairs ? total_pt : max_pairs);
-    if (p.bk == 64) conv_tc2_kernel<4><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+    if (p.e.fast == 2 && p.e.rowstat_mode == 1) conv_tc2_kernel<4, 1><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+    else if (p.e.fast == 2) conv_tc2_kernel<4, 2><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+    else if (p.bk == 64) conv_tc2_kernel<4><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
     else conv_tc2_kernel<2><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
   } else {
     const int total_tiles = p.m_tiles * p.n_tiles;

@@ -228,7 +228,7 @@ struct EpiParams {
   const float* norm_gamma;   // null: no fused norm
   __nv_bfloat16* y_act;
   int norm_silu;
-  int fast;                  // 1: epilogue_pixel_fast preconditions hold (set by the host)
+  int fast;                  // 1: epilogue_pixel_fast preconditions hold, 2: epilogue_pixel_rowstat's (set by the host)
   // per-row statistic of a GEMM whose rows are attention queries (generic path only; rv_gemm_rowstat):
   //   1: y = exp2(alpha * acc - rowstat[row])              probabilities from the forward's log-sum-exp
   //   2: y = residual * (alpha * acc - rowstat[row])       dS = P * (dP - delta) * scale (residual holds P)
@@ -564,6 +564,70 @@ __device__ __forceinline__ void epilogue_pixel_fast(const EpiParams& e, const fl
   const float rinv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
   for (int c0 = cb; c0 < c32; c0 += 32) fast_norm_pass2<32, RES>(e, sbias, sgamma, taddr, c0, n0 + c0, valid, pix, rinv);
   if (c32 < ce) fast_norm_pass2<16, RES>(e, sbias, sgamma, taddr, c32, n0 + c32, valid, pix, rinv);
+}
+
+// Lean epilogue of rv_gemm_rowstat (EpiParams::rowstat_mode; bf16 NHWC output, 32-byte aligned rows, column ranges in
+// multiples of 32, at most 128 columns per warp).  What does not depend on the accumulator -- the row's statistic and, in
+// mode 2, the thread's whole slice of the multiplicand (up to 4 x 64 bytes) -- is fetched BEFORE the warp waits for the
+// tile's MMAs, so its HBM latency hides behind them.
+struct RowstatPrefetch {
+  uint4 res[16];
+  float s;
+};
+
+template <int MODE>
+__device__ __forceinline__ void rowstat_prefetch(const EpiParams& e, int cb, int ce, int n0, bool valid, int64_t pix,
+                                                 RowstatPrefetch& pf) {
+  pf.s = valid ? __ldg(e.rowstat + pix) : 0.f;
+  if (MODE == 2 && valid) {
+    const __nv_bfloat16* rp = e.residual + pix * e.y_cstride + n0 + cb;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (cb + 32 * c < ce) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+          asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(pf.res[4 * c + 2 * q].x), "=r"(pf.res[4 * c + 2 * q].y), "=r"(pf.res[4 * c + 2 * q].z),
+                         "=r"(pf.res[4 * c + 2 * q].w), "=r"(pf.res[4 * c + 2 * q + 1].x), "=r"(pf.res[4 * c + 2 * q + 1].y),
+                         "=r"(pf.res[4 * c + 2 * q + 1].z), "=r"(pf.res[4 * c + 2 * q + 1].w)
+                       : "l"(rp + 32 * c + 16 * q));
+      }
+    }
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void epilogue_pixel_rowstat(const EpiParams& e, uint32_t taddr, int cb, int ce, int n0, bool valid,
+                                                       int64_t pix, const RowstatPrefetch& pf) {
+  const float s = pf.s, alpha = e.alpha;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int c0 = cb + 32 * c;
+    if (c0 < ce) {
+      uint32_t r[32];
+      tmem_ld32(taddr + (uint32_t)c0, r);
+      tmem_ld_wait();
+      if (valid) {
+        float v[32];
+        if (MODE == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = ex2_approx(fmaf(__uint_as_float(r[j]), alpha, -s));
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 u = pf.res[4 * c + q];
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              v[8 * q + 2 * j] = __uint_as_float(w[j] << 16) * fmaf(__uint_as_float(r[8 * q + 2 * j]), alpha, -s);
+              v[8 * q + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u) * fmaf(__uint_as_float(r[8 * q + 2 * j + 1]), alpha, -s);
+            }
+          }
+        }
+        fast_store<32>(reinterpret_cast<__nv_bfloat16*>(e.y) + pix * e.y_cstride + n0 + c0, v);
+      }
+    }
+  }
 }
 
 }  // namespace rv

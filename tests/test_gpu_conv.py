@@ -192,7 +192,7 @@ def test_fused_attention(ops, n_img, tokens, scale_up, d):
 
 
 @pytest.mark.parametrize("d", [384, 512])
-@pytest.mark.parametrize("tokens", [256, 1152])
+@pytest.mark.parametrize("tokens", [256, 640, 1152])  # 640: N tile of 160 columns -> generic epilogue; else the lean one
 def test_attention_lse_and_fused_score_gemms(ops, tokens, d):
     """rv_attention_lse's log-sum-exp, and the two score-matrix GEMMs of the attention backward with their elementwise step
     in the epilogue (rv_gemm_rowstat): P = exp2(s - lse) equals softmax(QK^T/sqrt(d)), dS = P * (dP - delta) / sqrt(d) with
