@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 22
+#define RV_ABI_VERSION 23
 #define RV_PROF_CATEGORIES 10
 
 int rv_abi_version(void);
@@ -147,6 +147,14 @@ int rv_attention(const void* q, const void* k, int64_t ld_qk, const void* vt, vo
  * src/training/rgba_vae_stage.py:516) recomputes probabilities without a second softmax pass. */
 int rv_attention_lse(const void* q, const void* k, int64_t ld_qk, const void* vt, void* out, int64_t ld_out, float* lse,
                      int n_img, int tokens, int d, void* stream);
+/* rv_attention_lse with a device workspace of rv_attention_workspace_bytes(tokens, d) bytes (0: this shape uses none; d = 512
+ * does).  With it the d = 512 kernel keeps pass 1's probability tiles there and its second output pass streams them back
+ * instead of recomputing S and the softmax (64 instead of 96 MMAs per key block).  The first 1024 bytes (slot ownership
+ * flags) must be zero before the first call and are zero again whenever no call is in flight; the rest needs no
+ * initialisation.  One workspace serves one stream at a time.  workspace == NULL: same as rv_attention_lse. */
+int64_t rv_attention_workspace_bytes(int tokens, int d);
+int rv_attention_ws(const void* q, const void* k, int64_t ld_qk, const void* vt, void* out, int64_t ld_out, float* lse,
+                    void* workspace, int64_t workspace_bytes, int n_img, int tokens, int d, void* stream);
 
 /* ---- layout plumbing at the NCHW boundary ----------------------------------------------- */
 /* y[n][hw][c_pad] = x[n][c][hw]*scale+shift (extra channels zero). */

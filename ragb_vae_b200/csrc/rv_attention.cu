@@ -20,9 +20,12 @@
 // TMEM: O 384 fp32 columns + S 128 = 512.  Shared memory: Q 96 KB + ring 80 KB + P 32 KB.
 //
 // d = 512 (diffusers Attention of the Flux AutoencoderKL mid block): O alone would fill TMEM, so the key loop runs TWICE per
-// query block, each pass producing 256 of the 512 output columns (S is recomputed: 1.5x the MMA work of an ideal kernel, still
-// no score traffic -- the unfused path moves ~100 GB for one 65 536-token image).  Q (8 chunks, 128 KB) stays resident, the
-// ring shrinks to 3 slots.
+// query block, each pass producing 256 of the 512 output columns.  Q (8 chunks, 128 KB) stays resident, the ring shrinks to
+// 3 slots.  Without a workspace the second pass recomputes S and the softmax (1.5x the MMA work of an ideal kernel).  With one
+// (rv_attention_ws, SPILL = true) pass 1 also leaves every probability tile -- the 32 KB shared-memory image the PV MMA reads,
+// plus the running maxima -- in a per-CTA slot of the workspace, and pass 2 is a pure P V stream: the tiles come back with
+// cp.async.bulk through a 13-slot ring laid over the Q, ring and P regions, the O rescales of pass 1 are replayed at the (rare)
+// blocks where a row's maximum moved, no S, no softmax: 64 instead of 96 MMAs per key block.
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -50,7 +53,21 @@ struct FaParams {
   float scale_log2;    // 1/sqrt(d) * log2(e)
   __nv_bfloat16* out;  // [n_img*tokens][ld_out]
   float* lse;          // optional [n_img*tokens]: log2-domain log-sum-exp of the scaled scores, P = exp2(s * scale_log2 - lse)
+  uint8_t* ws;         // SPILL: ws_slots slots of (tokens / 128) * FA_WS_BLOCK bytes
+  int* ws_flags;       // SPILL: one int per slot, 0 = free (a CTA owns a slot from its first to its last instruction)
+  int ws_slots;
 };
+
+constexpr int FA_RING2 = 13;                 // pass-2 ring of the SPILL form: Q (8) + ring (3) + P (2) slots of 16 KB
+constexpr uint32_t FA_WS_BLOCK = 32768 + 512;  // workspace per key block: the P tile's shared-memory image + m_used[128]
+constexpr int FA_WS_SLOTS = 160;             // > 148 co-resident CTAs (one per SM: 209 KB of shared memory each)
+constexpr int FA_MAX_NB = 1024;              // SPILL: key blocks per image (rescale flags live in shared memory)
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -80,7 +97,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 // 2: 933 vs 958 TFLOP/s; the kernel is paced by its softmax warps, not by operand reads.  Removed.)
 // DCH: 64-wide chunks of d; OPARTS: N = 128 parts of O per pass; NPASS: key-loop passes; RING: K / V^T ring slots
 // (6, 3, 1, 5 for d = 384; 8, 2, 2, 3 for d = 512) -- compile-time so that the d = 384 loops stay fully unrolled
-template <int DCH, int OPARTS, int NPASS, int RING>
+template <int DCH, int OPARTS, int NPASS, int RING, bool SPILL = false>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                   const __grid_constant__ CUtensorMap map_vt, const __grid_constant__ FaParams p) {
@@ -93,6 +110,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_xmax[2][FA_NSPLIT][128];  // [block parity][column part][row]
   __shared__ float s_xsum[FA_NSPLIT][128];
+  // SPILL form only
+  __shared__ __align__(8) uint64_t bar_full2[SPILL ? FA_RING2 : 1], bar_empty2[SPILL ? FA_RING2 : 1], bar_p1done, bar_go, bar_resc,
+      bar_p2done;
+  __shared__ uint8_t s_resc[SPILL ? FA_MAX_NB : 1];  // block j of pass 1 rescaled O for some row
+  __shared__ int s_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -117,8 +139,23 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     mbar_init(smem_u32(&bar_sempty), FA_SM_WARPS);
     mbar_init(smem_u32(&bar_pfull), FA_SM_WARPS);
     mbar_init(smem_u32(&bar_pvdone), 1);
+    if (SPILL) {
+      for (int s = 0; s < FA_RING2; ++s) {
+        mbar_init(smem_u32(&bar_full2[s]), 1);
+        mbar_init(smem_u32(&bar_empty2[s]), 1);
+      }
+      mbar_init(smem_u32(&bar_p1done), FA_SM_WARPS);
+      mbar_init(smem_u32(&bar_go), 1);
+      mbar_init(smem_u32(&bar_resc), FA_SM_WARPS);
+      mbar_init(smem_u32(&bar_p2done), 1);
+      int sl = (int)(blockIdx.x % (unsigned)p.ws_slots);
+      while (atomicCAS(p.ws_flags + sl, 0, 1) != 0) sl = sl + 1 == p.ws_slots ? 0 : sl + 1;
+      s_slot = sl;
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (SPILL)
+    for (int i = threadIdx.x; i < FA_MAX_NB; i += FA_THREADS) s_resc[i] = 0;
   if (warp == 1) {
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u)
@@ -132,6 +169,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const uint32_t fullk0 = smem_u32(&bar_fullk[0]), fullv0 = smem_u32(&bar_fullv[0]), empty0 = smem_u32(&bar_empty[0]);
   const uint32_t sfull = smem_u32(&bar_sfull), sempty = smem_u32(&bar_sempty), pfull = smem_u32(&bar_pfull),
                  pvdone = smem_u32(&bar_pvdone), qbar = smem_u32(&bar_q);
+  const uint32_t full20 = smem_u32(&bar_full2[0]), empty20 = smem_u32(&bar_empty2[0]), p1done = smem_u32(&bar_p1done),
+                 gobar = smem_u32(&bar_go), rescbar = smem_u32(&bar_resc), p2done = smem_u32(&bar_p2done);
+  constexpr int NP1 = SPILL ? 1 : NPASS;  // passes that compute S (the SPILL form's second pass replays stored P tiles)
+  uint8_t* const ws = SPILL ? p.ws + (size_t)s_slot * (size_t)nb * FA_WS_BLOCK : nullptr;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -142,7 +183,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     __syncwarp();
     uint32_t slot = 0, par = 0;
     // consumption order per pass: K(0), K(1), V(0), K(2), V(1), ..., K(nb-1), V(nb-2), V(nb-1)
-    for (int pass = 0; pass < NPASS; ++pass)
+    for (int pass = 0; pass < NP1; ++pass)
     for (int step = 0; step <= nb; ++step) {
       if (step < nb) {
         for (int c = 0; c < DCH; ++c) {
@@ -170,6 +211,31 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           }
       }
     }
+    if (SPILL) {
+      // pass 2: per key block and 64-key half the stored P chunk, then the two V^T chunks of output columns [256, 512)
+      mbar_wait(p1done, 0);  // every P tile is in the workspace (and fenced towards the async proxy); Q, ring and P are free
+      uint32_t s2 = 0, par2 = 0;
+      auto advance2 = [&]() { if (++s2 == (uint32_t)FA_RING2) { s2 = 0; par2 ^= 1u; } };
+      for (int j = 0; j < nb; ++j)
+        for (int kc = 0; kc < 2; ++kc) {
+          mbar_wait(empty20 + 8u * s2, par2 ^ 1u);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(full20 + 8u * s2, FA_SLOT);
+            bulk_load_1d(base + s2 * FA_SLOT, ws + (size_t)j * FA_WS_BLOCK + (size_t)kc * FA_SLOT, FA_SLOT, full20 + 8u * s2);
+          }
+          __syncwarp();
+          advance2();
+          for (int h = 0; h < OPARTS; ++h) {
+            mbar_wait(empty20 + 8u * s2, par2 ^ 1u);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(full20 + 8u * s2, FA_SLOT);
+              tma_load_3d(base + s2 * FA_SLOT, &map_vt, full20 + 8u * s2, j * FA_BK + kc * 64, OPARTS * 128 + h * 128, img);
+            }
+            __syncwarp();
+            advance2();
+          }
+        }
+    }
   } else if (warp == 1 || warp == FA_PV_WARP) {
     // ------------------------------ MMA issuers ------------------------------
     // Both walk the producer's push sequence (per pass: K(0) | K(1) V(0) | K(2) V(1) | ... | V(nb-1)); each consumes its own
@@ -189,7 +255,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     {
       if (is_qk) mbar_wait(qbar, 0);
       int g = 0;  // key blocks issued so far over all passes: every per-block barrier flips once per block
-      for (int pass = 0; pass < NPASS; ++pass)
+      for (int pass = 0; pass < NP1; ++pass)
         for (int step = 0; step <= nb; ++step) {
           if (step < nb) {
             if (is_qk) {
@@ -250,6 +316,46 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             }
           }
         }
+      if (SPILL && !is_qk) {
+        // pass 2: O[:, 256:512) += P(j) V(j)[:, 256:512) from the stored tiles, into TMEM columns [256, 512)
+        mbar_wait(p1done, 0);  // also orders the s_resc flags written in pass 1
+        tc_fence_after();
+        const uint32_t base_lo = (base & 0x3FFFFu) >> 4;
+        uint32_t s2 = 0, par2 = 0, rpar = 0;
+        auto advance2 = [&]() { if (++s2 == (uint32_t)FA_RING2) { s2 = 0; par2 ^= 1u; } };
+        for (int j = 0; j < nb; ++j) {
+          if (s_resc[j]) {  // replay of a pass-1 rescale: the softmax warps scale O once PV(j-1) has completed
+            if (elect_one()) commit(gobar);
+            __syncwarp();
+            mbar_wait(rescbar, rpar);
+            rpar ^= 1u;
+            tc_fence_after();
+          }
+          for (int kc = 0; kc < 2; ++kc) {
+            const uint32_t ps = s2;
+            mbar_wait(full20 + 8u * ps, par2);
+            advance2();
+            for (int h = 0; h < OPARTS; ++h) {
+              mbar_wait(full20 + 8u * s2, par2);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t ad = hi | (uint64_t)(base_lo + ps * (FA_SLOT >> 4));
+                const uint64_t bd = hi | (uint64_t)(base_lo + s2 * (FA_SLOT >> 4));
+                const uint32_t d_tmem = tmem_base + (uint32_t)(OPARTS + h) * 128u;
+                mma(d_tmem, ad, bd, (j == 0 && kc == 0) ? 0u : 1u);
+                mma(d_tmem, ad + 2u, bd + 2u, 1u);
+                mma(d_tmem, ad + 4u, bd + 4u, 1u);
+                mma(d_tmem, ad + 6u, bd + 6u, 1u);
+                commit(empty20 + 8u * s2);
+                if (h == OPARTS - 1) commit(empty20 + 8u * ps);
+                if (j == nb - 1 && kc == 1 && h == OPARTS - 1) commit(p2done);
+              }
+              __syncwarp();
+              advance2();
+            }
+          }
+        }
+      }
     }
   } else if (warp >= 2 && warp < FA_PV_WARP) {
     // ------------------------------ softmax / correction / output ------------------------------
@@ -263,7 +369,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const uint32_t p_row = p_smem + (uint32_t)(part >> 1) * 16384u + (uint32_t)row * 128u;
     const uint32_t u0 = (uint32_t)(part & 1) * 4u;
     const uint32_t sw = (uint32_t)(row & 7);
-    for (int pass = 0, jj = 0; pass < NPASS; ++pass) {
+    for (int pass = 0, jj = 0; pass < NP1; ++pass) {
       float m_used = -INFINITY, l = 0.f;
       for (int j = 0; j < nb; ++j, ++jj) {
         mbar_wait(sfull, (uint32_t)(jj & 1));
@@ -303,6 +409,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           sum += a + b;
         }
         l += sum;
+        if (SPILL) {
+          // the tile's shared-memory image (same swizzled offsets) and the maximum it is relative to go to the workspace
+          uint8_t* wt = ws + (size_t)j * FA_WS_BLOCK;
+          uint8_t* wrow = wt + (size_t)(part >> 1) * 16384u + (size_t)row * 128u;
+#pragma unroll
+          for (int u = 0; u < FA_KCOLS / 8; ++u)
+            *reinterpret_cast<uint4*>(wrow + (((u0 + (uint32_t)u) ^ sw) << 4)) =
+                make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+          if (part == 0) reinterpret_cast<float*>(wt + 32768)[row] = m_used;
+          if (need) s_resc[j] = 1;
+        }
         // the previous PV must be complete before P is overwritten or O is rescaled (block 0 of a later pass: already
         // waited for in the previous pass's output stage)
         if (j > 0) {
@@ -336,6 +453,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       s_xsum[part][row] = l;
       mbar_wait(pvdone, (uint32_t)((jj - 1) & 1));
       tc_fence_after();
+      if (SPILL) {  // hand the stored tiles to the async proxy (pass 2's bulk loads) and free Q / ring / P for its ring
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p1done);
+      }
       asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * FA_NSPLIT) : "memory");
       float lt = 0.f;
 #pragma unroll
@@ -352,7 +475,47 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(o[i]) * inv;
         fast_store<32>(orow + c * 32, v);
       }
-      if (pass + 1 < NPASS) {  // the next pass rewrites s_xsum and (through the MMA warp, after this thread's next pfull arrive) O
+      if (SPILL) {
+        // pass 2 runs on the MMA side alone; here only the replay of pass 1's O rescales (blocks where a row's maximum moved)
+        const uint32_t o2_taddr = o_taddr + (uint32_t)(OPARTS * 128);
+        uint32_t gpar = 0;
+        mbar_wait(p1done, 0);  // all sixteen warps' flags and maxima are in place
+        for (int j = 1; j < nb; ++j) {
+          if (!s_resc[j]) continue;
+          const float m0 = reinterpret_cast<const volatile float*>(ws + (size_t)(j - 1) * FA_WS_BLOCK + 32768)[row];
+          const float m1 = reinterpret_cast<const volatile float*>(ws + (size_t)j * FA_WS_BLOCK + 32768)[row];
+          const float alpha = fast_exp2(m0 - m1);
+          mbar_wait(gobar, gpar);  // PV(j-1) of pass 2 has completed; PV(j) waits for bar_resc
+          gpar ^= 1u;
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, m0 != m1)) {
+            for (int c = 0; c < ocols / 32; ++c) {
+              uint32_t o[32];
+              tmem_ld32(o2_taddr + (uint32_t)c * 32u, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(o2_taddr + (uint32_t)c * 32u, o);
+            }
+            tmem_st_wait();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(rescbar);
+        }
+        mbar_wait(p2done, 0);
+        tc_fence_after();
+        for (int c = 0; c < ocols / 32; ++c) {
+          uint32_t o[32];
+          tmem_ld32(o2_taddr + (uint32_t)c * 32u, o);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(o[i]) * inv;
+          fast_store<32>(orow + OPARTS * 128 + c * 32, v);
+        }
+      }
+      if (pass + 1 < NP1) {  // the next pass rewrites s_xsum and (through the MMA warp, after this thread's next pfull arrive) O
         tc_fence_before();
         asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * FA_NSPLIT) : "memory");
       }
@@ -365,6 +528,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+  if (SPILL && threadIdx.x == 0) {  // every bulk load of this CTA has been consumed: the workspace slot may change hands
+    __threadfence();
+    atomicExch(p.ws_flags + s_slot, 0);
   }
 }
 
@@ -384,6 +551,16 @@ extern "C" int rv_attention(const void* q, const void* k, int64_t ld_qk, const v
 
 extern "C" int rv_attention_lse(const void* q, const void* k, int64_t ld_qk, const void* vt, void* out, int64_t ld_out, float* lse,
                                 int n_img, int tokens, int d, void* stream) {
+  return rv_attention_ws(q, k, ld_qk, vt, out, ld_out, lse, nullptr, 0, n_img, tokens, d, stream);
+}
+
+extern "C" int64_t rv_attention_workspace_bytes(int tokens, int d) {
+  if (d != 512 || tokens <= 0 || tokens % 128 != 0 || tokens / 128 > rv::FA_MAX_NB) return 0;
+  return 1024 + (int64_t)rv::FA_WS_SLOTS * (tokens / 128) * (int64_t)rv::FA_WS_BLOCK;
+}
+
+extern "C" int rv_attention_ws(const void* q, const void* k, int64_t ld_qk, const void* vt, void* out, int64_t ld_out, float* lse,
+                               void* workspace, int64_t workspace_bytes, int n_img, int tokens, int d, void* stream) {
   using namespace rv;
   if (int rc = tc_ensure_init()) return rc;
   RV_CHECK_ARG(q && k && vt && out && n_img > 0 && tokens > 0, "attention: bad argument");
@@ -418,6 +595,7 @@ extern "C" int rv_attention_lse(const void* q, const void* k, int64_t ld_qk, con
       const int smem_max = 6 * 16384 + FA_RING * (int)FA_SLOT + (int)FA_P_BYTES + 1024;  // d = 384: 214 016 B; d = 512 needs the same
       RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<6, 3, 1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
       RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8, 2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8, 2, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
       g_fa_attr[dev] = true;
     }
   }
@@ -428,9 +606,18 @@ extern "C" int rv_attention_lse(const void* q, const void* k, int64_t ld_qk, con
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
   p.out = (__nv_bfloat16*)out;
   p.lse = lse;
+  // d = 512 with a workspace: pass 2 replays the probability tiles pass 1 left there instead of recomputing them
+  const int64_t ws_need = rv_attention_workspace_bytes(tokens, d);
+  const bool spill = workspace != nullptr && ws_need > 0;
+  RV_CHECK_ARG(!spill || (workspace_bytes >= ws_need && (uintptr_t)workspace % 128 == 0),
+               "attention: workspace of %lld bytes (128-byte aligned) needed, got %lld", (long long)ws_need, (long long)workspace_bytes);
+  p.ws_flags = (int*)workspace;
+  p.ws = spill ? (uint8_t*)workspace + 1024 : nullptr;
+  p.ws_slots = FA_WS_SLOTS;
   const int grid = n_img * (tokens / FA_BQ);
   LaunchScope scope(CAT_ATTN, st, 4.0 * (double)n_img * tokens * tokens * d);
   if (d == 384) flash_attn_kernel<6, 3, 1, 5><<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, p);
+  else if (spill) flash_attn_kernel<8, 2, 2, 3, true><<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, p);
   else flash_attn_kernel<8, 2, 2, 3><<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, p);
   RV_LAUNCH_CHECK();
   return 0;

@@ -192,14 +192,29 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, n_img: int, to
     if q.stride(0) != k.stride(0) or q.stride(1) != 1 or k.stride(1) != 1 or not vt.is_contiguous():
         raise ValueError("attention: q/k must share a row stride and be unit-stride in d; vt must be contiguous")
     out = torch.empty((n_img * tokens, d), dtype=torch.bfloat16, device=q.device)
-    if return_lse:
-        lse = torch.empty((n_img * tokens,), dtype=torch.float32, device=q.device)
-        check(_lib.load().rv_attention_lse(_ptr(q), _ptr(k), q.stride(0), _ptr(vt), _ptr(out), d, _ptr(lse), n_img, tokens, d,
-                                           _stream(q)), "rv_attention_lse")
-        return out, lse
-    check(_lib.load().rv_attention(_ptr(q), _ptr(k), q.stride(0), _ptr(vt), _ptr(out), d, n_img, tokens, d, _stream(q)),
-          "rv_attention")
-    return out
+    lse = torch.empty((n_img * tokens,), dtype=torch.float32, device=q.device) if return_lse else None
+    ws = _attention_workspace(q.device, tokens, d)
+    check(_lib.load().rv_attention_ws(_ptr(q), _ptr(k), q.stride(0), _ptr(vt), _ptr(out), d, _ptr(lse), _ptr(ws),
+                                      0 if ws is None else ws.numel(), n_img, tokens, d, _stream(q)), "rv_attention_ws")
+    return (out, lse) if return_lse else out
+
+
+_ATTN_WS: dict = {}
+
+
+def _attention_workspace(device: torch.device, tokens: int, d: int) -> Optional[torch.Tensor]:
+    """Per (device, stream) scratch of the d = 512 kernel (probability tiles of pass 1, replayed by pass 2); grow-only.
+    Its first 1024 bytes are the slot flags: zeroed once here, left zero by every launch."""
+    need = int(_lib.load().rv_attention_workspace_bytes(int(tokens), int(d)))
+    if need == 0:
+        return None
+    key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
+    ws = _ATTN_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty((need,), dtype=torch.uint8, device=device)
+        ws[:1024].zero_()
+        _ATTN_WS[key] = ws
+    return ws
 
 
 def gemm_rowstat(x: torch.Tensor, w: torch.Tensor, rowstat: torch.Tensor, mode: int, alpha: float,
