@@ -23,9 +23,10 @@
 // query block, each pass producing 256 of the 512 output columns.  Q (8 chunks, 128 KB) stays resident, the ring shrinks to
 // 3 slots.  Without a workspace the second pass recomputes S and the softmax (1.5x the MMA work of an ideal kernel).  With one
 // (rv_attention_ws, SPILL = true) pass 1 also leaves every probability tile -- the 32 KB shared-memory image the PV MMA reads,
-// plus the running maxima -- in a per-CTA slot of the workspace, and pass 2 is a pure P V stream: the tiles come back with
-// cp.async.bulk through a 13-slot ring laid over the Q, ring and P regions, the O rescales of pass 1 are replayed at the (rare)
-// blocks where a row's maximum moved, no S, no softmax: 64 instead of 96 MMAs per key block.
+// plus the running maxima -- in a per-CTA slot of the workspace, and pass 2 is a pure P V stream: the tiles come back by TMA
+// (the workspace seen as 128-byte rows, no swizzle: the image is already swizzled) through a 13-slot ring laid over the Q, ring
+// and P regions, the O rescales of pass 1 are replayed at the (rare) blocks where a row's maximum moved, no S, no softmax:
+// 64 instead of 96 MMAs per key block.  That form runs as CTA pairs (PAIR below) when tokens % 256 == 0.
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -63,12 +64,6 @@ constexpr uint32_t FA_WS_BLOCK = 32768 + 512;  // workspace per key block: the P
 constexpr int FA_WS_SLOTS = 160;             // > 148 co-resident CTAs (one per SM: 209 KB of shared memory each)
 constexpr int FA_MAX_NB = 1024;              // SPILL: key blocks per image (rescale flags live in shared memory)
 
-__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
@@ -93,19 +88,26 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
-// (A CTA-pair form -- M = 256 MMAs, K / V^T chunks split between two shared memories -- was built and measured in rounds 1 and
-// 2: 933 vs 958 TFLOP/s; the kernel is paced by its softmax warps, not by operand reads.  Removed.)
+// PAIR: two CTAs (256 queries of one image) issue M = 256 MMAs (cta_group::2) and split every K / V^T chunk between their shared
+// memories: each CTA streams HALF the operand bytes, so the same ring bytes hold twice as many (8 KB) slots.  The kernel is
+// paced by how far ahead of the MMAs its ring can run (measured: the d = 384 kernel with 3 instead of 5 slots drops from 1053
+// to 774 TFLOP/s, and d = 512 has room for 3), which is what the pair form buys -- with the SAME number of slots it was no
+// faster (933 vs 958 TFLOP/s, rounds 1-2).  Protocol as in conv_tc2_kernel: both CTAs' TMA loads complete on the LEADER's full
+// barriers, only the leader issues MMAs, tcgen05.commit is multicast to both CTAs' barriers, the peer's softmax warps arrive
+// remotely on the leader's sempty / pfull.
 // DCH: 64-wide chunks of d; OPARTS: N = 128 parts of O per pass; NPASS: key-loop passes; RING: K / V^T ring slots
-// (6, 3, 1, 5 for d = 384; 8, 2, 2, 3 for d = 512) -- compile-time so that the d = 384 loops stay fully unrolled
-template <int DCH, int OPARTS, int NPASS, int RING, bool SPILL = false>
+// (6, 3, 1, 5 for d = 384; 8, 2, 2, 3 for d = 512, 6 half-size slots in its pair form) -- compile-time so that the d = 384
+// loops stay fully unrolled
+template <bool PAIR, int DCH, int OPARTS, int NPASS, int RING, bool SPILL = false>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                  const __grid_constant__ CUtensorMap map_vt, const __grid_constant__ FaParams p) {
+                  const __grid_constant__ CUtensorMap map_vt, const __grid_constant__ CUtensorMap map_ws,
+                  const __grid_constant__ FaParams p) {
   extern __shared__ uint8_t smem_raw[];
   // One operand ring, two consumers (the S and the O issuer): a slot's "full" signal goes to the barrier of the KIND of chunk it
   // holds, so each consumer's parity wait can only ever see its own loads (with one shared barrier per slot a consumer that is
   // a whole phase behind would alias phases k and k+2).
-  __shared__ __align__(8) uint64_t bar_q, bar_fullk[FA_RING], bar_fullv[FA_RING], bar_empty[FA_RING], bar_sfull, bar_sempty, bar_pfull,
+  __shared__ __align__(8) uint64_t bar_q, bar_fullk[RING], bar_fullv[RING], bar_empty[RING], bar_sfull, bar_sempty, bar_pfull,
       bar_pvdone;
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_xmax[2][FA_NSPLIT][128];  // [block parity][column part][row]
@@ -119,14 +121,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   constexpr uint32_t q_bytes = (uint32_t)DCH * 16384u;
-  const uint32_t q_smem = base, ring = base + q_bytes, p_smem = ring + (uint32_t)RING * FA_SLOT;
+  constexpr uint32_t slot_bytes = PAIR ? FA_SLOT / 2 : FA_SLOT;
+  constexpr int nshare = PAIR ? 2 : 1;
+  const uint32_t q_smem = base, ring = base + q_bytes, p_smem = ring + (uint32_t)RING * slot_bytes;
   constexpr uint32_t nring = (uint32_t)RING;
   constexpr int ocols = OPARTS * 128 / FA_NSPLIT;  // O columns per softmax thread (rescale / output)
   const int nb = p.tokens / FA_BK;
   const int qblocks = p.tokens / FA_BQ;
   const int img = blockIdx.x / qblocks;
-  const int q0 = (blockIdx.x - img * qblocks) * FA_BQ;
-  constexpr uint32_t slot_bytes = FA_SLOT;
+  const int q0 = (blockIdx.x - img * qblocks) * FA_BQ;   // consecutive blocks = the two CTAs of a pair
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
 
   if (warp == 0 && lane == 0) {
     mbar_init(smem_u32(&bar_q), 1);
@@ -136,17 +141,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     mbar_init(smem_u32(&bar_sfull), 1);
-    mbar_init(smem_u32(&bar_sempty), FA_SM_WARPS);
-    mbar_init(smem_u32(&bar_pfull), FA_SM_WARPS);
+    mbar_init(smem_u32(&bar_sempty), FA_SM_WARPS * nshare);
+    mbar_init(smem_u32(&bar_pfull), FA_SM_WARPS * nshare);
     mbar_init(smem_u32(&bar_pvdone), 1);
     if (SPILL) {
       for (int s = 0; s < FA_RING2; ++s) {
         mbar_init(smem_u32(&bar_full2[s]), 1);
         mbar_init(smem_u32(&bar_empty2[s]), 1);
       }
-      mbar_init(smem_u32(&bar_p1done), FA_SM_WARPS);
+      mbar_init(smem_u32(&bar_p1done), FA_SM_WARPS * nshare);
       mbar_init(smem_u32(&bar_go), 1);
-      mbar_init(smem_u32(&bar_resc), FA_SM_WARPS);
+      mbar_init(smem_u32(&bar_resc), FA_SM_WARPS * nshare);
       mbar_init(smem_u32(&bar_p2done), 1);
       int sl = (int)(blockIdx.x % (unsigned)p.ws_slots);
       while (atomicCAS(p.ws_flags + sl, 0, 1) != 0) sl = sl + 1 == p.ws_slots ? 0 : sl + 1;
@@ -158,12 +163,19 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     for (int i = threadIdx.x; i < FA_MAX_NB; i += FA_THREADS) s_resc[i] = 0;
   if (warp == 1) {
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
   const uint32_t fullk0 = smem_u32(&bar_fullk[0]), fullv0 = smem_u32(&bar_fullv[0]), empty0 = smem_u32(&bar_empty[0]);
@@ -173,12 +185,24 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                  gobar = smem_u32(&bar_go), rescbar = smem_u32(&bar_resc), p2done = smem_u32(&bar_p2done);
   constexpr int NP1 = SPILL ? 1 : NPASS;  // passes that compute S (the SPILL form's second pass replays stored P tiles)
   uint8_t* const ws = SPILL ? p.ws + (size_t)s_slot * (size_t)nb * FA_WS_BLOCK : nullptr;
+  // barriers the MMA issuer (leader CTA) waits on, as cluster addresses, for signals that come from both CTAs
+  const uint32_t lead_fullk0 = PAIR ? mapa_rank(fullk0, 0) : fullk0;
+  const uint32_t lead_fullv0 = PAIR ? mapa_rank(fullv0, 0) : fullv0;
+  const uint32_t lead_q = PAIR ? mapa_rank(qbar, 0) : qbar;
+  const uint32_t lead_sempty = PAIR ? mapa_rank(sempty, 0) : sempty;
+  const uint32_t lead_pfull = PAIR ? mapa_rank(pfull, 0) : pfull;
+  const uint32_t lead_full20 = PAIR ? mapa_rank(full20, 0) : full20;
+  const uint32_t lead_resc = PAIR ? mapa_rank(rescbar, 0) : rescbar;
+  const uint32_t peer_p1done = PAIR ? mapa_rank(p1done, rank ^ 1u) : p1done;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
-      mbar_arrive_expect_tx(qbar, q_bytes);
-      for (int c = 0; c < DCH; ++c) tma_load_2d(q_smem + c * 16384u, &map_q, qbar, c * 64, img * p.tokens + q0);
+      if (leader) mbar_arrive_expect_tx(qbar, q_bytes * nshare);
+      for (int c = 0; c < DCH; ++c) {
+        if (PAIR) tma2_load_2d(q_smem + c * 16384u, &map_q, lead_q, c * 64, img * p.tokens + q0);
+        else tma_load_2d(q_smem + c * 16384u, &map_q, qbar, c * 64, img * p.tokens + q0);
+      }
     }
     __syncwarp();
     uint32_t slot = 0, par = 0;
@@ -189,8 +213,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int c = 0; c < DCH; ++c) {
           mbar_wait(empty0 + 8u * slot, par ^ 1u);
           if (elect_one()) {
-            mbar_arrive_expect_tx(fullk0 + 8u * slot, slot_bytes);
-            tma_load_2d(ring + slot * slot_bytes, &map_k, fullk0 + 8u * slot, c * 64, img * p.tokens + step * FA_BK);
+            if (leader) mbar_arrive_expect_tx(fullk0 + 8u * slot, slot_bytes * nshare);
+            if (PAIR)   // this CTA's 64 of the block's 128 keys
+              tma2_load_2d(ring + slot * slot_bytes, &map_k, lead_fullk0 + 8u * slot, c * 64,
+                           img * p.tokens + step * FA_BK + (int)rank * 64);
+            else
+              tma_load_2d(ring + slot * slot_bytes, &map_k, fullk0 + 8u * slot, c * 64, img * p.tokens + step * FA_BK);
           }
           __syncwarp();
           if (++slot == nring) { slot = 0; par ^= 1u; }
@@ -203,8 +231,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           for (int h = 0; h < OPARTS; ++h) {
             mbar_wait(empty0 + 8u * slot, par ^ 1u);
             if (elect_one()) {
-              mbar_arrive_expect_tx(fullv0 + 8u * slot, slot_bytes);
-              tma_load_3d(ring + slot * slot_bytes, &map_vt, fullv0 + 8u * slot, j * FA_BK + kc * 64, vrow0 + h * 128, img);
+              if (leader) mbar_arrive_expect_tx(fullv0 + 8u * slot, slot_bytes * nshare);
+              if (PAIR)  // this CTA's 64 of the 128 d-rows of the chunk
+                tma2_load_3d(ring + slot * slot_bytes, &map_vt, lead_fullv0 + 8u * slot, j * FA_BK + kc * 64,
+                             vrow0 + h * 128 + (int)rank * 64, img);
+              else
+                tma_load_3d(ring + slot * slot_bytes, &map_vt, fullv0 + 8u * slot, j * FA_BK + kc * 64, vrow0 + h * 128, img);
             }
             __syncwarp();
             if (++slot == nring) { slot = 0; par ^= 1u; }
@@ -220,16 +252,23 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int kc = 0; kc < 2; ++kc) {
           mbar_wait(empty20 + 8u * s2, par2 ^ 1u);
           if (elect_one()) {
-            mbar_arrive_expect_tx(full20 + 8u * s2, FA_SLOT);
-            bulk_load_1d(base + s2 * FA_SLOT, ws + (size_t)j * FA_WS_BLOCK + (size_t)kc * FA_SLOT, FA_SLOT, full20 + 8u * s2);
+            // this CTA's own tile (its 128 rows of P): a [128 rows x 128 B] box of the workspace seen as 128-byte rows
+            const int wrow = (int)(((size_t)(ws - p.ws) + (size_t)j * FA_WS_BLOCK + (size_t)kc * FA_SLOT) >> 7);
+            if (leader) mbar_arrive_expect_tx(full20 + 8u * s2, FA_SLOT * nshare);
+            if (PAIR) tma2_load_2d(base + s2 * FA_SLOT, &map_ws, lead_full20 + 8u * s2, 0, wrow);
+            else tma_load_2d(base + s2 * FA_SLOT, &map_ws, full20 + 8u * s2, 0, wrow);
           }
           __syncwarp();
           advance2();
           for (int h = 0; h < OPARTS; ++h) {
             mbar_wait(empty20 + 8u * s2, par2 ^ 1u);
             if (elect_one()) {
-              mbar_arrive_expect_tx(full20 + 8u * s2, FA_SLOT);
-              tma_load_3d(base + s2 * FA_SLOT, &map_vt, full20 + 8u * s2, j * FA_BK + kc * 64, OPARTS * 128 + h * 128, img);
+              if (leader) mbar_arrive_expect_tx(full20 + 8u * s2, slot_bytes * nshare);
+              if (PAIR)
+                tma2_load_3d(base + s2 * FA_SLOT, &map_vt, lead_full20 + 8u * s2, j * FA_BK + kc * 64,
+                             OPARTS * 128 + h * 128 + (int)rank * 64, img);
+              else
+                tma_load_3d(base + s2 * FA_SLOT, &map_vt, full20 + 8u * s2, j * FA_BK + kc * 64, OPARTS * 128 + h * 128, img);
             }
             __syncwarp();
             advance2();
@@ -241,18 +280,24 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     // Both walk the producer's push sequence (per pass: K(0) | K(1) V(0) | K(2) V(1) | ... | V(nb-1)); each consumes its own
     // kind of ring slot and only counts past the other's.
     const bool is_qk = warp == 1;
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
     const uint64_t hi = make_smem_desc(0u, 1024u, 2u);
     const uint32_t q_lo = (q_smem & 0x3FFFFu) >> 4, p_lo = (p_smem & 0x3FFFFu) >> 4, ring_lo = (ring & 0x3FFFFu) >> 4;
     const uint32_t s_tmem = tmem_base + 384u;
     uint32_t slot = 0, use_par = 0;  // bit s of use_par: parity of this issuer's next use of slot s
-    auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accf) { umma_bf16(d, a, b, idesc, accf); };
-    auto commit = [&](uint32_t bar) { umma_commit(bar); };
+    auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accf) {
+      if (PAIR) umma2_bf16(d, a, b, idesc, accf);
+      else umma_bf16(d, a, b, idesc, accf);
+    };
+    auto commit = [&](uint32_t bar) {
+      if (PAIR) umma2_commit_both(bar);
+      else umma_commit(bar);
+    };
     auto skip = [&](int n) {
       for (int i = 0; i < n; ++i)
         if (++slot == nring) slot = 0;
     };
-    {
+    if (leader) {
       if (is_qk) mbar_wait(qbar, 0);
       int g = 0;  // key blocks issued so far over all passes: every per-block barrier flips once per block
       for (int pass = 0; pass < NP1; ++pass)
@@ -318,7 +363,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         }
       if (SPILL && !is_qk) {
         // pass 2: O[:, 256:512) += P(j) V(j)[:, 256:512) from the stored tiles, into TMEM columns [256, 512)
-        mbar_wait(p1done, 0);  // also orders the s_resc flags written in pass 1
+        mbar_wait(p1done, 0);  // also orders the s_resc flags written in pass 1 (by both CTAs of a pair)
+        if (PAIR) asm volatile("fence.acq_rel.cluster;" ::: "memory");
         tc_fence_after();
         const uint32_t base_lo = (base & 0x3FFFFu) >> 4;
         uint32_t s2 = 0, par2 = 0, rpar = 0;
@@ -379,7 +425,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(sempty);
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(lead_sempty); else mbar_arrive(sempty); }
         float mx = -INFINITY;
 #pragma unroll
         for (int i = 0; i < FA_KCOLS; ++i) mx = fmaxf(mx, __uint_as_float(s0[i]));
@@ -418,7 +464,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             *reinterpret_cast<uint4*>(wrow + (((u0 + (uint32_t)u) ^ sw) << 4)) =
                 make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
           if (part == 0) reinterpret_cast<float*>(wt + 32768)[row] = m_used;
-          if (need) s_resc[j] = 1;
+          if (need) {
+            s_resc[j] = 1;
+            if (PAIR)  // the pair's PV MMAs stop for a rescale of either CTA's rows
+              asm volatile("st.shared::cluster.u8 [%0], %1;" ::"r"(mapa_rank(smem_u32(&s_resc[j]), rank ^ 1u)), "h"((unsigned short)1) : "memory");
+          }
         }
         // the previous PV must be complete before P is overwritten or O is rescaled (block 0 of a later pass: already
         // waited for in the previous pass's output stage)
@@ -444,10 +494,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                        "r"(pk[4 * u + 3])
                        : "memory");
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (PAIR) asm volatile("fence.proxy.async;" ::: "memory");
+        else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(pfull);
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(lead_pfull); else mbar_arrive(pfull); }
       }
       // ---- output of this pass: O / l into columns [pass * oparts * 128, ...) ----
       s_xsum[part][row] = l;
@@ -456,8 +507,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       if (SPILL) {  // hand the stored tiles to the async proxy (pass 2's bulk loads) and free Q / ring / P for its ring
         __threadfence();
         asm volatile("fence.proxy.async;" ::: "memory");
+        if (PAIR) asm volatile("fence.acq_rel.cluster;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(p1done);
+        if (lane == 0) {
+          mbar_arrive(p1done);
+          if (PAIR) mbar_arrive_cluster(peer_p1done);
+        }
       }
       asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * FA_NSPLIT) : "memory");
       float lt = 0.f;
@@ -479,7 +534,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         // pass 2 runs on the MMA side alone; here only the replay of pass 1's O rescales (blocks where a row's maximum moved)
         const uint32_t o2_taddr = o_taddr + (uint32_t)(OPARTS * 128);
         uint32_t gpar = 0;
-        mbar_wait(p1done, 0);  // all sixteen warps' flags and maxima are in place
+        mbar_wait(p1done, 0);  // all softmax warps' (of both CTAs of a pair) flags and maxima are in place
+        if (PAIR) asm volatile("fence.acq_rel.cluster;" ::: "memory");
         for (int j = 1; j < nb; ++j) {
           if (!s_resc[j]) continue;
           const float m0 = reinterpret_cast<const volatile float*>(ws + (size_t)(j - 1) * FA_WS_BLOCK + 32768)[row];
@@ -501,7 +557,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(rescbar);
+          if (lane == 0) { if (PAIR) mbar_arrive_cluster(lead_resc); else mbar_arrive(rescbar); }
         }
         mbar_wait(p2done, 0);
         tc_fence_after();
@@ -524,10 +580,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // nobody frees TMEM or exits while the peer may still signal / read
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
   if (SPILL && threadIdx.x == 0) {  // every bulk load of this CTA has been consumed: the workspace slot may change hands
     __threadfence();
@@ -570,32 +628,49 @@ extern "C" int rv_attention_ws(const void* q, const void* k, int64_t ld_qk, cons
   RV_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)vt % 16 == 0) && ((uintptr_t)out % 16 == 0),
                "attention: tensors must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  CUtensorMap mq, mk, mv;
+  // d = 512 with a workspace: pass 2 replays the probability tiles pass 1 left there instead of recomputing them
+  const int64_t ws_need = rv_attention_workspace_bytes(tokens, d);
+  const bool spill = workspace != nullptr && ws_need > 0;
+  RV_CHECK_ARG(!spill || (workspace_bytes >= ws_need && (uintptr_t)workspace % 128 == 0),
+               "attention: workspace of %lld bytes (128-byte aligned) needed, got %lld", (long long)ws_need, (long long)workspace_bytes);
+  // CTA pairs (two adjacent query blocks of one image) where the ring is the bound: the d = 512 SPILL form (3 full-size slots:
+  // 678 -> 784 TFLOP/s as a pair with 6 half-size ones).  Not d = 384, whose 5 slots suffice (pair with 10: 984 vs 1058).
+  const bool pair = tokens % 256 == 0 && spill;
+  const cuuint32_t share = pair ? 2u : 1u;
+  CUtensorMap mq, mk, mv, mw;
   {
     cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)((int64_t)n_img * tokens)};
     cuuint64_t str[1] = {(cuuint64_t)ld_qk * 2u};
     cuuint32_t box[2] = {64, 128};
     if (int rc = tc_encode_map(&mq, q, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    cuuint32_t boxk[2] = {64, 128};
+    cuuint32_t boxk[2] = {64, 128u / share};
     if (int rc = tc_encode_map(&mk, k, 2, dims, str, boxk, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   }
   {
     cuuint64_t dims[3] = {(cuuint64_t)tokens, (cuuint64_t)d, (cuuint64_t)n_img};
     cuuint64_t str[2] = {(cuuint64_t)tokens * 2u, (cuuint64_t)tokens * 2u * d};
-    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t box[3] = {64, 128u / share, 1};
     if (int rc = tc_encode_map(&mv, vt, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   }
-  const int ring_slots = d == 384 ? FA_RING : 3;
-  const size_t smem = (size_t)(d / 64) * 16384 + (size_t)ring_slots * FA_SLOT + FA_P_BYTES + 1024;
+  if (spill) {  // the workspace's tile area as 128-byte rows: a [128 x 128 B] box is one half (64 keys) of a stored P tile, verbatim
+    cuuint64_t dims[2] = {64, (cuuint64_t)((ws_need - 1024) / 128)};
+    cuuint64_t str[1] = {128};
+    cuuint32_t box[2] = {64, 128};
+    if (int rc = tc_encode_map(&mw, (const uint8_t*)workspace + 1024, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+  } else {
+    mw = mq;
+  }
+  const size_t smem = (size_t)(d / 64) * 16384 + (size_t)(d == 384 ? FA_RING : 3) * FA_SLOT + FA_P_BYTES + 1024;
   {
     std::lock_guard<std::mutex> lk(g_fa_mu);
     int dev = 0;
     RV_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !g_fa_attr[dev]) {
       const int smem_max = 6 * 16384 + FA_RING * (int)FA_SLOT + (int)FA_P_BYTES + 1024;  // d = 384: 214 016 B; d = 512 needs the same
-      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<6, 3, 1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8, 2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<8, 2, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<false, 6, 3, 1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<false, 8, 2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<false, 8, 2, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+      RV_CUDA(cudaFuncSetAttribute(flash_attn_kernel<true, 8, 2, 2, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
       g_fa_attr[dev] = true;
     }
   }
@@ -606,19 +681,32 @@ extern "C" int rv_attention_ws(const void* q, const void* k, int64_t ld_qk, cons
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
   p.out = (__nv_bfloat16*)out;
   p.lse = lse;
-  // d = 512 with a workspace: pass 2 replays the probability tiles pass 1 left there instead of recomputing them
-  const int64_t ws_need = rv_attention_workspace_bytes(tokens, d);
-  const bool spill = workspace != nullptr && ws_need > 0;
-  RV_CHECK_ARG(!spill || (workspace_bytes >= ws_need && (uintptr_t)workspace % 128 == 0),
-               "attention: workspace of %lld bytes (128-byte aligned) needed, got %lld", (long long)ws_need, (long long)workspace_bytes);
   p.ws_flags = (int*)workspace;
   p.ws = spill ? (uint8_t*)workspace + 1024 : nullptr;
   p.ws_slots = FA_WS_SLOTS;
   const int grid = n_img * (tokens / FA_BQ);
   LaunchScope scope(CAT_ATTN, st, 4.0 * (double)n_img * tokens * tokens * d);
-  if (d == 384) flash_attn_kernel<6, 3, 1, 5><<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, p);
-  else if (spill) flash_attn_kernel<8, 2, 2, 3, true><<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, p);
-  else flash_attn_kernel<8, 2, 2, 3><<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, p);
+  if (pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(FA_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RV_CUDA(cudaLaunchKernelEx(&cfg, flash_attn_kernel<true, 8, 2, 2, 6, true>, mq, mk, mv, mw, p));
+  } else if (d == 384) {
+    flash_attn_kernel<false, 6, 3, 1, 5><<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, mw, p);
+  } else if (spill) {
+    flash_attn_kernel<false, 8, 2, 2, 3, true><<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, mw, p);
+  } else {
+    flash_attn_kernel<false, 8, 2, 2, 3><<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, mw, p);
+  }
   RV_LAUNCH_CHECK();
   return 0;
 }
