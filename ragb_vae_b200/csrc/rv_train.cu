@@ -418,76 +418,124 @@ static inline dim3 train_grid(int64_t items, int n) {
 // they give dbeta / dgamma AND, weighted by gamma over a group's channels, S1 / S2.  Pass 2 streams dx (+ the skip branch).
 // Same block geometry as the forward kernels (the partition depends on H*W only).
 // ------------------------------------------------------------------------------------------
+// dy * silu'(u), u = xh * ga + be.  bf16 tensors: sigmoid through ONE tanh.approx (sg = (1 + t) / 2, t = tanh(u / 2)), so
+//   silu'(u) = sg * (1 + u * (1 - sg)) = (1 + t + h * (1 - t * t)) / 2,  h = u / 2 = xh * gh + bh  (gh = ga / 2, bh = be / 2):
+// one SFU op and five FMA-pipe ops, against expf + an IEEE divide (a ~10-instruction sequence) and seven more -- the two
+// GroupNorm backward passes ran ALU-bound at 1.7-1.9 TB/s with those (is the same story in the forward).
+// fp32 tensors (parity mode) keep the exact form.
+// Both passes work from the raw x: h = x * ah + bh with ah = rstd * gamma / 2, bh = (beta - mean * rstd * gamma) / 2 -- two
+// per-channel constants instead of four, and xh never materialises (pass 1 accumulates sum(du * x) and turns it into
+// sum(du * xh) = rstd * sum(du * x) - mean * rstd * sum(du) in fp64 at the end; pass 2 folds xh into its own constants): the
+// kernels drop from 127 to under 100 registers.
+template <typename T>
+__device__ __forceinline__ float gn_dsilu(float dy, float h) {
+  if (sizeof(T) == 2) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    const float w = fmaf(-t, t, 1.0f);
+    const float a = fmaf(h, w, t);
+    const float dh = 0.5f * dy;
+    return fmaf(dh, a, dh);
+  }
+  const float u = 2.0f * h;
+  const float sg = 1.0f / (1.0f + expf(-u));
+  return dy * sg * (1.0f + u * (1.0f - sg));
+}
+
 template <typename T, bool SILU>
-__global__ void __launch_bounds__(512) groupnorm_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+__global__ void __launch_bounds__(256, 3) groupnorm_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                                   const double* __restrict__ stats, const float* __restrict__ gamma,
                                                                   const float* __restrict__ beta, double* __restrict__ chan,
                                                                   int64_t hw, int c, int groups, int cpp, float eps,
                                                                   int64_t rows_per_block) {
   using V = Vec16<T>;
-  extern __shared__ double sacc[];  // [c][2]
+  extern __shared__ float sred[];  // [threads][2 * V::N]: every thread's partial sums, folded below without shared-memory atomics
+  __shared__ double s_mr[64][2];   // per group: mean, rstd -- computed ONCE per block (fp64 divide / sqrt are subroutine calls:
+                                   // done per thread and channel they were a sixth of the kernel's instructions)
   const int tid = threadIdx.x;
   const int n = blockIdx.y;
-  for (int i = tid; i < c * 2; i += blockDim.x) sacc[i] = 0.0;
-  __syncthreads();
   const int col = tid % cpp;
   const int rows_per_iter = blockDim.x / cpp;
   const int cg = c / groups;
   const double cnt = (double)hw * (double)cg;
-  float mean[V::N], rstd[V::N], ga[V::N], be[V::N], a[V::N], b[V::N];
-#pragma unroll
-  for (int j = 0; j < V::N; ++j) {
-    const int ch = col * V::N + j, g = ch / cg;
+  for (int g = tid; g < groups; g += blockDim.x) {
     const double m = stats[((int64_t)n * groups + g) * 2] / cnt;
     double var = stats[((int64_t)n * groups + g) * 2 + 1] / cnt - m * m;
     if (var < 0.0) var = 0.0;
-    mean[j] = (float)m;
-    rstd[j] = (float)(1.0 / sqrt(var + (double)eps));
-    ga[j] = gamma[ch];
-    be[j] = beta[ch];
+    s_mr[g][0] = m;
+    s_mr[g][1] = 1.0 / sqrt(var + (double)eps);
+  }
+  __syncthreads();
+  float ah[V::N], bh[V::N], a[V::N], b[V::N];  // a = sum du, b = sum du * x
+#pragma unroll
+  for (int j = 0; j < V::N; ++j) {
+    const int ch = col * V::N + j, g = ch / cg;
+    const float m = (float)s_mr[g][0], rs = (float)s_mr[g][1];
+    const float ga = gamma[ch];
+    ah[j] = 0.5f * rs * ga;
+    bh[j] = 0.5f * (beta[ch] - m * rs * ga);
     a[j] = b[j] = 0.f;
   }
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = min(hw, r0 + rows_per_block);
-  const T* xb = x + (int64_t)n * hw * c;
-  const T* gb = dy + (int64_t)n * hw * c;
-#pragma unroll 2
-  for (int64_t r = r0 + tid / cpp; r < r1; r += rows_per_iter) {
-    V vx, vg;
-    vx.load(xb + r * c + col * V::N);
-    vg.load(gb + r * c + col * V::N);
+  const T* xb = x + (int64_t)n * hw * c + col * V::N;
+  const T* gb = dy + (int64_t)n * hw * c + col * V::N;
+  constexpr int U = 3;  // rows in flight per thread: 6 x 16-byte loads, three blocks per SM
+  for (int64_t rb = r0 + tid / cpp; rb < r1; rb += (int64_t)U * rows_per_iter) {
+    V vx[U], vg[U];
 #pragma unroll
-    for (int j = 0; j < V::N; ++j) {
-      const float xh = (vx.get(j) - mean[j]) * rstd[j];
-      float du = vg.get(j);
-      if (SILU) {
-        const float u = fmaf(xh, ga[j], be[j]);
-        const float sg = 1.0f / (1.0f + __expf(-u));
-        du *= sg * (1.0f + u * (1.0f - sg));
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = rb + (int64_t)u * rows_per_iter;
+      if (r < r1) {
+        vx[u].load(xb + r * c);
+        vg[u].load(gb + r * c);
+      } else {
+        vx[u].zero();
+        vg[u].zero();
       }
-      a[j] += du;
-      b[j] = fmaf(du, xh, b[j]);
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < V::N; ++j) {
+        const float xv = vx[u].get(j);
+        const float du = SILU ? gn_dsilu<T>(vg[u].get(j), fmaf(xv, ah[j], bh[j])) : vg[u].get(j);
+        a[j] += du;
+        b[j] = fmaf(du, xv, b[j]);
+      }
   }
+  // one thread per channel adds the block's rows in fp64 (fp64 atomics on shared memory are compare-and-swap loops: 16 rows
+  // colliding per address made this tail as long as the streaming loop) and issues the two global atomics
+  float* my = sred + tid * (2 * V::N);
 #pragma unroll
   for (int j = 0; j < V::N; ++j) {
-    const int ch = col * V::N + j;
-    atomicAdd(&sacc[2 * ch], (double)a[j]);
-    atomicAdd(&sacc[2 * ch + 1], (double)b[j]);
+    my[j] = a[j];
+    my[V::N + j] = b[j];
   }
   __syncthreads();
-  for (int i = tid; i < c * 2; i += blockDim.x) atomicAdd(&chan[(int64_t)n * c * 2 + i], sacc[i]);
+  for (int ch = tid; ch < c; ch += blockDim.x) {
+    const int g = ch / cg;
+    const float* src = sred + (ch / V::N) * (2 * V::N) + (ch % V::N);
+    double sa = 0.0, sb = 0.0;
+    for (int r = 0; r < rows_per_iter; ++r) {
+      sa += (double)src[(int64_t)r * cpp * (2 * V::N)];
+      sb += (double)src[(int64_t)r * cpp * (2 * V::N) + V::N];
+    }
+    const double m = s_mr[g][0], rs = s_mr[g][1];
+    atomicAdd(&chan[(int64_t)n * c * 2 + 2 * ch], sa);
+    atomicAdd(&chan[(int64_t)n * c * 2 + 2 * ch + 1], rs * (sb - m * sa));  // sum du * xh
+  }
 }
 
 template <typename T, bool SILU>
-__global__ void __launch_bounds__(512) groupnorm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+__global__ void __launch_bounds__(256, 3) groupnorm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                                  const T* __restrict__ add, const double* __restrict__ stats,
                                                                  const double* __restrict__ chan, const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, T* __restrict__ dx,
                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t hw,
                                                                  int c, int groups, int cpp, float eps, int64_t rows_per_block) {
   using V = Vec16<T>;
-  extern __shared__ float sgrp[];  // [groups][2]: S1 / m, S2 / m
+  extern __shared__ float sgrp[];  // [groups][4]: S1 / m, S2 / m, mean, rstd
   const int tid = threadIdx.x;
   const int n = blockIdx.y;
   const int cg = c / groups;
@@ -500,8 +548,13 @@ __global__ void __launch_bounds__(512) groupnorm_bwd_apply_kernel(const T* __res
       s1 += (double)gamma[ch] * ch_n[2 * ch];
       s2 += (double)gamma[ch] * ch_n[2 * ch + 1];
     }
-    sgrp[2 * g] = (float)(s1 / cnt);
-    sgrp[2 * g + 1] = (float)(s2 / cnt);
+    const double m = stats[((int64_t)n * groups + g) * 2] / cnt;
+    double var = stats[((int64_t)n * groups + g) * 2 + 1] / cnt - m * m;
+    if (var < 0.0) var = 0.0;
+    sgrp[4 * g] = (float)(s1 / cnt);
+    sgrp[4 * g + 1] = (float)(s2 / cnt);
+    sgrp[4 * g + 2] = (float)m;
+    sgrp[4 * g + 3] = (float)(1.0 / sqrt(var + (double)eps));
   }
   if (blockIdx.x == 0) {  // parameter gradients: one block per sample adds the sample's channel sums
     for (int ch = tid; ch < c; ch += blockDim.x) {
@@ -512,44 +565,52 @@ __global__ void __launch_bounds__(512) groupnorm_bwd_apply_kernel(const T* __res
   __syncthreads();
   const int col = tid % cpp;
   const int rows_per_iter = blockDim.x / cpp;
-  float mean[V::N], rstd[V::N], ga[V::N], be[V::N], m1[V::N], m2[V::N];
+  // dx = rstd * (du * ga - m1 - xh * m2), xh = (x - mean) * rstd  =>  dx = du * rg - x * k2 - k1 with rg = rstd * ga,
+  // k2 = rstd^2 * m2, k1 = rstd * m1 - mean * rstd^2 * m2
+  float ah[V::N], bh[V::N], rg[V::N], k1[V::N], k2[V::N];
 #pragma unroll
   for (int j = 0; j < V::N; ++j) {
     const int ch = col * V::N + j, g = ch / cg;
-    const double m = stats[((int64_t)n * groups + g) * 2] / cnt;
-    double var = stats[((int64_t)n * groups + g) * 2 + 1] / cnt - m * m;
-    if (var < 0.0) var = 0.0;
-    mean[j] = (float)m;
-    rstd[j] = (float)(1.0 / sqrt(var + (double)eps));
-    ga[j] = gamma[ch];
-    be[j] = beta[ch];
-    m1[j] = sgrp[2 * g];
-    m2[j] = sgrp[2 * g + 1];
+    const float m1 = sgrp[4 * g], m2 = sgrp[4 * g + 1], m = sgrp[4 * g + 2], rs = sgrp[4 * g + 3];
+    const float ga = gamma[ch];
+    ah[j] = 0.5f * rs * ga;
+    bh[j] = 0.5f * (beta[ch] - m * rs * ga);
+    rg[j] = rs * ga;
+    k2[j] = rs * rs * m2;
+    k1[j] = rs * m1 - m * k2[j];
   }
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = min(hw, r0 + rows_per_block);
-  const int64_t base = (int64_t)n * hw * c;
-#pragma unroll 2
-  for (int64_t r = r0 + tid / cpp; r < r1; r += rows_per_iter) {
-    V vx, vg, va, o;
-    const int64_t off = base + r * c + col * V::N;
-    vx.load(x + off);
-    vg.load(dy + off);
-    if (add) va.load(add + off);
+  const int64_t base = (int64_t)n * hw * c + col * V::N;
+  constexpr int U = 2;  // rows in flight per thread: 4 (6 with the skip branch) x 16-byte loads, three blocks per SM
+  for (int64_t rb = r0 + tid / cpp; rb < r1; rb += (int64_t)U * rows_per_iter) {
+    V vx[U], vg[U], va[U];
 #pragma unroll
-    for (int j = 0; j < V::N; ++j) {
-      const float xh = (vx.get(j) - mean[j]) * rstd[j];
-      float du = vg.get(j);
-      if (SILU) {
-        const float u = fmaf(xh, ga[j], be[j]);
-        const float sg = 1.0f / (1.0f + __expf(-u));
-        du *= sg * (1.0f + u * (1.0f - sg));
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = rb + (int64_t)u * rows_per_iter;
+      if (r < r1) {
+        const int64_t off = base + r * c;
+        vx[u].load(x + off);
+        vg[u].load(dy + off);
+        if (add) va[u].load(add + off);
       }
-      float d = rstd[j] * (du * ga[j] - m1[j] - xh * m2[j]);
-      if (add) d += va.get(j);
-      o.set(j, d);
     }
-    o.store(dx + off);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = rb + (int64_t)u * rows_per_iter;
+      if (r < r1) {
+        V o;
+#pragma unroll
+        for (int j = 0; j < V::N; ++j) {
+          const float xv = vx[u].get(j);
+          const float du = SILU ? gn_dsilu<T>(vg[u].get(j), fmaf(xv, ah[j], bh[j])) : vg[u].get(j);
+          float d = fmaf(-xv, k2[j], fmaf(du, rg[j], -k1[j]));
+          if (add) d += va[u].get(j);
+          o.set(j, d);
+        }
+        o.store(dx + base + r * c);
+      }
+    }
   }
 }
 
@@ -561,9 +622,9 @@ struct GnBwdGeom {
 template <typename T>
 static int gn_bwd_geometry(int64_t hw, int c, int groups, GnBwdGeom* g) {  // = gn_geometry of rv_elementwise.cu
   constexpr int VN = Vec16<T>::N;
-  RV_CHECK_ARG(groups > 0 && c % groups == 0 && c % VN == 0, "groupnorm_bwd: bad channel/group count %d/%d", c, groups);
+  RV_CHECK_ARG(groups > 0 && groups <= 64 && c % groups == 0 && c % VN == 0, "groupnorm_bwd: bad channel/group count %d/%d", c, groups);
   g->cpp = c / VN;
-  RV_CHECK_ARG(g->cpp <= 512, "groupnorm_bwd: too many channels (%d)", c);
+  RV_CHECK_ARG(g->cpp <= 256, "groupnorm_bwd: too many channels (%d)", c);
   int rows = 256 / g->cpp;
   if (rows < 1) rows = 1;
   g->block = rows * g->cpp;
@@ -582,7 +643,7 @@ static int groupnorm_bwd_launch(const void* x, const void* dy, const void* add, 
   const double bytes = (double)n * hw * c * sizeof(T);
   {
     LaunchScope scope(CAT_NORM, st, 2.0 * bytes);
-    const size_t smem = sizeof(double) * 2 * c;
+    const size_t smem = sizeof(float) * 2 * (16 / sizeof(T)) * g.block;
     if (apply_silu)
       groupnorm_bwd_reduce_kernel<T, true><<<dim3(g.blocks_x, n), g.block, smem, st>>>((const T*)x, (const T*)dy, stats, gamma, beta, chan, hw,
                                                                                      c, groups, g.cpp, eps, g.rows_per_block);
@@ -593,7 +654,7 @@ static int groupnorm_bwd_launch(const void* x, const void* dy, const void* add, 
   }
   {
     LaunchScope scope(CAT_NORM, st, (add ? 4.0 : 3.0) * bytes);
-    const size_t smem = sizeof(float) * 2 * groups;
+    const size_t smem = sizeof(float) * 4 * groups;
     if (apply_silu)
       groupnorm_bwd_apply_kernel<T, true><<<dim3(g.blocks_x, n), g.block, smem, st>>>((const T*)x, (const T*)dy, (const T*)add, stats, chan, gamma,
                                                                                     beta, (T*)dx, dgamma, dbeta, hw, c, groups, g.cpp, eps,
