@@ -180,8 +180,16 @@ __global__ void __launch_bounds__(256) rmsnorm_silu_bwd_kernel(const T* __restri
         float d = dv[k].get(j);
         if (SILU) {
           const float u = xr * g[k][j];
-          const float sg = __fdividef(1.0f, 1.0f + __expf(-u));
-          d *= sg * (1.0f + u * (1.0f - sg));
+          if (sizeof(T) == 2) {  // silu'(u) = (1 + t + h * (1 - t * t)) / 2, t = tanh(h), h = u / 2: one SFU op (see gn_dsilu)
+            const float h = 0.5f * u;
+            float t;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+            const float dh = 0.5f * d;
+            d = fmaf(dh, fmaf(h, fmaf(-t, t, 1.0f), t), dh);
+          } else {
+            const float sg = __fdividef(1.0f, 1.0f + __expf(-u));
+            d *= sg * (1.0f + u * (1.0f - sg));
+          }
         }
         du[k][j] = d;
         dg[k][j] = fmaf(xr, d, dg[k][j]);
