@@ -137,7 +137,7 @@ def reference_arm(a):
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "one CPU process on rank 0's host cores whatever --gpus says: only the N=1 ratio against it is an anchor"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -674,8 +674,31 @@ def ensure_library():
             time.sleep(2.0)
 
 
+_STDOUT_FD = None
+
+
+def claim_stdout():
+    """ONE JSON line is the contract: whatever libraries print to fd 1 while the benchmark runs (NCCL's version banner under
+    torchrun, for one) goes to stderr instead; emit() writes the line to the real stdout."""
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _STDOUT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_STDOUT_FD, data)
+
+
 def main():
     a = parse()
+    claim_stdout()
     if a.impl == "reference":
         reference_arm(a)
         return
@@ -705,7 +728,7 @@ def main():
                 else:
                     line["cpu_baseline"] = None
         if cx.rank == 0 and line is not None:
-            print(json.dumps(line), flush=True)
+            emit(line)
     finally:
         cx.close()
 
