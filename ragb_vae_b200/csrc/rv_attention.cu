@@ -260,18 +260,28 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           }
           __syncwarp();
           advance2();
-          for (int h = 0; h < OPARTS; ++h) {
+          if (PAIR) {
+            // ONE slot per 64-key half: this CTA's 128 of the 256 d-rows [256, 512) as two 64-row boxes -- the pair's PV MMA is
+            // N = 256 (8 instead of 16 MMAs per key block, and two ring slots per half instead of three)
             mbar_wait(empty20 + 8u * s2, par2 ^ 1u);
             if (elect_one()) {
-              if (leader) mbar_arrive_expect_tx(full20 + 8u * s2, slot_bytes * nshare);
-              if (PAIR)
-                tma2_load_3d(base + s2 * FA_SLOT, &map_vt, lead_full20 + 8u * s2, j * FA_BK + kc * 64,
-                             OPARTS * 128 + h * 128 + (int)rank * 64, img);
-              else
-                tma_load_3d(base + s2 * FA_SLOT, &map_vt, full20 + 8u * s2, j * FA_BK + kc * 64, OPARTS * 128 + h * 128, img);
+              if (leader) mbar_arrive_expect_tx(full20 + 8u * s2, FA_SLOT * nshare);
+              for (int hh = 0; hh < 2; ++hh)
+                tma2_load_3d(base + s2 * FA_SLOT + (uint32_t)hh * (FA_SLOT / 2), &map_vt, lead_full20 + 8u * s2, j * FA_BK + kc * 64,
+                             OPARTS * 128 + (int)rank * 128 + hh * 64, img);
             }
             __syncwarp();
             advance2();
+          } else {
+            for (int h = 0; h < OPARTS; ++h) {
+              mbar_wait(empty20 + 8u * s2, par2 ^ 1u);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(full20 + 8u * s2, FA_SLOT);
+                tma_load_3d(base + s2 * FA_SLOT, &map_vt, full20 + 8u * s2, j * FA_BK + kc * 64, OPARTS * 128 + h * 128, img);
+              }
+              __syncwarp();
+              advance2();
+            }
           }
         }
     }
@@ -381,20 +391,30 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             const uint32_t ps = s2;
             mbar_wait(full20 + 8u * ps, par2);
             advance2();
-            for (int h = 0; h < OPARTS; ++h) {
+            constexpr int H2 = PAIR ? 1 : OPARTS;  // pair form: one N = 256 MMA covers both 128-column parts
+            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((256u >> 4) << 24);
+            for (int h = 0; h < H2; ++h) {
               mbar_wait(full20 + 8u * s2, par2);
               tc_fence_after();
               if (elect_one()) {
                 const uint64_t ad = hi | (uint64_t)(base_lo + ps * (FA_SLOT >> 4));
                 const uint64_t bd = hi | (uint64_t)(base_lo + s2 * (FA_SLOT >> 4));
                 const uint32_t d_tmem = tmem_base + (uint32_t)(OPARTS + h) * 128u;
-                mma(d_tmem, ad, bd, (j == 0 && kc == 0) ? 0u : 1u);
-                mma(d_tmem, ad + 2u, bd + 2u, 1u);
-                mma(d_tmem, ad + 4u, bd + 4u, 1u);
-                mma(d_tmem, ad + 6u, bd + 6u, 1u);
+                const uint32_t acc0 = (j == 0 && kc == 0) ? 0u : 1u;
+                if (PAIR) {
+                  umma2_bf16(d_tmem, ad, bd, idesc2, acc0);
+                  umma2_bf16(d_tmem, ad + 2u, bd + 2u, idesc2, 1u);
+                  umma2_bf16(d_tmem, ad + 4u, bd + 4u, idesc2, 1u);
+                  umma2_bf16(d_tmem, ad + 6u, bd + 6u, idesc2, 1u);
+                } else {
+                  mma(d_tmem, ad, bd, acc0);
+                  mma(d_tmem, ad + 2u, bd + 2u, 1u);
+                  mma(d_tmem, ad + 4u, bd + 4u, 1u);
+                  mma(d_tmem, ad + 6u, bd + 6u, 1u);
+                }
                 commit(empty20 + 8u * s2);
-                if (h == OPARTS - 1) commit(empty20 + 8u * ps);
-                if (j == nb - 1 && kc == 1 && h == OPARTS - 1) commit(p2done);
+                if (h == H2 - 1) commit(empty20 + 8u * ps);
+                if (j == nb - 1 && kc == 1 && h == H2 - 1) commit(p2done);
               }
               __syncwarp();
               advance2();

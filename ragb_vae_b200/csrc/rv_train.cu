@@ -636,7 +636,9 @@ static int gn_bwd_geometry(int64_t hw, int c, int groups, GnBwdGeom* g) {  // = 
   int rows = 256 / g->cpp;
   if (rows < 1) rows = 1;
   g->block = rows * g->cpp;
-  g->rows_per_block = (int64_t)rows * 64;
+  int64_t rpt = hw / ((int64_t)rows * 296);  // as gn_geometry: fewer rows per thread for small tensors
+  rpt = rpt > 64 ? 64 : (rpt < 8 ? 8 : rpt / 8 * 8);
+  g->rows_per_block = (int64_t)rows * rpt;
   g->blocks_x = (unsigned)((hw + g->rows_per_block - 1) / g->rows_per_block);
   return 0;
 }
