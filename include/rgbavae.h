@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 23
+#define RV_ABI_VERSION 24
 #define RV_PROF_CATEGORIES 10
 
 int rv_abi_version(void);
@@ -105,6 +105,18 @@ int rv_conv_out(const rv_conv_desc* d, const void* x, const void* w_taps, const 
 int rv_conv2d_tc_norm(const rv_conv_desc* d, const void* x, const void* w_packed, int64_t w_ld,
                       const float* bias, const void* residual, void* y, void* y_act,
                       const float* gamma_scaled, int apply_silu, void* stream);
+
+/* rv_conv2d_tc that also leaves the GroupNorm(groups = 32) statistics of its OUTPUT -- the [n][groups][2] fp64 (sum, sum of
+ * squares) rv_groupnorm_stats would compute from y, in the layout rv_groupnorm_silu reads -- so that the consumer's GroupNorm
+ * (norm1 / norm2 of diffusers' ResnetBlock2D inside vae.encode / vae.decode) needs no statistics pass over the tensor: the
+ * epilogue sums the values it stores per (tile, channel group), a finishing kernel adds a sample's tiles in a fixed order.
+ * Covers the CTA-pair implicit-GEMM layers with 256 / 512 output channels (NHWC bf16, per-channel bias, optional
+ * residual); rv_conv2d_tc_gnstats_scratch_bytes returns the device scratch it needs, or 0 where the layer is not covered
+ * (the caller then runs rv_conv2d_tc + rv_groupnorm_stats). */
+int64_t rv_conv2d_tc_gnstats_scratch_bytes(const rv_conv_desc* d, int groups);
+int rv_conv2d_tc_gnstats(const rv_conv_desc* d, const void* x, const void* w_packed, int64_t w_ld, const float* bias,
+                         const void* residual, void* y, int groups, double* stats, void* scratch, int64_t scratch_bytes,
+                         void* stream);
 
 /* Packs fp32 weights [cout][cin][ksize][ksize] (PyTorch layout; for the Qwen causal-conv3d
  * the caller passes the live temporal slice w[:, :, kt-1]) into the bf16 K-major matrix

@@ -9,7 +9,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "librgbavae.so")
 
 RV_F32, RV_BF16 = 0, 1
-ABI_VERSION = 23
+ABI_VERSION = 24
 PROF_CATEGORIES = 10
 PROF_NAMES = ("conv_tc", "conv_direct", "norm_silu", "softmax", "layout", "reparam", "recon_loss", "composite_psnr",
               "attention", "conv_tc_upsample")
@@ -54,6 +54,8 @@ SIGNATURES = {
     "rv_conv2d_tc": (_I, [C.POINTER(ConvDesc), _P, _P, _L, _P, _P, _P, _P]),
     "rv_conv_out": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P]),
     "rv_conv2d_tc_norm": (_I, [C.POINTER(ConvDesc), _P, _P, _L, _P, _P, _P, _P, _P, _I, _P]),
+    "rv_conv2d_tc_gnstats_scratch_bytes": (_L, [C.POINTER(ConvDesc), _I]),
+    "rv_conv2d_tc_gnstats": (_I, [C.POINTER(ConvDesc), _P, _P, _L, _P, _P, _P, _I, _P, _P, _L, _P]),
     "rv_pack_conv_weights": (_I, [_P, _I, _I, _I, _I, _P, C.POINTER(C.c_int64), _P]),
     "rv_pack_conv_weights_direct": (_I, [_P, _I, _I, _I, _P, _P]),
     "rv_rmsnorm_silu": (_I, [_P, _P, _P, _L, _I, _I, _I, _P]),

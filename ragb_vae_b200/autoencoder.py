@@ -234,10 +234,11 @@ def _build_qwen(in_ch, out_ch, base, z_dim, dim_mult, num_res_blocks, t_down):
 class _Stream:
     """The residual stream between blocks: the raw tensor and, when the producing conv could fuse it, the
     already normalised + activated copy for the consumer identified by ``act_key = (id(norm), silu)``."""
-    __slots__ = ("raw", "act", "act_key")
+    __slots__ = ("raw", "act", "act_key", "gn_stats")
 
-    def __init__(self, raw, act=None, act_key=None):
+    def __init__(self, raw, act=None, act_key=None, gn_stats=None):
         self.raw, self.act, self.act_key = raw, act, act_key
+        self.gn_stats = gn_stats  # (groups, [N, groups, 2] fp64 sums of ``raw``) when the producing conv's epilogue left them
 
 
 class AutoencoderKLOutput(SimpleNamespace):
@@ -333,6 +334,7 @@ class RgbaAutoencoder(nn.Module):
         self.fused_attention = True
         self.hpack_stem = True    # conv_in as 3 vertical taps over a horizontally packed 16-channel image (see _stem)
         self.fuse_norm = True  # RMS norm + SiLU in the producing conv's epilogue where one tile holds all channels
+        self.fuse_gn_stats = True  # GroupNorm statistics out of the producing conv's epilogue (256 / 512-channel layers)
         self._pack_cache: Dict[tuple, tuple] = {}
         self.weights_generation = 0
         self.requires_grad_(False)
@@ -593,6 +595,13 @@ class RgbaAutoencoder(nn.Module):
                                      lambda: (norm.gamma.detach().to(torch.float32).reshape(-1) * math.sqrt(cout)).contiguous())
                 ops.conv2d_tc_norm(desc, x, wp, wp.shape[1], bias, residual, y, act, gamma, silu)
                 return _Stream(y, act, (id(norm), silu))
+            if (self.fuse_gn_stats and next_norm is not None and isinstance(next_norm[0], GroupNorm) and not y_nchw
+                    and y_dt == torch.bfloat16 and not upsample and not hpack):
+                # the consumer is a GroupNorm: its statistics come out of this conv's epilogue where the layer has that form
+                groups = int(next_norm[0].num_groups)
+                stats = ops.conv2d_tc_gnstats(desc, x, wp, wp.shape[1], bias, residual, y, groups)
+                if stats is not None:
+                    return _Stream(y, None, None, (groups, stats))
             ops.conv2d_tc(desc, x, wp, wp.shape[1], bias, residual, y)
         else:
             wp = self._conv_weights(conv, False)
@@ -603,13 +612,16 @@ class RgbaAutoencoder(nn.Module):
         """act(norm(stream)): the fused copy if the producer already wrote it for this norm, else the norm kernel."""
         if st.act is not None and st.act_key == (id(norm), silu):
             return st.act
-        return self._norm(st.raw, norm, silu)
+        stats = None
+        if st.gn_stats is not None and not isinstance(norm, RMSNorm) and st.gn_stats[0] == norm.num_groups:
+            stats = st.gn_stats[1]
+        return self._norm(st.raw, norm, silu, stats=stats)
 
-    def _norm(self, x: torch.Tensor, norm, silu: bool = True) -> torch.Tensor:
+    def _norm(self, x: torch.Tensor, norm, silu: bool = True, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
         if isinstance(norm, RMSNorm):
             return ops.rmsnorm_silu(x, self._f32(norm.gamma, "gamma"), silu)
         return ops.groupnorm_silu(x, self._f32(norm.weight, "gn_w"), self._f32(norm.bias, "gn_b"), norm.num_groups, norm.eps,
-                                  silu)
+                                  silu, stats=stats)
 
     def _resblock(self, st: "_Stream", blk, next_norm=None) -> "_Stream":
         """h = shortcut(x); x = conv2(act(norm2(conv1(act(norm1(x)))))) + h   (diffusers ResnetBlock2D /

@@ -270,8 +270,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 //   * the peer's epilogue warps release the accumulator on the leader's barrier through a remote mbarrier arrive;
 //   * TMEM is allocated / freed with the cta_group::2 forms; cluster barriers fence set-up and tear-down.
 // ---------------------------------------------------------------------------------------
-// RS: 0, or the row-statistic mode (1 / 2) of rv_gemm_rowstat's lean epilogue -- its own instantiations, so that the 64 registers
-// of prefetched multiplicand never weigh on the convolutions' epilogue
+// RS: 0, or the row-statistic mode (1 / 2) of rv_gemm_rowstat's lean epilogue, or 3: the GroupNorm statistics of the output
+// (rv_conv2d_tc_gnstats) -- their own instantiations, so that the 64 registers of prefetched multiplicand / the group sums
+// never weigh on the convolutions' epilogue
 template <int KSTEPS, int RS = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -431,12 +432,25 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int oy = ty * p.osy + p.ooy, ox = tx * p.osx + p.oox;
       const int64_t pix = ((int64_t)t.img * p.e.out_h + oy) * p.e.out_w + ox;
       RowstatPrefetch pf;
-      if (RS) rowstat_prefetch<RS>(p.e, cb, ce, t.n0, valid, pix, pf);
+      if (RS == 1 || RS == 2) rowstat_prefetch<(RS == 2 ? 2 : 1)>(p.e, cb, ce, t.n0, valid, pix, pf);
       mbar_wait(bar_accf0 + 8u * (uint32_t)acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
-      if (RS) {
-        epilogue_pixel_rowstat<RS ? RS : 1>(p.e, taddr, cb, ce, t.n0, valid, pix, pf);
+      if (RS == 1 || RS == 2) {
+        epilogue_pixel_rowstat<(RS == 2 ? 2 : 1)>(p.e, taddr, cb, ce, t.n0, valid, pix, pf);
+      } else if (RS == 3) {
+        // this warp's 32 floats of this tile: [tile][half * 4 + q][lane]
+        float* part = p.e.gn_part + ((int64_t)(m_tile * p.n_tiles + nt) * 8 + half * 4 + q) * 32;
+        const bool res = p.e.residual != nullptr;
+        if (m_tile < p.m_tiles) {
+          if (p.e.gn_gs == 8) {
+            if (res) epilogue_pixel_gnstats<8, 4, true>(p.e, sbias, taddr, cb, t.n0, valid, pix, part, lane);
+            else epilogue_pixel_gnstats<8, 4, false>(p.e, sbias, taddr, cb, t.n0, valid, pix, part, lane);
+          } else {
+            if (res) epilogue_pixel_gnstats<16, 4, true>(p.e, sbias, taddr, cb, t.n0, valid, pix, part, lane);
+            else epilogue_pixel_gnstats<16, 4, false>(p.e, sbias, taddr, cb, t.n0, valid, pix, part, lane);
+          }
+        }
       } else if (p.e.fast == 1) {
         if (p.e.residual)
           epilogue_pixel_fast<true>(p.e, sbias, s_gamma, taddr, cb, ce, t.n0, valid, pix, &s_ss[acc][0][0], row, half, nsplit,
@@ -498,6 +512,7 @@ int tc_ensure_init() {
     RV_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 2048)));
     RV_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 2048)));
     RV_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 2048)));
+    RV_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_BUDGET + 2048)));
     g_attr_set[dev] = true;
   }
   return 0;
@@ -577,6 +592,8 @@ void fill_epi(EpiParams* e, const rv_conv_desc* d, const float* bias, const void
   e->fast = 0;  // decided by the launcher once the N tiling is known
   e->rowstat = nullptr;
   e->rowstat_mode = 0;
+  e->gn_part = nullptr;
+  e->gn_gs = 0;
   e->vec_ok = (d->y_cstride % 8 == 0) && (!y || (uintptr_t)y % 16 == 0) && (!residual || (uintptr_t)residual % 16 == 0) &&
               (!nf || (uintptr_t)nf->y_act % 16 == 0);
 }
@@ -595,7 +612,7 @@ int launch_halo(const rv_conv_desc* d, const void* x, const void* w, int64_t w_l
 
 static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_t w_ld, const float* bias,
                      const void* residual, void* y, cudaStream_t st, int phase /* -1: not upsample */,
-                     const NormFuse* nf = nullptr, const RowStat* rs = nullptr) {
+                     const NormFuse* nf = nullptr, const RowStat* rs = nullptr, float* gn_part = nullptr, int gn_gs = 0) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.n_img = d->n;
@@ -708,11 +725,17 @@ static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_
   const double flops = 2.0 * (double)d->n * d->oh * d->ow * d->cout * d->cin * d->ksize * (d->taps_1d ? 1 : d->ksize) / (phase >= 0 ? 4.0 : 1.0);
   LaunchScope scope(phase >= 0 ? CAT_CONV_UPS : CAT_CONV_TC, st, flops);
   if (!pair && p.e.fast == 2) p.e.fast = 0;
+  if (gn_part) {
+    RV_CHECK_ARG(pair && p.bk == 64 && p.e.fast == 1 && !nf && !rs, "conv_tc gnstats: layer not eligible");
+    p.e.gn_part = gn_part;
+    p.e.gn_gs = gn_gs;
+  }
   if (pair) {
     const int total_pt = ((p.m_tiles + 1) / 2) * p.n_tiles;
     const int max_pairs = num_sms() / 2;
     const int grid = 2 * (total_pt < max_pairs ? total_pt : max_pairs);
-    if (p.e.fast == 2 && p.e.rowstat_mode == 1) conv_tc2_kernel<4, 1><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+    if (gn_part) conv_tc2_kernel<4, 3><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+    else if (p.e.fast == 2 && p.e.rowstat_mode == 1) conv_tc2_kernel<4, 1><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
     else if (p.e.fast == 2) conv_tc2_kernel<4, 2><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
     else if (p.bk == 64) conv_tc2_kernel<4><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
     else conv_tc2_kernel<2><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
@@ -725,6 +748,71 @@ static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_
   }
   RV_LAUNCH_CHECK();
   return 0;
+}
+
+// Sums the per-tile partials conv_tc2_kernel<4, 3> left (epilogue_pixel_gnstats) into the [n][groups][2] fp64 (sum, sum of
+// squares) rv_groupnorm_silu reads.  Block = (group, sample); fixed summation order.
+__global__ void __launch_bounds__(128) gn_finish_kernel(const float* __restrict__ part, double* __restrict__ stats, int tpi,
+                                                       int n_tiles, int bn, int gs, int lane_step, int groups) {
+  __shared__ double red[2][4];
+  const int G = blockIdx.x, n = blockIdx.y;
+  const int ch0 = G * gs;
+  const int nt = ch0 / bn, col = ch0 - nt * bn;
+  const int half = col / (bn / 2);
+  const int g_local = (col - half * (bn / 2)) / gs;
+  const int lane_s = 2 * g_local * lane_step, lane_q = (2 * g_local + 1) * lane_step;
+  double sa = 0.0, sq = 0.0;
+  for (int i = threadIdx.x; i < tpi * 4; i += 128) {
+    const int mt = n * tpi + (i >> 2), q = i & 3;
+    const float* w = part + (((int64_t)mt * n_tiles + nt) * 8 + half * 4 + q) * 32;
+    sa += (double)w[lane_s];
+    sq += (double)w[lane_q];
+  }
+  for (int o = 16; o >= 1; o >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = sa;
+    red[1][threadIdx.x >> 5] = sq;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    stats[((int64_t)n * groups + G) * 2] = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+    stats[((int64_t)n * groups + G) * 2 + 1] = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+  }
+}
+
+// tiling of a layer as launch_tc would choose it, and whether the statistics epilogue covers it; 0 or the scratch bytes
+static int64_t gnstats_geometry(const rv_conv_desc* d, int groups, int* tpi, int* n_tiles, int* bn, int* gs, int* lane_step) {
+  if (groups != 32 || d->upsample || d->y_nchw || d->y_dtype != RV_BF16 || d->x_dtype != RV_BF16 || d->cout % groups) return 0;
+  if (d->taps_1d || d->bias_mode != 1 || d->alpha != 1.0f || d->out_scale != 1.0f || d->out_shift != 0.0f || d->clamp) return 0;
+  const int bk = (d->cin % 64 == 0 || (d->cin > 64 && d->stride == 1)) ? 64 : 0;
+  if (bk != 64 || d->cout % 16 || d->y_cstride != d->cout) return 0;
+  int bw, bh, b, t;
+  choose_tile(d->oh, d->ow, &bw, &bh);
+  const int tx = (d->ow + bw - 1) / bw, ty = (d->oh + bh - 1) / bh;
+  choose_bn(d->cout, &b, &t);
+  if (b * t != d->cout || b % 64 || d->n * tx * ty < 2) return 0;
+  const int g = d->cout / groups;
+  const int nst = b / 2 / 32;  // 32-column steps per epilogue warp
+  // 256 / 512 output channels.  (128: measured a small net loss -- N = 128 layers are paced by their epilogue, 256 -> 128 @1024^2
+  // 2.44 -> 2.73 ms for 0.23 ms of statistics pass saved -- so those keep the stand-alone pass.)
+  if (!((g == 8 && nst == 4) || (g == 16 && nst == 4))) return 0;
+  {  // the halo kernel takes the narrow full-resolution layers: its epilogue has no statistics form
+    EpiParams e;
+    fill_epi(&e, d, (const float*)16, nullptr, (void*)16, nullptr);
+    e.fast = 1;
+    static const bool no_halo = getenv("RGBAVAE_DISABLE_HALO") != nullptr;
+    if (!no_halo && halo_eligible(d, e)) return 0;
+  }
+  *tpi = tx * ty;
+  *n_tiles = t;
+  *bn = b;
+  *gs = g;
+  *lane_step = 32 / (2 * nst * (32 / g));
+  const int64_t m_tiles = (int64_t)d->n * tx * ty;
+  return ((m_tiles + 1) / 2 * 2) * t * 8 * 32 * (int64_t)sizeof(float);
 }
 
 // fp32 [cout][cin][k][k] -> bf16 [cout][taps][cin]  (upsample: [cout][4 phases][4 taps][cin], folded)
@@ -812,6 +900,34 @@ int rv_conv2d_tc_norm(const rv_conv_desc* d, const void* x, const void* w_packed
                       const void* residual, void* y, void* y_act, const float* gamma_scaled, int apply_silu, void* stream) {
   rv::NormFuse nf{gamma_scaled, y_act, apply_silu};
   return conv2d_tc_impl(d, x, w_packed, w_ld, bias, residual, y, stream, &nf);
+}
+
+int64_t rv_conv2d_tc_gnstats_scratch_bytes(const rv_conv_desc* d, int groups) {
+  if (!d || rv::check_conv_desc(d)) return 0;
+  int tpi, n_tiles, bn, gs, lane_step;
+  return rv::gnstats_geometry(d, groups, &tpi, &n_tiles, &bn, &gs, &lane_step);
+}
+
+int rv_conv2d_tc_gnstats(const rv_conv_desc* d, const void* x, const void* w_packed, int64_t w_ld, const float* bias,
+                         const void* residual, void* y, int groups, double* stats, void* scratch, int64_t scratch_bytes,
+                         void* stream) {
+  if (int rc = rv::check_conv_desc(d)) return rc;
+  if (int rc = rv::tc_ensure_init()) return rc;
+  int tpi, n_tiles, bn, gs, lane_step;
+  const int64_t need = rv::gnstats_geometry(d, groups, &tpi, &n_tiles, &bn, &gs, &lane_step);
+  RV_CHECK_ARG(need > 0, "conv2d_tc_gnstats: this layer has no statistics epilogue (rv_conv2d_tc_gnstats_scratch_bytes returned 0)");
+  RV_CHECK_ARG(x && w_packed && y && bias && stats && scratch && scratch_bytes >= need && (uintptr_t)scratch % 128 == 0,
+               "conv2d_tc_gnstats: null tensor or scratch smaller than %lld bytes", (long long)need);
+  RV_CHECK_ARG(d->cin % 16 == 0 && d->x_cstride % 8 == 0 && w_ld % 8 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)w_packed % 16 == 0) &&
+                   (uintptr_t)bias % 16 == 0 && d->in_scale == 1.0f && d->in_shift == 0.0f,
+               "conv2d_tc_gnstats: operand alignment / layout as for rv_conv2d_tc");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = rv::launch_tc(d, x, w_packed, w_ld, bias, residual, y, st, -1, nullptr, nullptr, (float*)scratch, gs)) return rc;
+  rv::LaunchScope scope(rv::CAT_NORM, st, (double)need);
+  rv::gn_finish_kernel<<<dim3((unsigned)groups, (unsigned)d->n), 128, 0, st>>>((const float*)scratch, stats, tpi, n_tiles, bn, gs, lane_step,
+                                                                            groups);
+  RV_LAUNCH_CHECK();
+  return 0;
 }
 
 int rv_gemm_rowstat(const rv_conv_desc* d, const void* x, const void* w, int64_t w_ld, const float* rowstat, int mode,

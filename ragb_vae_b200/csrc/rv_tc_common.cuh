@@ -234,6 +234,9 @@ struct EpiParams {
   //   2: y = residual * (alpha * acc - rowstat[row])       dS = P * (dP - delta) * scale (residual holds P)
   const float* rowstat;
   int rowstat_mode;
+  // GroupNorm statistics of the output (rv_conv2d_tc_gnstats): per-tile partial sums, [tile][8 epilogue warps][32] floats
+  float* gn_part;
+  int gn_gs;                 // channels per group
 };
 
 // optional per-row statistic (host-side description; see EpiParams::rowstat_mode)
@@ -628,6 +631,73 @@ __device__ __forceinline__ void epilogue_pixel_rowstat(const EpiParams& e, uint3
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// GroupNorm statistics of a conv's OUTPUT from its epilogue (rv_conv2d_tc_gnstats): the lean plain epilogue, plus per
+// (pixel, channel group) sum and sum of squares of the values it stores, folded over the warp's 32 pixels by a
+// transpose-reduction (V values on every lane -> lane l holds the total of value l / (32 / V): 31 shuffles for V = 32
+// instead of 160) and written as the warp's 32 floats of this tile.  A finishing kernel adds the tiles of a sample in a fixed
+// order (fp64): deterministic, and independent of the batch the sample is in.
+// GS = channels per group (C / 32); NST = 32-column steps of the warp's column range; V = 2 * NST * 32 / GS <= 32.
+// vals[2 * g + stat] with g counting groups from the warp's first column.
+// ---------------------------------------------------------------------------------------
+template <int V>
+__device__ __forceinline__ float warp_transpose_reduce(float (&vals)[V], int lane) {
+  static_assert(V == 8 || V == 16 || V == 32, "V must be 8, 16 or 32");
+  int n = V;
+#pragma unroll
+  for (int mask = 16; mask >= 1; mask >>= 1) {
+    if (n > 1) {
+      n >>= 1;
+      const bool up = (lane & mask) != 0;
+#pragma unroll
+      for (int i = 0; i < V / 2; ++i) {
+        if (i < n) {
+          const float send = up ? vals[i] : vals[i + n];
+          const float keep = up ? vals[i + n] : vals[i];
+          vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+        }
+      }
+    } else {
+      vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], mask);
+    }
+  }
+  return vals[0];
+}
+
+template <int GS, int NST, bool RES>
+__device__ __forceinline__ void epilogue_pixel_gnstats(const EpiParams& e, const float* sbias, uint32_t taddr, int cb, int n0,
+                                                       bool valid, int64_t pix, float* part, int lane) {
+  constexpr int GP = 32 / GS;       // groups per 32-column step
+  constexpr int V = 2 * NST * GP;
+  float vals[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) vals[i] = 0.f;
+#pragma unroll
+  for (int st = 0; st < NST; ++st) {
+    const int c0 = cb + 32 * st;
+    FastStep<32, RES> fs;
+    fs.load(e, taddr + (uint32_t)c0, n0 + c0, pix, valid);
+    if (valid) {
+      float v[32];
+      fs.values(sbias, n0 + c0, v);
+      fast_store<32>(reinterpret_cast<__nv_bfloat16*>(e.y) + pix * e.y_cstride + n0 + c0, v);
+#pragma unroll
+      for (int g = 0; g < GP; ++g) {
+        float sa = 0.f, sq = 0.f;
+#pragma unroll
+        for (int k = 0; k < GS; ++k) {
+          sa += v[g * GS + k];
+          sq = fmaf(v[g * GS + k], v[g * GS + k], sq);
+        }
+        vals[2 * (st * GP + g)] = sa;
+        vals[2 * (st * GP + g) + 1] = sq;
+      }
+    }
+  }
+  const float tot = warp_transpose_reduce<V>(vals, lane);
+  part[lane] = tot;
 }
 
 }  // namespace rv

@@ -97,6 +97,29 @@ def conv2d_tc(desc: ConvDesc, x, w_packed, w_ld: int, bias, residual, y) -> None
                                    _stream(x)), "rv_conv2d_tc")
 
 
+_GN_SCRATCH: dict = {}
+
+
+def conv2d_tc_gnstats(desc: ConvDesc, x, w_packed, w_ld: int, bias, residual, y, groups: int = 32):
+    """conv2d_tc whose epilogue also leaves the GroupNorm statistics of y: returns the [N, groups, 2] fp64 (sum, sum of
+    squares) tensor ``groupnorm_silu(..., stats=)`` takes, or None where the layer has no statistics epilogue (nothing is
+    launched then: the caller runs ``conv2d_tc``)."""
+    _need_cuda(x, w_packed, bias, residual, y)
+    lib = _lib.load()
+    need = int(lib.rv_conv2d_tc_gnstats_scratch_bytes(C.byref(desc), int(groups)))
+    if need == 0 or bias is None:
+        return None
+    key = (x.device.index, torch.cuda.current_stream(x.device).cuda_stream)
+    scratch = _GN_SCRATCH.get(key)
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty((need,), dtype=torch.uint8, device=x.device)
+        _GN_SCRATCH[key] = scratch
+    stats = torch.empty((desc.n, groups, 2), dtype=torch.float64, device=x.device)
+    check(lib.rv_conv2d_tc_gnstats(C.byref(desc), _ptr(x), _ptr(w_packed), int(w_ld), _ptr(bias), _ptr(residual), _ptr(y),
+                                   int(groups), _ptr(stats), _ptr(scratch), scratch.numel(), _stream(x)), "rv_conv2d_tc_gnstats")
+    return stats
+
+
 def conv_out(desc: ConvDesc, x, w_taps, bias, y) -> None:
     """The decoder's conv_out (3x3, 64/96/128 -> <= 5 channels, NCHW output) on its HBM-bound kernel (rv_conv_out)."""
     _need_cuda(x, w_taps, bias, y)
@@ -164,15 +187,19 @@ def rmsnorm_silu(x: torch.Tensor, gamma: torch.Tensor, silu: bool = True, out: O
 
 
 def groupnorm_silu(x: torch.Tensor, gamma, beta, groups: int = 32, eps: float = 1e-6, silu: bool = True,
-                   out: Optional[torch.Tensor] = None, return_stats: bool = False):
+                   out: Optional[torch.Tensor] = None, return_stats: bool = False, stats: Optional[torch.Tensor] = None):
     """x: [N, H, W, C] (or [N, HW, C]) NHWC-dense.  ``return_stats``: also the [N, groups, 2] fp64 (sum, sum of squares)
-    the backward pass needs."""
-    _need_cuda(x, gamma, beta)
+    the backward pass needs.  ``stats``: those sums if the producer of x already has them (``conv2d_tc_gnstats``): the
+    statistics pass over x is skipped."""
+    _need_cuda(x, gamma, beta, stats)
     n, c = x.shape[0], x.shape[-1]
     hw = x.numel() // (n * c)
-    stats = torch.empty((n, groups, 2), dtype=torch.float64, device=x.device)
     lib = _lib.load()
-    check(lib.rv_groupnorm_stats(_ptr(x), _ptr(stats), n, hw, c, groups, _dt(x), _stream(x)), "rv_groupnorm_stats")
+    if stats is None:
+        stats = torch.empty((n, groups, 2), dtype=torch.float64, device=x.device)
+        check(lib.rv_groupnorm_stats(_ptr(x), _ptr(stats), n, hw, c, groups, _dt(x), _stream(x)), "rv_groupnorm_stats")
+    elif tuple(stats.shape) != (n, groups, 2) or stats.dtype != torch.float64 or not stats.is_contiguous():
+        raise ValueError(f"groupnorm_silu: stats must be a contiguous float64 [{n}, {groups}, 2] tensor")
     y = torch.empty_like(x) if out is None else out
     check(lib.rv_groupnorm_silu(_ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(y), n, hw, c, groups, eps, _dt(x),
                                 int(silu), _stream(x)), "rv_groupnorm_silu")

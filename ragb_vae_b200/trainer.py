@@ -79,12 +79,14 @@ class VaeTrainStep:
     def _norm(self, x, norm, silu=True):
         return self.vae._norm(x, norm, silu)
 
-    def _norm_fwd(self, x, norm, silu=True):
-        """-> (act(norm(x)), what the backward needs besides x: the GroupNorm statistics, or None for the RMS norm)."""
+    def _norm_fwd(self, x, norm, silu=True, stats=None):
+        """-> (act(norm(x)), what the backward needs besides x: the GroupNorm statistics, or None for the RMS norm).
+        ``stats``: (groups, sums) when the conv that produced x left them (``_Stream.gn_stats``)."""
         if self.flux:
             v = self.vae
+            pre = stats[1] if stats is not None and stats[0] == norm.num_groups else None
             return ops.groupnorm_silu(x, v._f32(norm.weight, "gn_w"), v._f32(norm.bias, "gn_b"), norm.num_groups, norm.eps, silu,
-                                      return_stats=True)
+                                      return_stats=True, stats=pre)
         return self.vae._norm(x, norm, silu), None
 
     def _norm_bwd(self, norm, x, dy, silu=True, add=None, aux=None):
@@ -133,7 +135,7 @@ class VaeTrainStep:
         if st.act is not None:
             b = st.act
         else:
-            b, s2 = self._norm_fwd(t, blk.norm2)
+            b, s2 = self._norm_fwd(t, blk.norm2, stats=st.gn_stats)
         y = self._conv(b, blk.conv2, residual=h)
         if tape is not None:
             # gradient checkpointing (diffusers: per block): keep only the block input, recompute the rest in the backward
@@ -150,7 +152,7 @@ class VaeTrainStep:
             if st.act is not None:
                 b = st.act
             else:
-                b, s2 = self._norm_fwd(t, blk.norm2)
+                b, s2 = self._norm_fwd(t, blk.norm2, stats=st.gn_stats)
         db = self._conv_bwd(blk.conv2, b, dy)
         dt = self._norm_bwd(blk.norm2, t, db, aux=s2)
         da = self._conv_bwd(blk.conv1, a, dt)

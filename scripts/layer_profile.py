@@ -38,6 +38,14 @@ def d_sm(s, dt):
 
 ops.conv2d_tc = wrap("conv_tc", ops.conv2d_tc, d_conv)
 ops.conv2d_tc_norm = wrap("conv_tc+norm", ops.conv2d_tc_norm, d_conv)
+_gn_inner = wrap("conv_tc+gnst", ops.conv2d_tc_gnstats, d_conv)
+def _gnstats(*a, **k):
+    n = len(recs)
+    out = _gn_inner(*a, **k)
+    if out is None:      # layer without a statistics epilogue: nothing was launched
+        del recs[n:]
+    return out
+ops.conv2d_tc_gnstats = _gnstats
 ops.conv_out = wrap("conv_out", ops.conv_out, d_conv)
 ops.attention = wrap("attention", ops.attention, lambda q, k, vt, n, t: dict(shape=f"n{n} tokens {t} d{vt.shape[1]}", flops=4.0 * n * t * t * vt.shape[1]))
 ops.conv2d_direct = wrap("conv_direct", ops.conv2d_direct, d_conv)
