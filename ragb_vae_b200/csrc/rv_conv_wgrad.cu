@@ -13,6 +13,7 @@
 // TMA ring and adds the tiles to dW with fp32 atomics (split-K over pixels; the bias gradient = column sums of dY rides along as
 // one more N = 16 MMA against a tile of ones); dW is addressed through three strides so
 // the gradient lands directly in the parameter's own layout.  Warps: 0 TMA, 1 / 6 / 7 MMA (one per tap), 2-5 epilogue.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -39,6 +40,11 @@ struct WgParams {
   long long s_co, s_ci, s_tap;
   int stages;
   uint32_t stage_bytes, tx_bytes, tmem_cols;
+  int tapn;       // 1 (ksize 3, bn = 128): ONE N = 192 MMA covers the three taps of a 64-channel block of X -- the taps are the same
+                  // box one pixel row (128 B) apart, so they are consecutive "MN blocks" of a descriptor whose LBO is 128 B.
+                  // Two issuers (one per channel block) instead of three (one per tap): 8 MMAs reading 10 KB of operands each
+                  // per K block instead of 12 reading 8 KB -- the shared-memory port is what paces these MMAs.
+                  // Accumulator columns: [block][tap][64 channels].
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -71,7 +77,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   const int num_kb = max(0, row_hi - row_lo) * p.x_blocks;
 
   const bool do_bias = p.dbias != nullptr && ty == 0 && ci_t == 0;
-  const uint32_t issuers = (uint32_t)p.ksize + (do_bias ? 1u : 0u);
+  const int n_issue = p.tapn ? 2 : p.ksize;  // tap issuers (tapn: channel-block issuers)
+  const uint32_t issuers = (uint32_t)n_issue + (do_bias ? 1u : 0u);
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
@@ -123,26 +130,28 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     // one issuer left the pipe 54 % idle at N = 96; independent instruction streams overlap that cost.
     const int tx = warp == 1 ? 0 : warp - 5;   // 3: the bias issuer
     const bool bias_warp = tx == 3;
-    if (tx < p.ksize || (bias_warp && do_bias)) {
-      // D fp32, A/B bf16, both MN-major (bits 15, 16), N = bn, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.bn >> 3) << 17) |
-                             ((128u >> 4) << 24);
-      // MN-major SW128 descriptors: LBO = distance between 64-element MN blocks (one box), SBO = 8 K-rows = 1024 B
+    if (tx < n_issue || (bias_warp && do_bias)) {
+      // D fp32, A/B bf16, both MN-major (bits 15, 16), N = bn (tapn: 192 = three taps of one 64-channel block), M = 128
+      const uint32_t n_mma = p.tapn ? 192u : (uint32_t)p.bn;
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((n_mma >> 3) << 17) | ((128u >> 4) << 24);
+      // MN-major SW128 descriptors: LBO = distance between 64-element MN blocks (one box; tapn: one pixel row, i.e. the next
+      // tap of the same box), SBO = 8 K-rows = 1024 B
       uint64_t hi_a = 0, hi_b = 0;
       hi_a |= (uint64_t)(WG_A_BOX >> 4) << 16;
-      hi_b |= (uint64_t)(WG_B_BOX >> 4) << 16;
+      hi_b |= (uint64_t)((p.tapn ? 128u : WG_B_BOX) >> 4) << 16;
       hi_a |= (uint64_t)(1024u >> 4) << 32;
       hi_b |= (uint64_t)(1024u >> 4) << 32;
       hi_a |= ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
       hi_b |= ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-      const uint32_t d_tmem = tmem_base + (uint32_t)(tx * p.bn);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(p.tapn ? tx * 192 : tx * p.bn);
       // bias gradient (its own issuer, so that its ~46 cycles per MMA overlap the taps'): D[co][0..15] += dY^T . ones
       const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t d_bias = tmem_base + (uint32_t)(p.ksize * p.bn);
+      const uint32_t d_bias = tmem_base + (uint32_t)(p.tapn ? 384 : p.ksize * p.bn);
       const uint64_t ones_d = hi_a | (uint64_t)(((smem_base + p.ones_off) & 0x3FFFFu) >> 4);
       const uint32_t stage_lo = p.stage_bytes >> 4;
       const uint32_t a_lo0 = (smem_base & 0x3FFFFu) >> 4;
-      const uint32_t b_off = (a_bytes >> 4) + (uint32_t)tx * 8u;  // tap tx starts tx pixel rows (128 B) into the X box
+      // tap tx starts tx pixel rows (128 B) into the X box; tapn: channel block tx is the tx-th box
+      const uint32_t b_off = (a_bytes >> 4) + (p.tapn ? (uint32_t)tx * (WG_B_BOX >> 4) : (uint32_t)tx * 8u);
       uint32_t stage = 0, phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full0 + 8u * stage, phase);
@@ -179,7 +188,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
       float* out = p.dw + (long long)co * p.s_co + (long long)(ty * p.ksize + tx) * p.s_tap;
       for (int c0 = 0; c0 < p.bn; c0 += 16) {
         uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)(tx * p.bn + c0), r);
+        tmem_ld16(taddr + (uint32_t)(p.tapn ? (c0 >> 6) * 192 + tx * 64 + (c0 & 63) : tx * p.bn + c0), r);
         tmem_ld_wait();
         if (co < p.cout_valid) {
 #pragma unroll
@@ -190,7 +199,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     }
     if (do_bias) {
       uint32_t r[16];
-      tmem_ld16(taddr + (uint32_t)(p.ksize * p.bn), r);
+      tmem_ld16(taddr + (uint32_t)(p.tapn ? 384 : p.ksize * p.bn), r);
       tmem_ld_wait();
       if (co < p.cout_valid) atomicAdd(p.dbias + co, __uint_as_float(r[0]));
     }
@@ -269,6 +278,8 @@ extern "C" int rv_conv2d_wgrad(const void* x, const void* dy, float* dw, int64_t
   // split, 0.97 -> 1.10 PFLOP/s incl. the bias), a loss where they are a third of them (96 / 192 channels: the extra work
   // unbalances the grid) -- there a separate streaming pass over dY (colsum_kernel) is cheaper.
   const bool fuse_bias = dbias != nullptr && ksize * p.co_tiles * p.ci_tiles >= 9;
+  static const bool no_tapn = getenv("RGBAVAE_WGRAD_NO_TAPN") != nullptr;
+  p.tapn = (!no_tapn && ksize == 3 && p.bn == 128) ? 1 : 0;
   while ((int)p.tmem_cols < ksize * p.bn + (fuse_bias ? 16 : 0)) p.tmem_cols <<= 1;
   const int tiles = ksize * p.co_tiles * p.ci_tiles;
   const int total_rows = n * h;

@@ -111,7 +111,9 @@ def test_flat_adamw_matches_torch(T):
 
 
 @pytest.mark.parametrize("n,h,w,cin,cout,k", [(1, 8, 64, 64, 64, 3), (2, 12, 136, 96, 96, 3), (1, 16, 70, 192, 96, 3),
-                                              (2, 9, 64, 96, 192, 1), (1, 8, 128, 384, 384, 3)])
+                                              (2, 9, 64, 96, 192, 1), (1, 8, 128, 384, 384, 3),
+                                              # Cin tiles of 128: one N = 192 MMA per 64-channel block covers the three taps
+                                              (2, 10, 72, 128, 128, 3), (1, 6, 64, 256, 512, 3), (1, 7, 200, 512, 256, 3)])
 def test_conv_wgrad_matches_autograd(T, n, h, w, cin, cout, k):
     g = torch.Generator().manual_seed(n + h + w + cin + cout)
     x = torch.randn(n, cin, h, w, generator=g).bfloat16().float()
