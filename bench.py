@@ -550,7 +550,8 @@ def c4_arm(cx: Ctx, a, steps=None):
                                    "and conv_wgrad_kernel")
     lim = max(range(len(exposed_max)), key=lambda i: exposed_max[i]) if exposed_max else None
     comm = {"collective": "NCCL all-reduce (SUM) of the flat fp32 gradient, one per bucket, issued between the CUDA-graph replays "
-                          "(decoder buckets right after graph 1, so they overlap the encoder's backward in graph 2)",
+                          "(decoder buckets right after graph 1, the deep encoder stages' after graph 2, so they overlap the rest of the backward; "
+                          "only the small shallow-encoder bucket is issued after the last graph)",
             "bytes_per_step_per_rank": nbytes, "bucket_bytes": buckets, "world": world,
             "join_order_buckets": order, "exposed_ms_per_join": exposed_max,
             "exposed_ms_total": sum(exposed_max) if exposed_max else 0.0,

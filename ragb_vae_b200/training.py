@@ -255,10 +255,12 @@ class GradientAllReducer:
     (SUM) asynchronously as soon as it is marked ready, and ``wait`` joins them before the optimizer step.  On the GPUs
     this is one NCCL all-reduce per bucket over NVLink/NVSwitch; the division by the world size is fused into AdamW."""
 
-    def __init__(self, flat_grad: torch.Tensor, num_buckets: int = 4, group=None, boundary: Optional[int] = None):
-        """``boundary``: offset in the flat buffer where the parameters whose gradients come FIRST in the backward pass
-        begin (the decoder side of a VAE).  Bucket edges then never straddle it: [boundary, n) and [0, boundary) are cut
-        separately, in proportion to their sizes, so every late-side bucket can start before the early side's backward."""
+    def __init__(self, flat_grad: torch.Tensor, num_buckets: int = 4, group=None, boundary=None):
+        """``boundary``: offset(s) in the flat buffer where a group of parameters begins whose gradients are complete EARLIER
+        in the backward pass than those before it -- for a VAE the decoder side, or [deep encoder, decoder] (ascending).
+        Bucket edges never straddle a boundary: the segments are cut separately (last segment first), every segment gets
+        at least one bucket and the rest go in proportion to the sizes, so each segment's buckets can start as soon as its
+        part of the backward is done."""
         self.grad, self.group = flat_grad, group
         n = flat_grad.numel()
         num_buckets = max(1, min(num_buckets, n))
@@ -267,11 +269,18 @@ class GradientAllReducer:
             edges = [hi - ((hi - lo) * i) // k for i in range(k + 1)]
             return [(edges[i + 1], edges[i]) for i in range(k)]
 
-        if boundary is None or boundary <= 0 or boundary >= n or num_buckets < 2:
+        bounds = [] if boundary is None else ([boundary] if isinstance(boundary, int) else list(boundary))
+        bounds = sorted(b for b in set(bounds) if 0 < b < n)
+        if not bounds or num_buckets < 2:
             self.buckets = cut(0, n, num_buckets)  # last parameters first
         else:
-            k_late = min(num_buckets - 1, max(1, round(num_buckets * (n - boundary) / n)))
-            self.buckets = cut(boundary, n, k_late) + cut(0, boundary, num_buckets - k_late)
+            bounds = bounds[-(num_buckets - 1):]        # at most one segment per bucket
+            segs = list(zip([0] + bounds, bounds + [n]))  # ascending; processed last -> first
+            k = [1] * len(segs)
+            for _ in range(num_buckets - len(segs)):      # hand the spare buckets to the segments with the largest share each
+                i = max(range(len(segs)), key=lambda j: (segs[j][1] - segs[j][0]) / k[j])
+                k[i] += 1
+            self.buckets = [b for (lo, hi), kk in reversed(list(zip(segs, k))) for b in cut(lo, hi, kk)]
         self._work = []
         # measurement (bench.py): with ``timing`` on, ``wait`` brackets every bucket's join with CUDA events on the compute
         # stream; ``exposed_ms()`` then gives, per bucket, how long the compute stream sat blocked on that all-reduce

@@ -71,6 +71,10 @@ def _allreduce_worker(rank, world, port, tmp):
     red2 = GradientAllReducer(g, num_buckets=4, boundary=600)
     assert red2.buckets == [(800, 1000), (600, 800), (300, 600), (0, 300)]
     assert GradientAllReducer(g, num_buckets=4, boundary=950).buckets[0] == (950, 1000)
+    # two boundaries (shallow encoder | deep encoder | decoder): every segment its own buckets, the spare one to the largest share
+    red3 = GradientAllReducer(g, num_buckets=4, boundary=[100, 600])
+    assert red3.buckets == [(600, 1000), (350, 600), (100, 350), (0, 100)]
+    assert GradientAllReducer(g, num_buckets=2, boundary=[100, 600]).buckets == [(600, 1000), (0, 600)]
     for b in range(4):      # buckets become ready in backward order
         red.ready(b)
     scale = red.wait()
@@ -87,8 +91,9 @@ def test_world_size_2_gloo_gradient_allreduce(tmp_path, lib_built):
 
 
 def test_trainer_bucket_schedule_covers_every_bucket_once(lib_built):
-    """Host logic of VaeTrainStep's two-phase all-reduce schedule (no GPU): after the decoder's backward only buckets made
-    of decoder / post_quant_conv parameters start; after the encoder's backward the rest; every bucket exactly once."""
+    """Host logic of VaeTrainStep's three-phase all-reduce schedule (no GPU): after the decoder's backward only buckets made
+    of decoder / post_quant_conv parameters start; after the encoder's deep stages the buckets past the shallow segment; after
+    the encoder's backward the rest; every bucket exactly once."""
     from types import SimpleNamespace
 
     from ragb_vae_b200.trainer import VaeTrainStep
@@ -111,16 +116,22 @@ def test_trainer_bucket_schedule_covers_every_bucket_once(lib_built):
         def ready(self, bucket):
             started.append(bucket)
 
-    step.reducer = FakeReducer(torch.zeros(offsets[-1]), num_buckets=7)
-    step._mark_ready(decoder_done=True)
+    step.reducer = FakeReducer(torch.zeros(offsets[-1]), num_buckets=7, boundary=[300, 550])
+    step._shallow_end = 300   # "encoder.a" is the shallow segment
+    step._mark_ready(0)
     first = list(started)
     for b in first:  # only decoder-side parameters inside these buckets
         lo, hi = step.reducer.buckets[b]
         inside = [n for i, n in enumerate(names) if offsets[i + 1] > lo and offsets[i] < hi]
         assert inside and all(n.startswith(("decoder.", "post_quant_conv.")) for n in inside), (b, inside)
     assert first, "some decoder-only bucket must be ready after the decoder's backward"
-    step._mark_ready(decoder_done=False)
+    step._mark_ready(1)
+    second = [b for b in started if b not in first]
+    assert second and all(step.reducer.buckets[b][0] >= 300 for b in second)   # deep encoder side only
+    assert all(b in started for b, (lo, hi) in enumerate(step.reducer.buckets) if lo >= 300)
+    step._mark_ready(2)
     assert sorted(started) == list(range(len(step.reducer.buckets)))
+    assert [b for b in started if b not in first and b not in second] == [b for b, (lo, hi) in enumerate(step.reducer.buckets) if hi <= 300]
     # a bucket that mixes encoder-side and decoder-side parameters waits for the second phase
     mixed = [b for b, (lo, hi) in enumerate(step.reducer.buckets)
              if any(offsets[i + 1] > lo and offsets[i] < hi and not n.startswith(("decoder.", "post_quant_conv."))
