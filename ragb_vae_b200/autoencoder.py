@@ -587,7 +587,10 @@ class RgbaAutoencoder(nn.Module):
             if hpack:
                 wp = self._hpack_weights(conv)
             else:
-                wp = self._conv_weights(conv, True, upsample, cin_pad=cx)
+                # stride-2 convs whose channel count is not a multiple of 64 (Qwen's 96 -> 96 down-sampler): every tap's K range
+                # padded to 128 with zero weights, so that the kernel can use 128-byte operand rows on the parity view
+                pad_k = (cx + 63) // 64 * 64 if (stride == 2 and k == 3 and cx > 64 and cx % 64) else cx
+                wp = self._conv_weights(conv, True, upsample, cin_pad=pad_k)
             if fuse:
                 norm, silu = next_norm
                 act = torch.empty((n, oh, ow, cout), dtype=y_dt, device=x.device)

@@ -49,6 +49,7 @@ struct TcParams {
   int cin_pitch;            // pixel pitch of x in elements (parity view: offset of the odd column)
   int cin;
   int w_k_base;             // column offset into the weight matrix (upsample phase)
+  int tap_k;                // weight columns per tap (cin, or cin padded to 64 for the stride-2 form)
   signed char tap_dx[TC_MAX_TAPS], tap_dy[TC_MAX_TAPS], tap_wp[TC_MAX_TAPS], tap_hp[TC_MAX_TAPS];
   // output mapping: out pixel = tile pixel * os + oo
   int osy, osx, ooy, oox;
@@ -140,7 +141,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const TileCoord t = decode_tile(p, tile);
       for (int tap = 0; tap < p.ntaps; ++tap) {
         const int ax = t.x0 + p.tap_dx[tap], ay = t.y0 + p.tap_dy[tap];
-        const int kcol = p.w_k_base + tap * p.cin;
+        const int kcol = p.w_k_base + tap * p.tap_k;
         const int c5 = p.tap_wp[tap] * p.cin_pitch, hp = p.tap_hp[tap];
         for (int kc = 0; kc < p.kc_per_tap; ++kc) {
           mbar_wait(bar_empty0 + 8u * stage, phase ^ 1u);
@@ -345,7 +346,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const TileCoord t = decode_tile(p, (2 * mp + (int)rank) * p.n_tiles + nt);
       for (int tap = 0; tap < p.ntaps; ++tap) {
         const int ax = t.x0 + p.tap_dx[tap], ay = t.y0 + p.tap_dy[tap];
-        const int kcol = p.w_k_base + tap * p.cin;
+        const int kcol = p.w_k_base + tap * p.tap_k;
         const int c5 = p.tap_wp[tap] * p.cin_pitch, hp = p.tap_hp[tap];
         for (int kc = 0; kc < p.kc_per_tap; ++kc) {
           mbar_wait(bar_empty0 + 8u * stage, phase ^ 1u);
@@ -622,8 +623,16 @@ static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_
   // byte rate, bounds small-N layers), so channel counts above 64 always use BK=64: the last block of a tap
   // is partly out of bounds in x (zero-filled), which cancels whatever weight columns it is paired with.
   // (not for the stride-2 parity view, whose folded channel axis has real data past cin)
-  p.bk = (d->cin % 64 == 0 || (d->cin > 64 && d->stride == 1)) ? 64 : (d->cin % 32 == 0 ? 32 : 16);
+  // The stride-2 parity view has real data past cin on its folded channel axis (the odd column's pixel), so a 64-wide block
+  // that overhangs cin needs ZERO WEIGHTS under the overhang instead: the caller packs such a conv (Qwen's 96 -> 96
+  // down-sampler) with every tap's K range padded to a multiple of 64 (w_ld = 9 * 128), recognised here by the row pitch.
+  int tap_k = d->cin;
+  if (phase < 0 && d->stride == 2 && d->ksize == 3 && !d->taps_1d && w_ld % 9 == 0 && (w_ld / 9) % 64 == 0 && w_ld / 9 >= d->cin &&
+      w_ld / 9 < d->cin + 64)
+    tap_k = (int)(w_ld / 9);
+  p.bk = (d->cin % 64 == 0 || (d->cin > 64 && (d->stride == 1 || tap_k % 64 == 0))) ? 64 : (d->cin % 32 == 0 ? 32 : 16);
   p.kc_per_tap = (d->cin + p.bk - 1) / p.bk;
+  p.tap_k = tap_k;
   const CUtensorMapSwizzle sw =
       p.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   p.layout_type = p.bk == 64 ? 2u : (p.bk == 32 ? 4u : 6u);
@@ -664,7 +673,7 @@ static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_
         p.tap_dx[t] = (signed char)(dx - d->pad_lo);
       }
     }
-    k_extent = p.ntaps * d->cin;
+    k_extent = p.ntaps * tap_k;
   }
   p.mode = d->stride == 2 ? 1 : 0;
   choose_tile(p.th, p.tw, &p.bw, &p.bh);
