@@ -562,7 +562,7 @@ def c4_arm(cx: Ctx, a, steps=None):
             "config": {"workload": f"c4: rgba_vae training step, batch {B} x {S}x{S} per GPU, recon (reduce_mean) + 1e-6 KL, "
                                    "no LPIPS, bucketed NCCL gradient all-reduce, clip 1.0, AdamW",
                        "arch": a.arch, "parallelism": f"data parallel x{world}",
-                       "launch": "eager launches" if a.no_graph else "three CUDA graphs per step, all-reduces issued between the replays",
+                       "launch": "eager launches" if a.no_graph else "four CUDA graphs per step (forward + decoder backward | deep encoder backward | shallow encoder backward | clip + AdamW), all-reduces issued between the replays",
                        "l2": "multi-GB activation tape per step (inputs and working set exceed the 126 MB L2)"},
             "e2e": {"value": mpix * steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
                     "h2d_bytes_per_step": (x_host.numel() + n_host.numel()) * 4 * world, "d2h_bytes_per_step": 4 * world},
