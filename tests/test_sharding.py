@@ -137,3 +137,29 @@ def test_trainer_bucket_schedule_covers_every_bucket_once(lib_built):
              if any(offsets[i + 1] > lo and offsets[i] < hi and not n.startswith(("decoder.", "post_quant_conv."))
                     for i, n in enumerate(names))]
     assert all(b not in first for b in mixed)
+
+
+@pytest.mark.parametrize("arch", ["qwen", "flux"])
+def test_trainer_encoder_split_is_a_contiguous_shallow_prefix(lib_built, arch):
+    """Host logic behind the three-phase all-reduce (no GPU): the shallow phase of the encoder's backward is the stem plus the
+    first blocks, their parameters are exactly the head [0, shallow_end) of the flat buffer and at most 10 % of the encoder side."""
+    import ragb_vae_b200 as R
+    from ragb_vae_b200.trainer import VaeTrainStep
+
+    vae = R.RgbaAutoencoder(arch)
+    step = object.__new__(VaeTrainStep)
+    step.vae, step.flux = vae, arch == "flux"
+    named = [(n, p) for n, p in vae.named_parameters() if ".time_conv." not in n]
+    named = [np for np in named if not step._decoder_side(np[0])] + [np for np in named if step._decoder_side(np[0])]
+    boundary = sum(p.numel() for n, p in named if not step._decoder_side(n))
+    split, shallow_end = step._encoder_split(named, boundary)
+    assert split >= 1 and shallow_end is not None and 0 < shallow_end <= 0.10 * boundary
+    mods = [vae.encoder.conv_in] + [m for _, m in step._encoder_items()][:split]
+    ids = {id(p) for m in mods for p in m.parameters()}
+    off = 0
+    for _, p in named:                      # the shallow modules' parameters are the first ones, nothing else in between
+        if off < shallow_end:
+            assert id(p) in ids
+        else:
+            assert id(p) not in ids
+        off += p.numel()
