@@ -599,7 +599,7 @@ class RgbaAutoencoder(nn.Module):
                 ops.conv2d_tc_norm(desc, x, wp, wp.shape[1], bias, residual, y, act, gamma, silu)
                 return _Stream(y, act, (id(norm), silu))
             if (self.fuse_gn_stats and next_norm is not None and isinstance(next_norm[0], GroupNorm) and not y_nchw
-                    and y_dt == torch.bfloat16 and not upsample and not hpack):
+                    and y_dt == torch.bfloat16 and not hpack):
                 # the consumer is a GroupNorm: its statistics come out of this conv's epilogue where the layer has that form
                 groups = int(next_norm[0].num_groups)
                 stats = ops.conv2d_tc_gnstats(desc, x, wp, wp.shape[1], bias, residual, y, groups)

@@ -762,7 +762,8 @@ static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_
 // Sums the per-tile partials conv_tc2_kernel<4, 3> left (epilogue_pixel_gnstats) into the [n][groups][2] fp64 (sum, sum of
 // squares) rv_groupnorm_silu reads.  Block = (group, sample); fixed summation order.
 __global__ void __launch_bounds__(128) gn_finish_kernel(const float* __restrict__ part, double* __restrict__ stats, int tpi,
-                                                       int n_tiles, int bn, int gs, int lane_step, int groups) {
+                                                       int n_tiles, int bn, int gs, int lane_step, int groups, int nseg,
+                                                       int64_t seg_stride) {
   __shared__ double red[2][4];
   const int G = blockIdx.x, n = blockIdx.y;
   const int ch0 = G * gs;
@@ -771,12 +772,13 @@ __global__ void __launch_bounds__(128) gn_finish_kernel(const float* __restrict_
   const int g_local = (col - half * (bn / 2)) / gs;
   const int lane_s = 2 * g_local * lane_step, lane_q = (2 * g_local + 1) * lane_step;
   double sa = 0.0, sq = 0.0;
-  for (int i = threadIdx.x; i < tpi * 4; i += 128) {
-    const int mt = n * tpi + (i >> 2), q = i & 3;
-    const float* w = part + (((int64_t)mt * n_tiles + nt) * 8 + half * 4 + q) * 32;
-    sa += (double)w[lane_s];
-    sq += (double)w[lane_q];
-  }
+  for (int seg = 0; seg < nseg; ++seg)  // the four phase launches of an up-sampling conv leave a segment each
+    for (int i = threadIdx.x; i < tpi * 4; i += 128) {
+      const int mt = n * tpi + (i >> 2), q = i & 3;
+      const float* w = part + seg * seg_stride + (((int64_t)mt * n_tiles + nt) * 8 + half * 4 + q) * 32;
+      sa += (double)w[lane_s];
+      sq += (double)w[lane_q];
+    }
   for (int o = 16; o >= 1; o >>= 1) {
     sa += __shfl_xor_sync(0xffffffffu, sa, o);
     sq += __shfl_xor_sync(0xffffffffu, sq, o);
@@ -793,14 +795,17 @@ __global__ void __launch_bounds__(128) gn_finish_kernel(const float* __restrict_
 }
 
 // tiling of a layer as launch_tc would choose it, and whether the statistics epilogue covers it; 0 or the scratch bytes
-static int64_t gnstats_geometry(const rv_conv_desc* d, int groups, int* tpi, int* n_tiles, int* bn, int* gs, int* lane_step) {
-  if (groups != 32 || d->upsample || d->y_nchw || d->y_dtype != RV_BF16 || d->x_dtype != RV_BF16 || d->cout % groups) return 0;
+static int64_t gnstats_geometry(const rv_conv_desc* d, int groups, int* tpi, int* n_tiles, int* bn, int* gs, int* lane_step,
+                                int64_t* seg_floats) {
+  if (groups != 32 || d->y_nchw || d->y_dtype != RV_BF16 || d->x_dtype != RV_BF16 || d->cout % groups) return 0;
+  if (d->upsample && (d->ksize != 3 || d->stride != 1 || d->cin % 64)) return 0;
   if (d->taps_1d || d->bias_mode != 1 || d->alpha != 1.0f || d->out_scale != 1.0f || d->out_shift != 0.0f || d->clamp) return 0;
   const int bk = (d->cin % 64 == 0 || (d->cin > 64 && d->stride == 1)) ? 64 : 0;
   if (bk != 64 || d->cout % 16 || d->y_cstride != d->cout) return 0;
   int bw, bh, b, t;
-  choose_tile(d->oh, d->ow, &bw, &bh);
-  const int tx = (d->ow + bw - 1) / bw, ty = (d->oh + bh - 1) / bh;
+  const int gh = d->upsample ? d->h : d->oh, gw = d->upsample ? d->w : d->ow;  // the tiled grid (source grid for the phase convs)
+  choose_tile(gh, gw, &bw, &bh);
+  const int tx = (gw + bw - 1) / bw, ty = (gh + bh - 1) / bh;
   choose_bn(d->cout, &b, &t);
   if (b * t != d->cout || b % 64 || d->n * tx * ty < 2) return 0;
   const int g = d->cout / groups;
@@ -821,7 +826,8 @@ static int64_t gnstats_geometry(const rv_conv_desc* d, int groups, int* tpi, int
   *gs = g;
   *lane_step = 32 / (2 * nst * (32 / g));
   const int64_t m_tiles = (int64_t)d->n * tx * ty;
-  return ((m_tiles + 1) / 2 * 2) * t * 8 * 32 * (int64_t)sizeof(float);
+  *seg_floats = ((m_tiles + 1) / 2 * 2) * t * 8 * 32;
+  return *seg_floats * (d->upsample ? 4 : 1) * (int64_t)sizeof(float);
 }
 
 // fp32 [cout][cin][k][k] -> bf16 [cout][taps][cin]  (upsample: [cout][4 phases][4 taps][cin], folded)
@@ -914,7 +920,8 @@ int rv_conv2d_tc_norm(const rv_conv_desc* d, const void* x, const void* w_packed
 int64_t rv_conv2d_tc_gnstats_scratch_bytes(const rv_conv_desc* d, int groups) {
   if (!d || rv::check_conv_desc(d)) return 0;
   int tpi, n_tiles, bn, gs, lane_step;
-  return rv::gnstats_geometry(d, groups, &tpi, &n_tiles, &bn, &gs, &lane_step);
+  int64_t seg;
+  return rv::gnstats_geometry(d, groups, &tpi, &n_tiles, &bn, &gs, &lane_step, &seg);
 }
 
 int rv_conv2d_tc_gnstats(const rv_conv_desc* d, const void* x, const void* w_packed, int64_t w_ld, const float* bias,
@@ -923,7 +930,8 @@ int rv_conv2d_tc_gnstats(const rv_conv_desc* d, const void* x, const void* w_pac
   if (int rc = rv::check_conv_desc(d)) return rc;
   if (int rc = rv::tc_ensure_init()) return rc;
   int tpi, n_tiles, bn, gs, lane_step;
-  const int64_t need = rv::gnstats_geometry(d, groups, &tpi, &n_tiles, &bn, &gs, &lane_step);
+  int64_t seg = 0;
+  const int64_t need = rv::gnstats_geometry(d, groups, &tpi, &n_tiles, &bn, &gs, &lane_step, &seg);
   RV_CHECK_ARG(need > 0, "conv2d_tc_gnstats: this layer has no statistics epilogue (rv_conv2d_tc_gnstats_scratch_bytes returned 0)");
   RV_CHECK_ARG(x && w_packed && y && bias && stats && scratch && scratch_bytes >= need && (uintptr_t)scratch % 128 == 0,
                "conv2d_tc_gnstats: null tensor or scratch smaller than %lld bytes", (long long)need);
@@ -931,10 +939,16 @@ int rv_conv2d_tc_gnstats(const rv_conv_desc* d, const void* x, const void* w_pac
                    (uintptr_t)bias % 16 == 0 && d->in_scale == 1.0f && d->in_shift == 0.0f,
                "conv2d_tc_gnstats: operand alignment / layout as for rv_conv2d_tc");
   cudaStream_t st = (cudaStream_t)stream;
-  if (int rc = rv::launch_tc(d, x, w_packed, w_ld, bias, residual, y, st, -1, nullptr, nullptr, (float*)scratch, gs)) return rc;
+  if (d->upsample) {  // nearest x2 + 3x3 as four phase convs on the source grid: a segment of partials per phase
+    for (int phase = 0; phase < 4; ++phase)
+      if (int rc = rv::launch_tc(d, x, w_packed, w_ld, bias, residual, y, st, phase, nullptr, nullptr, (float*)scratch + phase * seg, gs))
+        return rc;
+  } else if (int rc = rv::launch_tc(d, x, w_packed, w_ld, bias, residual, y, st, -1, nullptr, nullptr, (float*)scratch, gs)) {
+    return rc;
+  }
   rv::LaunchScope scope(rv::CAT_NORM, st, (double)need);
   rv::gn_finish_kernel<<<dim3((unsigned)groups, (unsigned)d->n), 128, 0, st>>>((const float*)scratch, stats, tpi, n_tiles, bn, gs, lane_step,
-                                                                            groups);
+                                                                            groups, d->upsample ? 4 : 1, seg);
   RV_LAUNCH_CHECK();
   return 0;
 }

@@ -287,6 +287,16 @@ def test_conv_out_kernel_matches_conv2d(ops, cin, cout, shape, f32):
 @pytest.mark.parametrize("n,h,w,cin,cout,res", [(2, 64, 64, 256, 256, True), (1, 32, 96, 512, 512, False), (3, 48, 40, 128, 256, False),
                                                (2, 32, 32, 128, 512, True), (1, 40, 24, 512, 256, False)])
 def test_conv_gnstats_epilogue(ops, n, h, w, cin, cout, res):
+    _gnstats_case(ops, n, h, w, cin, cout, res, False)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 24, 40, 256, 256), (1, 16, 16, 512, 512)])
+def test_conv_gnstats_epilogue_upsample(ops, n, h, w, cin, cout):
+    """The nearest-x2 + 3x3 conv (four phase launches): one segment of partials per phase."""
+    _gnstats_case(ops, n, h, w, cin, cout, False, True)
+
+
+def _gnstats_case(ops, n, h, w, cin, cout, res, up):
     """rv_conv2d_tc_gnstats: same output bits as rv_conv2d_tc, and statistics equal to rv_groupnorm_stats of that output
     (the fused ones are taken before the bf16 rounding: relative 2e-3 on the sums of squares); ragged tiles, odd tile counts,
     one and two N tiles, with and without residual; batch independence of a sample's statistics."""
@@ -296,28 +306,29 @@ def test_conv_gnstats_epilogue(ops, n, h, w, cin, cout, res):
     x = torch.randn(n, h, w, cin, generator=g).bfloat16().cuda()
     wt = (torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).cuda()
     bias = torch.randn(cout, generator=g).cuda()
-    r = torch.randn(n, h, w, cout, generator=g).bfloat16().cuda() if res else None
-    wp = ops.pack_conv_weights_tc(wt)
-    desc = ops.make_desc(n, h, w, cin, cout, 3, 1, False, x_dtype=_lib.RV_BF16, y_dtype=_lib.RV_BF16)
-    y0 = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device="cuda")
+    s_ = 2 if up else 1
+    r = torch.randn(n, h * s_, w * s_, cout, generator=g).bfloat16().cuda() if res else None
+    wp = ops.pack_conv_weights_tc(wt, up)
+    desc = ops.make_desc(n, h, w, cin, cout, 3, 1, up, x_dtype=_lib.RV_BF16, y_dtype=_lib.RV_BF16)
+    y0 = torch.empty(n, h * s_, w * s_, cout, dtype=torch.bfloat16, device="cuda")
     ops.conv2d_tc(desc, x, wp, wp.shape[1], bias, r, y0)
     y1 = torch.empty_like(y0)
     stats = ops.conv2d_tc_gnstats(desc, x, wp, wp.shape[1], bias, r, y1, 32)
     assert stats is not None and tuple(stats.shape) == (n, 32, 2)
-    d128 = ops.make_desc(n, h, w, cin, 128, 3, 1, False, x_dtype=_lib.RV_BF16, y_dtype=_lib.RV_BF16)
+    d128 = ops.make_desc(n, h, w, cin, 128, 3, 1, up, x_dtype=_lib.RV_BF16, y_dtype=_lib.RV_BF16)
     assert ops.conv2d_tc_gnstats(d128, x, wp[:128], wp.shape[1], bias[:128].contiguous(), None, y1[..., :128].contiguous(), 32) is None
     assert torch.equal(y0, y1)
     ref = torch.empty((n, 32, 2), dtype=torch.float64, device="cuda")
-    _lib.check(_lib.load().rv_groupnorm_stats(ops._ptr(y0), ops._ptr(ref), n, h * w, cout, 32, _lib.RV_BF16, ops._stream(y0)), "stats")
-    cnt = h * w * (cout // 32)
+    _lib.check(_lib.load().rv_groupnorm_stats(ops._ptr(y0), ops._ptr(ref), n, h * w * s_ * s_, cout, 32, _lib.RV_BF16, ops._stream(y0)), "stats")
+    cnt = h * w * s_ * s_ * (cout // 32)
     mean_f, mean_r = stats[..., 0] / cnt, ref[..., 0] / cnt
     var_f, var_r = stats[..., 1] / cnt - mean_f ** 2, ref[..., 1] / cnt - mean_r ** 2
     assert float((mean_f - mean_r).abs().max()) < 2e-3 * float(var_r.sqrt().max())
     assert float(((var_f - var_r).abs() / var_r).max()) < 4e-3
     # a sample's statistics do not depend on the batch it is in
     if n > 1:
-        d1 = ops.make_desc(1, h, w, cin, cout, 3, 1, False, x_dtype=_lib.RV_BF16, y_dtype=_lib.RV_BF16)
-        ya = torch.empty(1, h, w, cout, dtype=torch.bfloat16, device="cuda")
+        d1 = ops.make_desc(1, h, w, cin, cout, 3, 1, up, x_dtype=_lib.RV_BF16, y_dtype=_lib.RV_BF16)
+        ya = torch.empty(1, h * s_, w * s_, cout, dtype=torch.bfloat16, device="cuda")
         sa = ops.conv2d_tc_gnstats(d1, x[-1:].contiguous(), wp, wp.shape[1], bias, None if r is None else r[-1:].contiguous(), ya, 32)
         if sa is not None:
             assert torch.equal(sa[0], stats[-1])
