@@ -761,24 +761,39 @@ static int launch_tc(const rv_conv_desc* d, const void* x, const void* w, int64_
 
 // Sums the per-tile partials conv_tc2_kernel<4, 3> left (epilogue_pixel_gnstats) into the [n][groups][2] fp64 (sum, sum of
 // squares) rv_groupnorm_silu reads.  Block = (group, sample); fixed summation order.
-__global__ void __launch_bounds__(128) gn_finish_kernel(const float* __restrict__ part, double* __restrict__ stats, int tpi,
+__global__ void __launch_bounds__(512) gn_finish_kernel(const float* __restrict__ part, double* __restrict__ stats, int tpi,
                                                        int n_tiles, int bn, int gs, int lane_step, int groups, int nseg,
                                                        int64_t seg_stride) {
-  __shared__ double red[2][4];
+  __shared__ double red[2][16];
   const int G = blockIdx.x, n = blockIdx.y;
   const int ch0 = G * gs;
   const int nt = ch0 / bn, col = ch0 - nt * bn;
   const int half = col / (bn / 2);
   const int g_local = (col - half * (bn / 2)) / gs;
   const int lane_s = 2 * g_local * lane_step, lane_q = (2 * g_local + 1) * lane_step;
+  // 512 threads x 4 independent loads in flight each: the (tile, lane quarter) partials of one (sample, group) are 128-byte
+  // strided 8-byte pairs -- a latency-bound gather (128 threads walking it one load at a time took 26 us per conv)
   double sa = 0.0, sq = 0.0;
-  for (int seg = 0; seg < nseg; ++seg)  // the four phase launches of an up-sampling conv leave a segment each
-    for (int i = threadIdx.x; i < tpi * 4; i += 128) {
-      const int mt = n * tpi + (i >> 2), q = i & 3;
-      const float* w = part + seg * seg_stride + (((int64_t)mt * n_tiles + nt) * 8 + half * 4 + q) * 32;
-      sa += (double)w[lane_s];
-      sq += (double)w[lane_q];
+  const int items = tpi * 4;
+  for (int seg = 0; seg < nseg; ++seg) {  // the four phase launches of an up-sampling conv leave a segment each
+    const float* base = part + seg * seg_stride + ((int64_t)n * tpi * n_tiles + nt) * 8 * 32 + half * 4 * 32;
+    for (int i0 = threadIdx.x; i0 < items; i0 += 512 * 4) {
+      float a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 512;
+        const bool ok = i < items;
+        const float* w = base + ((int64_t)(i >> 2) * n_tiles * 8 + (i & 3)) * 32;
+        a[u] = ok ? w[lane_s] : 0.f;
+        b[u] = ok ? w[lane_q] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        sa += (double)a[u];
+        sq += (double)b[u];
+      }
     }
+  }
   for (int o = 16; o >= 1; o >>= 1) {
     sa += __shfl_xor_sync(0xffffffffu, sa, o);
     sq += __shfl_xor_sync(0xffffffffu, sq, o);
@@ -789,8 +804,13 @@ __global__ void __launch_bounds__(128) gn_finish_kernel(const float* __restrict_
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    stats[((int64_t)n * groups + G) * 2] = red[0][0] + red[0][1] + red[0][2] + red[0][3];
-    stats[((int64_t)n * groups + G) * 2 + 1] = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+    double ta = 0.0, tq = 0.0;
+    for (int k = 0; k < 16; ++k) {
+      ta += red[0][k];
+      tq += red[1][k];
+    }
+    stats[((int64_t)n * groups + G) * 2] = ta;
+    stats[((int64_t)n * groups + G) * 2 + 1] = tq;
   }
 }
 
@@ -947,7 +967,7 @@ int rv_conv2d_tc_gnstats(const rv_conv_desc* d, const void* x, const void* w_pac
     return rc;
   }
   rv::LaunchScope scope(rv::CAT_NORM, st, (double)need);
-  rv::gn_finish_kernel<<<dim3((unsigned)groups, (unsigned)d->n), 128, 0, st>>>((const float*)scratch, stats, tpi, n_tiles, bn, gs, lane_step,
+  rv::gn_finish_kernel<<<dim3((unsigned)groups, (unsigned)d->n), 512, 0, st>>>((const float*)scratch, stats, tpi, n_tiles, bn, gs, lane_step,
                                                                             groups, d->upsample ? 4 : 1, seg);
   RV_LAUNCH_CHECK();
   return 0;
