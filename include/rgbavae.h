@@ -26,7 +26,7 @@ extern "C" {
 #define RV_F32 0
 #define RV_BF16 1
 
-#define RV_ABI_VERSION 24
+#define RV_ABI_VERSION 25
 #define RV_PROF_CATEGORIES 10
 
 int rv_abi_version(void);
@@ -163,10 +163,14 @@ int rv_attention_lse(const void* q, const void* k, int64_t ld_qk, const void* vt
  * does).  With it the d = 512 kernel keeps pass 1's probability tiles there and its second output pass streams them back
  * instead of recomputing S and the softmax (64 instead of 96 MMAs per key block).  The first 1024 bytes (slot ownership
  * flags) must be zero before the first call and are zero again whenever no call is in flight; the rest needs no
- * initialisation.  One workspace serves one stream at a time.  workspace == NULL: same as rv_attention_lse. */
+ * initialisation.  One workspace serves one stream at a time.  workspace == NULL: same as rv_attention_lse.
+ * V^T is addressed through two pitches in elements: ld_vt between consecutive d-rows and vt_img_pitch between images --
+ * (tokens, d * tokens) for the dense [n_img][d][tokens] of rv_attention, (n_img * tokens, tokens) for a [d][n_img * tokens]
+ * matrix that ONE projection GEMM over all images writes. */
 int64_t rv_attention_workspace_bytes(int tokens, int d);
-int rv_attention_ws(const void* q, const void* k, int64_t ld_qk, const void* vt, void* out, int64_t ld_out, float* lse,
-                    void* workspace, int64_t workspace_bytes, int n_img, int tokens, int d, void* stream);
+int rv_attention_ws(const void* q, const void* k, int64_t ld_qk, const void* vt, int64_t ld_vt, int64_t vt_img_pitch, void* out,
+                    int64_t ld_out, float* lse, void* workspace, int64_t workspace_bytes, int n_img, int tokens, int d,
+                    void* stream);
 
 /* ---- layout plumbing at the NCHW boundary ----------------------------------------------- */
 /* y[n][hw][c_pad] = x[n][c][hw]*scale+shift (extra channels zero). */

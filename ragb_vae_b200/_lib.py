@@ -9,7 +9,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "librgbavae.so")
 
 RV_F32, RV_BF16 = 0, 1
-ABI_VERSION = 24
+ABI_VERSION = 25
 PROF_CATEGORIES = 10
 PROF_NAMES = ("conv_tc", "conv_direct", "norm_silu", "softmax", "layout", "reparam", "recon_loss", "composite_psnr",
               "attention", "conv_tc_upsample")
@@ -65,7 +65,7 @@ SIGNATURES = {
     "rv_attention": (_I, [_P, _P, _L, _P, _P, _L, _I, _I, _I, _P]),
     "rv_attention_lse": (_I, [_P, _P, _L, _P, _P, _L, _P, _I, _I, _I, _P]),
     "rv_attention_workspace_bytes": (_L, [_I, _I]),
-    "rv_attention_ws": (_I, [_P, _P, _L, _P, _P, _L, _P, _P, _L, _I, _I, _I, _P]),
+    "rv_attention_ws": (_I, [_P, _P, _L, _P, _L, _L, _P, _L, _P, _P, _L, _I, _I, _I, _P]),
     "rv_gemm_rowstat": (_I, [C.POINTER(ConvDesc), _P, _P, _L, _P, _I, _P, _P, _P]),
     "rv_rowdot": (_I, [_P, _P, _L, _I, _L, _L, _F, _P, _P]),
     "rv_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _L, _I, _I, _I, _F, _F, _P]),

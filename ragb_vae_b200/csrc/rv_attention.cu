@@ -629,7 +629,7 @@ extern "C" int rv_attention(const void* q, const void* k, int64_t ld_qk, const v
 
 extern "C" int rv_attention_lse(const void* q, const void* k, int64_t ld_qk, const void* vt, void* out, int64_t ld_out, float* lse,
                                 int n_img, int tokens, int d, void* stream) {
-  return rv_attention_ws(q, k, ld_qk, vt, out, ld_out, lse, nullptr, 0, n_img, tokens, d, stream);
+  return rv_attention_ws(q, k, ld_qk, vt, tokens, (int64_t)d * tokens, out, ld_out, lse, nullptr, 0, n_img, tokens, d, stream);
 }
 
 extern "C" int64_t rv_attention_workspace_bytes(int tokens, int d) {
@@ -637,14 +637,17 @@ extern "C" int64_t rv_attention_workspace_bytes(int tokens, int d) {
   return 1024 + (int64_t)rv::FA_WS_SLOTS * (tokens / 128) * (int64_t)rv::FA_WS_BLOCK;
 }
 
-extern "C" int rv_attention_ws(const void* q, const void* k, int64_t ld_qk, const void* vt, void* out, int64_t ld_out, float* lse,
-                               void* workspace, int64_t workspace_bytes, int n_img, int tokens, int d, void* stream) {
+extern "C" int rv_attention_ws(const void* q, const void* k, int64_t ld_qk, const void* vt, int64_t ld_vt, int64_t vt_img_pitch,
+                               void* out, int64_t ld_out, float* lse, void* workspace, int64_t workspace_bytes, int n_img,
+                               int tokens, int d, void* stream) {
   using namespace rv;
   if (int rc = tc_ensure_init()) return rc;
   RV_CHECK_ARG(q && k && vt && out && n_img > 0 && tokens > 0, "attention: bad argument");
   RV_CHECK_ARG(d == 384 || d == 512, "attention: the fused kernel is built for d = 384 or 512 (got %d)", d);
   RV_CHECK_ARG(tokens % 128 == 0, "attention: tokens (%d) must be a multiple of 128", tokens);
   RV_CHECK_ARG(ld_qk % 8 == 0 && ld_out % 8 == 0 && ld_qk >= d && ld_out >= d, "attention: pitches must be multiples of 8 and >= d");
+  RV_CHECK_ARG(ld_vt % 8 == 0 && vt_img_pitch % 8 == 0 && ld_vt >= tokens && vt_img_pitch >= tokens,
+               "attention: V^T pitches (row %lld, image %lld) must be multiples of 8 and >= tokens", (long long)ld_vt, (long long)vt_img_pitch);
   RV_CHECK_ARG(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)vt % 16 == 0) && ((uintptr_t)out % 16 == 0),
                "attention: tensors must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
@@ -668,7 +671,7 @@ extern "C" int rv_attention_ws(const void* q, const void* k, int64_t ld_qk, cons
   }
   {
     cuuint64_t dims[3] = {(cuuint64_t)tokens, (cuuint64_t)d, (cuuint64_t)n_img};
-    cuuint64_t str[2] = {(cuuint64_t)tokens * 2u, (cuuint64_t)tokens * 2u * d};
+    cuuint64_t str[2] = {(cuuint64_t)ld_vt * 2u, (cuuint64_t)vt_img_pitch * 2u};
     cuuint32_t box[3] = {64, 128u / share, 1};
     if (int rc = tc_encode_map(&mv, vt, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   }

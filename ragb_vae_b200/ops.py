@@ -212,16 +212,22 @@ FUSED_ATTENTION_DIMS = (384, 512)  # + the Flux AutoencoderKL mid block (two out
 
 def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, n_img: int, tokens: int, return_lse: bool = False):
     """Fused softmax(Q K^T / sqrt(d)) V.  q, k: bf16 [n_img*tokens, d] row views (may be column slices of one
-    tensor, same row stride); vt: bf16 [n_img, d, tokens].  Returns bf16 [n_img*tokens, d]; with ``return_lse`` also the
+    tensor, same row stride); vt: bf16 [n_img, d, tokens] or [d, n_img*tokens].  Returns bf16 [n_img*tokens, d]; with ``return_lse`` also the
     per-row base-2 log-sum-exp of the scaled scores (fp32 [n_img*tokens]) the attention backward recomputes P from."""
     _need_cuda(q, k, vt)
-    d = vt.shape[1]
-    if q.stride(0) != k.stride(0) or q.stride(1) != 1 or k.stride(1) != 1 or not vt.is_contiguous():
-        raise ValueError("attention: q/k must share a row stride and be unit-stride in d; vt must be contiguous")
+    # vt: dense [n_img, d, tokens], or [d, n_img * tokens] (what one projection GEMM over all images writes)
+    if vt.dim() == 3:
+        d, ld_vt, img_pitch = vt.shape[1], tokens, vt.shape[1] * tokens
+        ok = vt.is_contiguous() and tuple(vt.shape) == (n_img, d, tokens)
+    else:
+        d, ld_vt, img_pitch = vt.shape[0], vt.stride(0), tokens
+        ok = vt.dim() == 2 and vt.stride(1) == 1 and vt.shape[1] == n_img * tokens
+    if q.stride(0) != k.stride(0) or q.stride(1) != 1 or k.stride(1) != 1 or not ok:
+        raise ValueError("attention: q/k must share a row stride and be unit-stride in d; vt must be [n, d, t] dense or [d, n*t]")
     out = torch.empty((n_img * tokens, d), dtype=torch.bfloat16, device=q.device)
     lse = torch.empty((n_img * tokens,), dtype=torch.float32, device=q.device) if return_lse else None
     ws = _attention_workspace(q.device, tokens, d)
-    check(_lib.load().rv_attention_ws(_ptr(q), _ptr(k), q.stride(0), _ptr(vt), _ptr(out), d, _ptr(lse), _ptr(ws),
+    check(_lib.load().rv_attention_ws(_ptr(q), _ptr(k), q.stride(0), _ptr(vt), ld_vt, img_pitch, _ptr(out), d, _ptr(lse), _ptr(ws),
                                       0 if ws is None else ws.numel(), n_img, tokens, d, _stream(q)), "rv_attention_ws")
     return (out, lse) if return_lse else out
 

@@ -224,10 +224,9 @@ class VaeTrainStep:
         scale = ops.attn_scale(c)
         if self.vae.fused_attention and c in ops.FUSED_ATTENTION_DIMS and t % 128 == 0:
             # flash kernel: scores / probabilities never reach HBM in the forward (the backward recomputes them per block)
-            vt_all = torch.empty((n, c, t), dtype=torch.bfloat16, device=dev)
-            for i in range(n):
-                self._gemm(wqkv[2 * c:], xn2[i * t:(i + 1) * t], rows=c, k=c, cols=t, x_ld=c, w_ld=c, y=vt_all[i], y_ld=t,
-                           bias=bqkv[2 * c:].contiguous(), bias_mode=2)
+            vt_all = torch.empty((c, n * t), dtype=torch.bfloat16, device=dev)  # V^T of all images from one GEMM
+            self._gemm(wqkv[2 * c:], xn2, rows=c, k=c, cols=n * t, x_ld=c, w_ld=c, y=vt_all, y_ld=n * t,
+                       bias=bqkv[2 * c:].contiguous(), bias_mode=2)
             o, lse = ops.attention(q, k, vt_all, n, t, return_lse=True)
         else:
             lse = None
