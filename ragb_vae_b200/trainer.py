@@ -295,17 +295,18 @@ class VaeTrainStep:
         else:
             s = torch.empty((q_chunk, t), dtype=torch.float32, device=dev)
             dp = torch.empty((q_chunk, t), dtype=torch.float32, device=dev)
-        kt = torch.empty((c, t), dtype=torch.bfloat16, device=dev)
         wqkv, bqkv, _, _ = self._attn_weights(attn)
         xn2 = xn.view(n * t, c)
+        # K^T[c][image * token] for all images from one GEMM (dQ = dS K wants the key index contiguous in its second operand)
+        kt_all = torch.empty((c, n * t), dtype=torch.bfloat16, device=dev)
+        self._gemm(wqkv[c:2 * c], xn2, rows=c, k=c, cols=n * t, x_ld=c, w_ld=c, y=kt_all, y_ld=n * t, bias=bqkv[c:2 * c].contiguous(),
+                   bias_mode=2)
         from . import _lib
         for i in range(n):
             sl = slice(i * t, (i + 1) * t)
             dv = torch.zeros((t, c), dtype=torch.float32, device=dev)
             dk = torch.zeros((t, c), dtype=torch.float32, device=dev)
-            # K^T[c][token] (dQ = dS K wants the key index contiguous in its second operand)
-            self._gemm(wqkv[c:2 * c], xn2[sl], rows=c, k=c, cols=t, x_ld=c, w_ld=c, y=kt, y_ld=t, bias=bqkv[c:2 * c].contiguous(),
-                       bias_mode=2)
+            kt = kt_all[:, i * t:(i + 1) * t]
             for r0 in range(0, t, q_chunk):
                 rows = min(q_chunk, t - r0)
                 rs = slice(i * t + r0, i * t + r0 + rows)
@@ -323,7 +324,7 @@ class VaeTrainStep:
                 T.gemm_tn_accumulate(dv, p, d_o[rs])
                 T.gemm_tn_accumulate(dk, ds[:rows], q[rs])
                 # dQ = dS K, straight into its third of dqkv
-                self._gemm(ds[:rows], kt, rows=rows, k=t, cols=c, x_ld=t, w_ld=t, y=dqkv[rs, :c], y_ld=3 * c)
+                self._gemm(ds[:rows], kt, rows=rows, k=t, cols=c, x_ld=t, w_ld=n * t, y=dqkv[rs, :c], y_ld=3 * c)
             dqkv[sl, c:2 * c] = dk
             dqkv[sl, 2 * c:] = dv
         if self.flux:  # three Linear(C, C): one stacked [3C, C] weight gradient, then a slice into each parameter's view
